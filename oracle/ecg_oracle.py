@@ -1,0 +1,419 @@
+"""CPU oracle for the ECG 1D-CNN train / infer / Grad-CAM hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``ptbxl_multimodal_b200/`` may import
+this module; only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` do, and there only
+as the checker / the timed CPU baseline -- never as the product path.
+
+What it is: a functional restatement, in plain fp32 PyTorch on the CPU, of the
+algorithm the reference composes out of ``torch.nn`` modules.  The arithmetic
+of the reference lives in PyTorch itself (third party, pinned ``torch==2.8.0``
+in /root/reference/requirements.txt:54; this image has 2.11.0), so the oracle
+calls the same ATen ops through ``torch.nn.functional`` with the PyTorch
+defaults the reference relies on, over an explicit ``state_dict``-keyed
+parameter dictionary instead of an ``nn.Module`` tree.
+
+Parity pin: ``tests/golden/make_golden.py`` ran the UNMODIFIED reference
+(imported from /root/reference in the build container) and this oracle on the
+same seeded inputs and asserted bit-equality; the outputs are committed under
+``tests/golden/`` and re-checked by ``tests/test_oracle_golden.py`` on every
+run, together with the reference's shipped known-answer artefacts (prediction
+CSV rows, ``outputs/gradcam/sample_0_MI_cam.npy``).
+
+Reference citations are ``path:line`` relative to /root/reference.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+StateDict = Dict[str, Tensor]
+
+CHANNELS = (32, 64, 128, 256)       # src/models/ecg_cnn.py:35, ecg_multimodal.py:27
+KSIZE = 15                          # src/models/ecg_cnn.py:10 (k=15, padding=k//2)
+BN_EPS = 1e-5                       # nn.BatchNorm1d default, ecg_cnn.py:14
+BN_MOMENTUM = 0.1
+
+
+# --------------------------------------------------------------------------
+# ConvBlock: Conv1d(k=15,pad=7) -> BatchNorm1d -> ReLU -> MaxPool1d(2)
+# src/models/ecg_cnn.py:5-20 (duplicate at src/models/ecg_multimodal.py:5-16)
+# --------------------------------------------------------------------------
+def conv_block(sd: StateDict, prefix: str, x: Tensor, train: bool,
+               update_running: bool = True) -> Tuple[Tensor, Tensor]:
+    """Returns (pooled output, raw conv output A).  ``prefix`` is e.g.
+    ``backbone.3.`` ; keys follow nn.Sequential numbering net.0 / net.1."""
+    w = sd[prefix + "net.0.weight"]
+    b = sd[prefix + "net.0.bias"]
+    a = F.conv1d(x, w, b, stride=1, padding=KSIZE // 2)          # ecg_cnn.py:13
+    rm = sd[prefix + "net.1.running_mean"]
+    rv = sd[prefix + "net.1.running_var"]
+    if train and not update_running:
+        rm, rv = rm.clone(), rv.clone()
+    h = F.batch_norm(a, rm, rv, sd[prefix + "net.1.weight"], sd[prefix + "net.1.bias"],
+                     training=train, momentum=BN_MOMENTUM, eps=BN_EPS)   # ecg_cnn.py:14
+    if train and update_running:
+        sd[prefix + "net.1.num_batches_tracked"] += 1
+    h = F.relu(h)                                                 # ecg_cnn.py:15
+    h = F.max_pool1d(h, kernel_size=2)                            # ecg_cnn.py:16 (floor mode)
+    return h, a
+
+
+def backbone_features(sd: StateDict, prefix: str, x: Tensor, train: bool,
+                      update_running: bool = True) -> Tuple[Tensor, Tensor]:
+    """4 ConvBlocks + AdaptiveAvgPool1d(1) + proj.  Returns (z, conv4 raw output).
+    src/models/ecg_cnn.py:61-63, src/models/ecg_multimodal.py:37-41."""
+    h = x
+    a = None
+    for i in range(len(CHANNELS)):
+        h, a = conv_block(sd, f"{prefix}backbone.{i}.", h, train, update_running)
+    g = h.mean(dim=2)                                             # gap + squeeze, ecg_cnn.py:62
+    z = F.linear(g, sd[prefix + "proj.weight"], sd[prefix + "proj.bias"])   # ecg_cnn.py:63
+    return z, a
+
+
+def ecgcnn_forward(sd: StateDict, x: Tensor, train: bool = False,
+                   update_running: bool = True, return_features: bool = False,
+                   return_conv4: bool = False):
+    """ECGCNN.forward, src/models/ecg_cnn.py:52-68."""
+    z, a = backbone_features(sd, "", x, train, update_running)
+    logits = F.linear(z, sd["head.weight"], sd["head.bias"])      # ecg_cnn.py:64
+    out = (logits, z) if return_features else logits
+    if return_conv4:
+        return out, a
+    return out
+
+
+def demo_encoder(sd: StateDict, d: Tensor) -> Tensor:
+    """DemoEncoder, src/models/ecg_multimodal.py:44-59 (ReLU after each Linear)."""
+    h = F.relu(F.linear(d, sd["demo_encoder.mlp.0.weight"], sd["demo_encoder.mlp.0.bias"]))
+    h = F.relu(F.linear(h, sd["demo_encoder.mlp.2.weight"], sd["demo_encoder.mlp.2.bias"]))
+    return h
+
+
+def multimodal_forward(sd: StateDict, x: Tensor, d: Tensor, train: bool = False,
+                       update_running: bool = True, return_conv4: bool = False):
+    """ECGMultimodal.forward (FiLM), src/models/ecg_multimodal.py:88-99."""
+    z, a = backbone_features(sd, "ecg_backbone.", x, train, update_running)
+    h = demo_encoder(sd, d)
+    film = F.linear(h, sd["film_gen.weight"], sd["film_gen.bias"])
+    gamma, beta = torch.chunk(film, 2, dim=-1)                    # :93 first half = gamma
+    gamma = 1.0 + torch.tanh(gamma)                               # :95
+    z_cond = gamma * z + beta                                     # :96
+    logits = F.linear(z_cond, sd["head.weight"], sd["head.bias"])
+    if return_conv4:
+        return logits, a
+    return logits
+
+
+def bce_with_logits(logits: Tensor, y: Tensor) -> Tensor:
+    """Mean over all B*C elements; src/training/loop.py:32, loop_demo.py:10,33."""
+    return F.binary_cross_entropy_with_logits(logits, y)
+
+
+def bce_with_logits_explicit(logits: Tensor, y: Tensor) -> Tensor:
+    """Closed form used by the CUDA kernel: for checking."""
+    x = logits
+    return (torch.clamp(x, min=0) - x * y + torch.log1p(torch.exp(-x.abs()))).mean()
+
+
+def predict(prob: Tensor, threshold: float = 0.5) -> Tensor:
+    """y_pred = (y_prob >= thr), scripts/06_ecg_baseline_test.py:127, metrics.py:37."""
+    return (prob >= threshold).to(torch.int32)
+
+
+# --------------------------------------------------------------------------
+# Parameter bookkeeping
+# --------------------------------------------------------------------------
+def is_param(key: str) -> bool:
+    return not (key.endswith("running_mean") or key.endswith("running_var")
+                or key.endswith("num_batches_tracked"))
+
+
+def param_keys(sd: StateDict) -> List[str]:
+    """Trainable tensors in state_dict order == nn.Module.parameters() order."""
+    return [k for k in sd if is_param(k)]
+
+
+def clone_sd(sd: StateDict) -> StateDict:
+    return {k: v.detach().clone() for k, v in sd.items()}
+
+
+# --------------------------------------------------------------------------
+# AdamW exactly as torch.optim.AdamW(lr, weight_decay) with defaults;
+# constructed at scripts/03_train_ecg_baseline.py:133, 04:158-162, 05:130,
+# stepped at src/training/loop.py:34.
+# --------------------------------------------------------------------------
+class AdamWState:
+    def __init__(self, sd: StateDict, lr: float, weight_decay: float,
+                 betas=(0.9, 0.999), eps: float = 1e-8):
+        self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
+        self.t = 0
+        self.m = {k: torch.zeros_like(sd[k]) for k in param_keys(sd)}
+        self.v = {k: torch.zeros_like(sd[k]) for k in param_keys(sd)}
+
+
+def adamw_step(sd: StateDict, grads: Dict[str, Tensor], st: AdamWState) -> None:
+    """Single-tensor formulation of torch/optim/adamw.py (decoupled weight decay)."""
+    st.t += 1
+    b1, b2 = st.betas
+    bc1 = 1.0 - b1 ** st.t
+    bc2 = 1.0 - b2 ** st.t
+    step_size = st.lr / bc1
+    bc2_sqrt = math.sqrt(bc2)
+    for k, g in grads.items():
+        p = sd[k]
+        p.mul_(1.0 - st.lr * st.wd)
+        st.m[k].lerp_(g, 1.0 - b1)
+        st.v[k].mul_(b2).addcmul_(g, g, value=1.0 - b2)
+        denom = (st.v[k].sqrt() / bc2_sqrt).add_(st.eps)
+        p.addcdiv_(st.m[k], denom, value=-step_size)
+
+
+# --------------------------------------------------------------------------
+# One training step: loop body of src/training/loop.py:22-36 and
+# src/training/loop_demo.py:25-41.
+# --------------------------------------------------------------------------
+def train_step(sd: StateDict, x: Tensor, y: Tensor, st: Optional[AdamWState],
+               demo: Optional[Tensor] = None, want_conv4_grad: bool = False):
+    """Forward (train-mode BN, running stats updated in ``sd``), BCE, backward,
+    AdamW.  Returns dict(loss, logits, grads[, conv4, conv4_grad])."""
+    keys = param_keys(sd)
+    leaves = {k: sd[k].detach().clone().requires_grad_(True) for k in keys}
+    work = dict(sd)
+    work.update(leaves)
+    if demo is None:
+        logits, a = ecgcnn_forward(work, x, train=True, return_conv4=True)
+    else:
+        logits, a = multimodal_forward(work, x, demo, train=True, return_conv4=True)
+    # running stats were updated in-place on sd's own tensors (same storage)
+    loss = bce_with_logits(logits, y)
+    wanted = [leaves[k] for k in keys] + ([a] if want_conv4_grad else [])
+    gs = torch.autograd.grad(loss, wanted)
+    grads = {k: g for k, g in zip(keys, gs)}
+    out = {"loss": loss.detach(), "logits": logits.detach(), "grads": grads}
+    if want_conv4_grad:
+        out["conv4"] = a.detach()
+        out["conv4_grad"] = gs[-1]
+    if st is not None:
+        adamw_step(sd, grads, st)
+    return out
+
+
+# --------------------------------------------------------------------------
+# Grad-CAM.  V1 = src/interpretability/grad_cam_1d.py:53-103;
+# V2 = scripts/00_demo_inference.py:39-61 and scripts/13_grad_cam_af.py:51-76;
+# V3 = scripts/12_grad_cam_ecg_demo.py:44-75.
+# --------------------------------------------------------------------------
+def _conv4_and_grad(sd: StateDict, x: Tensor, class_idx: int, demo: Optional[Tensor],
+                    sum_batch: bool) -> Tuple[Tensor, Tensor]:
+    """(A, dScore/dA) at the 4th Conv1d's raw output (before BN), eval mode."""
+    prefix = "" if demo is None else "ecg_backbone."
+    h = x
+    with torch.no_grad():
+        for i in range(3):
+            h, _ = conv_block(sd, f"{prefix}backbone.{i}.", h, train=False)
+        a = F.conv1d(h, sd[f"{prefix}backbone.3.net.0.weight"],
+                     sd[f"{prefix}backbone.3.net.0.bias"], padding=KSIZE // 2)
+    a = a.detach().requires_grad_(True)
+    p = f"{prefix}backbone.3."
+    r = F.batch_norm(a, sd[p + "net.1.running_mean"], sd[p + "net.1.running_var"],
+                     sd[p + "net.1.weight"], sd[p + "net.1.bias"], training=False, eps=BN_EPS)
+    r = F.max_pool1d(F.relu(r), 2)
+    z = F.linear(r.mean(dim=2), sd[prefix + "proj.weight"], sd[prefix + "proj.bias"])
+    if demo is not None:
+        hd = demo_encoder(sd, demo)
+        film = F.linear(hd, sd["film_gen.weight"], sd["film_gen.bias"])
+        gamma, beta = torch.chunk(film, 2, dim=-1)
+        z = (1.0 + torch.tanh(gamma)) * z + beta
+    logits = F.linear(z, sd["head.weight"], sd["head.bias"])
+    score = logits[:, class_idx].sum() if sum_batch else logits[0, class_idx]
+    (g,) = torch.autograd.grad(score, a)
+    return a.detach(), g
+
+
+def linear_upsample(cam: Tensor, out_len: int) -> Tensor:
+    """F.interpolate(mode='linear', align_corners=False) over the last dim;
+    grad_cam_1d.py:95-101.  cam: (N, L')."""
+    return F.interpolate(cam.unsqueeze(1), size=out_len, mode="linear",
+                         align_corners=False).squeeze(1)
+
+
+def linear_upsample_explicit(cam: Tensor, out_len: int) -> Tensor:
+    """Closed form that the CUDA kernel implements."""
+    n, lin = cam.shape
+    scale = lin / out_len
+    d = torch.arange(out_len, dtype=torch.float32)
+    src = torch.clamp((d + 0.5) * scale - 0.5, min=0.0)
+    i0 = src.floor().to(torch.int64)
+    i1 = torch.clamp(i0 + 1, max=lin - 1)
+    lam = src - i0.to(torch.float32)
+    return (1.0 - lam) * cam[:, i0] + lam * cam[:, i1]
+
+
+def gradcam_v1(sd: StateDict, x: Tensor, class_idx: int,
+               signal_length: Optional[int] = None, demo: Optional[Tensor] = None) -> Tensor:
+    """GradCAM1D.generate_cam: normalise at L' THEN upsample; batch-1 semantics
+    (score = logits[0, c]; global min/max).  grad_cam_1d.py:75-101."""
+    a, g = _conv4_and_grad(sd, x, class_idx, demo, sum_batch=False)
+    w = g.mean(dim=2, keepdim=True)                               # :85
+    cam = torch.relu((w * a).sum(dim=1))                          # :88-89  (N, L')
+    cam = cam - cam.min()                                         # :46
+    mx = cam.max()
+    if mx > 0:                                                    # :48-49
+        cam = cam / mx
+    cam = cam.squeeze(0)
+    if signal_length is not None and cam.shape[-1] != signal_length:
+        cam = linear_upsample(cam.reshape(1, -1), signal_length).squeeze(0)
+    return cam
+
+
+def gradcam_v2(sd: StateDict, x: Tensor, class_idx: int, signal_length: int,
+               demo: Optional[Tensor] = None, eps: float = 1e-9) -> Tensor:
+    """Script variants: upsample THEN (cam-min)/(max+eps); returns cam[0].
+    scripts/00_demo_inference.py:39-61 (eps 1e-9), 13_grad_cam_af.py:51-76 (eps 1e-9),
+    12_grad_cam_ecg_demo.py:44-75 (eps 1e-8, pass demo)."""
+    a, g = _conv4_and_grad(sd, x, class_idx, demo, sum_batch=True)
+    w = g.mean(dim=-1, keepdim=True)
+    cam = F.relu((w * a).sum(dim=1))
+    cam = linear_upsample(cam, signal_length)
+    cam = cam - cam.min()
+    cam = cam / (cam.max() + eps)
+    return cam[0]
+
+
+def gradcam_raw_closed_form(sd: StateDict, x: Tensor, demo: Optional[Tensor] = None) -> Tensor:
+    """All-class un-normalised CAM relu(sum_ch w_c[ch] A[ch,t]) -> (N, num_labels, L')
+    without autograd, via the closed form of SURVEY 8(a): in eval mode
+    G_c[ch,t] = v_c[ch] * s[ch] * mask[ch,t] / L_p,   s = bn_w / sqrt(rv + eps),
+    mask = (t < 2 L_p) & relu-active & first-argmax-of-its-pool-pair,
+    v_c = W_head[c] @ W_proj  (FiLM: (W_head[c] * gamma(d)) @ W_proj per sample).
+    This is what the batched CUDA Grad-CAM kernel computes."""
+    prefix = "" if demo is None else "ecg_backbone."
+    h = x
+    for i in range(3):
+        h, _ = conv_block(sd, f"{prefix}backbone.{i}.", h, train=False)
+    p = f"{prefix}backbone.3."
+    a = F.conv1d(h, sd[p + "net.0.weight"], sd[p + "net.0.bias"], padding=KSIZE // 2)
+    n, c, lp_full = a.shape
+    s = sd[p + "net.1.weight"] / torch.sqrt(sd[p + "net.1.running_var"] + BN_EPS)
+    r = torch.relu((a - sd[p + "net.1.running_mean"][None, :, None]) * s[None, :, None]
+                   + sd[p + "net.1.bias"][None, :, None])
+    lp = lp_full // 2
+    re, ro = r[:, :, 0:2 * lp:2], r[:, :, 1:2 * lp:2]
+    mask = torch.zeros_like(r)
+    mask[:, :, 0:2 * lp:2] = ((re >= ro) & (re > 0)).float()
+    mask[:, :, 1:2 * lp:2] = (ro > re).float()
+    cnt = mask.sum(dim=2)                                         # (N, C) class independent
+    wh = sd["head.weight"]                                        # (num_labels, feat)
+    wp = sd[prefix + "proj.weight"]                               # (feat, 256)
+    if demo is None:
+        v = (wh @ wp)[None].expand(n, -1, -1)                     # (N, labels, 256)
+    else:
+        film = F.linear(demo_encoder(sd, demo), sd["film_gen.weight"], sd["film_gen.bias"])
+        gamma = 1.0 + torch.tanh(torch.chunk(film, 2, dim=-1)[0])  # (N, feat)
+        v = torch.einsum("cf,nf,fk->nck", wh, gamma, wp)
+    w = v * (s * 1.0)[None, None, :] * cnt[:, None, :] / float(lp * lp_full)
+    cam = torch.relu(torch.einsum("nck,nkt->nct", w, a))
+    return cam
+
+
+def gradcam_batched(sd: StateDict, x: Tensor, signal_length: Optional[int] = None,
+                    demo: Optional[Tensor] = None, variant: str = "v1",
+                    eps: float = 1e-9) -> Tensor:
+    """Per-sample, all-class Grad-CAM (the config-5 workload): every (n, c) row
+    equals the corresponding single-sample V1 / V2 call of the reference."""
+    cam = gradcam_raw_closed_form(sd, x, demo)                    # (N, labels, L')
+    n, k, lq = cam.shape
+    flat = cam.reshape(n * k, lq)
+    if variant == "v1":
+        flat = flat - flat.min(dim=1, keepdim=True).values
+        mx = flat.max(dim=1, keepdim=True).values
+        flat = torch.where(mx > 0, flat / torch.where(mx > 0, mx, torch.ones_like(mx)), flat)
+        if signal_length is not None and signal_length != lq:
+            flat = linear_upsample(flat, signal_length)
+    else:
+        flat = linear_upsample(flat, signal_length)
+        flat = flat - flat.min(dim=1, keepdim=True).values
+        flat = flat / (flat.max(dim=1, keepdim=True).values + eps)
+    return flat.reshape(n, k, -1)
+
+
+def demo_importance(sd: StateDict, x: Tensor, demo: Tensor, class_idx: int) -> Tensor:
+    """abs(grad * input) on the demographic vector, normalised by its max;
+    scripts/12_grad_cam_ecg_demo.py:78-97."""
+    d = demo.clone().detach().requires_grad_(True)
+    logits = multimodal_forward(dict(sd), x, d, train=False)
+    score = logits[:, class_idx].sum()
+    (g,) = torch.autograd.grad(score, d)
+    imp = (g[0] * d.detach()[0]).abs()
+    if imp.max() > 0:
+        imp = imp / imp.max()
+    return imp
+
+
+# --------------------------------------------------------------------------
+# Synthetic workloads of SURVEY 8(d) (configs 2-5)
+# --------------------------------------------------------------------------
+PREVALENCE = (0.25, 0.24, 0.12, 0.23, 0.44)
+
+
+def synth_batch(batch: int, t: int, num_labels: int = 5, seed: int = 0,
+                with_demo: bool = False):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(batch, 12, t, generator=g)
+    if num_labels == 1:
+        y = (torch.rand(batch, 1, generator=g) < 0.07).float()
+    else:
+        p = torch.tensor(PREVALENCE[:num_labels])
+        y = (torch.rand(batch, num_labels, generator=g) < p).float()
+    if not with_demo:
+        return x, y
+    u = torch.rand(batch, 8, generator=g)
+    demo = torch.stack([u[:, 0], (u[:, 1] < 0.5).float(),
+                        u[:, 2] * (u[:, 3] < 0.4).float(),
+                        u[:, 4] * (u[:, 5] < 0.4).float(),
+                        (u[:, 6] < 0.02).float()], dim=1)
+    return x, demo, y
+
+
+def init_state_dict(kind: str = "cnn", num_labels: int = 5, seed: int = 42,
+                    feat_dim: int = 256, in_leads: int = 12) -> StateDict:
+    """PyTorch default init in the reference's module construction order
+    (ecg_cnn.py:40-50; ecg_multimodal.py:82-86) so that a shared seed gives the
+    same random-init weights as ``torch.manual_seed(seed); ECGCNN(...)``."""
+    import torch.nn as nn
+    torch.manual_seed(seed)
+    sd: StateDict = {}
+
+    def block(prefix, cin, cout):
+        conv = nn.Conv1d(cin, cout, KSIZE, padding=KSIZE // 2)
+        bn = nn.BatchNorm1d(cout)
+        sd[prefix + "net.0.weight"] = conv.weight.detach()
+        sd[prefix + "net.0.bias"] = conv.bias.detach()
+        for k, v in bn.state_dict().items():
+            sd[prefix + "net.1." + k] = v.detach().clone()
+
+    def linear(prefix, fin, fout):
+        lin = nn.Linear(fin, fout)
+        sd[prefix + "weight"] = lin.weight.detach()
+        sd[prefix + "bias"] = lin.bias.detach()
+
+    bp = "" if kind == "cnn" else "ecg_backbone."
+    c = in_leads
+    for i, n in enumerate(CHANNELS):
+        block(f"{bp}backbone.{i}.", c, n)
+        c = n
+    linear(bp + "proj.", CHANNELS[-1], feat_dim)
+    if kind == "cnn":
+        linear("head.", feat_dim, num_labels)
+    else:
+        linear("demo_encoder.mlp.0.", 5, 64)
+        linear("demo_encoder.mlp.2.", 64, 64)
+        linear("film_gen.", 64, 2 * feat_dim)
+        linear("head.", feat_dim, num_labels)
+    return sd

@@ -1,0 +1,128 @@
+"""CPU: pin oracle/ecg_oracle.py against (1) the reference's shipped known-answer
+artefacts and (2) vectors produced by the live reference (tests/golden/make_golden.py).
+Tolerances: (2) is bit-exact on the machine that generated it; across CPUs oneDNN
+may pick another conv kernel, so allow 2e-6 relative there.  (1) carries the
+author's GPU TF32 residual: 2e-4 abs on probabilities, 5e-4 on CAM."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ecg_oracle as O
+from conftest import load_ckpt
+
+CLOSE = dict(rtol=2e-5, atol=2e-6)
+
+
+def test_shipped_baseline_rows(demo_inputs, expected_probs):
+    x, _ = demo_inputs
+    p = torch.sigmoid(O.ecgcnn_forward(load_ckpt("ecg_baseline_best.pth"), x)).numpy()
+    exp = np.array(expected_probs["baseline_prob"])
+    assert np.abs(p - exp).max() < 1e-4
+    far = np.abs(exp - 0.5) > 1e-3
+    pred = O.predict(torch.from_numpy(p)).numpy()
+    assert np.array_equal(pred[far], np.array(expected_probs["baseline_pred"], dtype=int)[far])
+
+
+def test_shipped_multimodal_rows(demo_inputs, expected_probs):
+    x, d = demo_inputs
+    p = torch.sigmoid(O.multimodal_forward(load_ckpt("ecg_multimodal_best.pth"), x[3:], d)).numpy()
+    assert np.abs(p - np.array(expected_probs["mm_prob"])).max() < 2e-4
+
+
+def test_shipped_af_rows(demo_inputs, expected_probs):
+    x, _ = demo_inputs
+    p = torch.sigmoid(O.ecgcnn_forward(load_ckpt("af_binary_best.pth"), x)).numpy()
+    exp = np.array(expected_probs["af_prob"])
+    assert np.abs(p - exp).max() < 5e-4 and (np.abs(p - exp) / np.maximum(exp, 1e-6)).max() < 2e-3
+
+
+def test_shipped_cam(demo_inputs):
+    import os
+    from conftest import GOLDEN
+    x, _ = demo_inputs
+    shipped = np.load(os.path.join(GOLDEN, "sample_0_MI_cam.npy"))
+    cam = O.gradcam_v1(load_ckpt("ecg_baseline_best.pth"), x[0:1], 0, 5000).numpy()
+    assert cam.argmax() == shipped.argmax() == 620
+    assert np.abs(cam - shipped).max() < 6e-4
+
+
+def test_live_eval_logits(golden, demo_inputs):
+    x, d = demo_inputs
+    np.testing.assert_allclose(O.ecgcnn_forward(load_ckpt("ecg_baseline_best.pth"), x).numpy(),
+                               golden["eval/baseline_logits"], **CLOSE)
+    np.testing.assert_allclose(O.multimodal_forward(load_ckpt("ecg_multimodal_best.pth"), x[3:], d).numpy(),
+                               golden["eval/mm_logits"], **CLOSE)
+    np.testing.assert_allclose(O.ecgcnn_forward(load_ckpt("af_binary_best.pth"), x).numpy(),
+                               golden["eval/af_logits"], rtol=2e-5, atol=2e-5)
+
+
+def _check_sig(golden, prefix, name, t, rtol=1e-4):
+    vals = golden[f"{prefix}/{name}/vals"]
+    l2, s, amax, full = golden[f"{prefix}/{name}/meta"]
+    flat = t.detach().double().flatten()
+    got = (flat if full else flat[::61]).float().numpy()
+    scale = max(amax, 1e-12)
+    assert np.abs(got - vals).max() <= rtol * scale, (prefix, name, np.abs(got - vals).max(), scale)
+    assert abs(float(flat.norm()) - l2) <= rtol * max(l2, 1e-12)
+
+
+@pytest.mark.parametrize("tag,kind", [("train_cnn", "cnn"), ("train_mm", "mm"),
+                                      ("train_af", "cnn"), ("train_cnn_t250", "cnn")])
+def test_live_train_steps(golden, tag, kind):
+    B, T, nl, lr, wd, steps = golden[f"{tag}/cfg"]
+    sd = O.init_state_dict(kind, int(nl), seed=42)
+    st = O.AdamWState(sd, float(lr), float(wd))
+    x = torch.from_numpy(golden[f"{tag}/x"]); y = torch.from_numpy(golden[f"{tag}/y"])
+    demo = torch.from_numpy(golden[f"{tag}/demo"]) if kind == "mm" else None
+    for s in range(int(steps)):
+        o = O.train_step(sd, x, y, st, demo=demo)
+        np.testing.assert_allclose(o["logits"].numpy(), golden[f"{tag}/step{s}/logits"], rtol=1e-4, atol=1e-5)
+        assert abs(float(o["loss"]) - float(golden[f"{tag}/step{s}/loss"])) < 1e-5
+        if s == 0:
+            for k, g in o["grads"].items():
+                _check_sig(golden, f"{tag}/step0/grad", k, g)
+    for k, v in sd.items():
+        if not k.endswith("num_batches_tracked"):
+            _check_sig(golden, f"{tag}/final", k, v, rtol=2e-3)   # Adam's 1/sqrt(v) amplifies 1e-7 grads diffs
+        else:
+            assert int(v) == int(steps)
+
+
+def test_live_gradcam_variants(golden, demo_inputs):
+    x, d = demo_inputs
+    sb = load_ckpt("ecg_baseline_best.pth"); sa = load_ckpt("af_binary_best.pth")
+    sm = load_ckpt("ecg_multimodal_best.pth")
+    for c in range(5):
+        for key, sl in ((f"cam/v1_base_s0_c{c}_T", 5000), (f"cam/v1_base_s0_c{c}_lo", None)):
+            cam = O.gradcam_v1(sb, x[0:1], c, sl).numpy()
+            assert cam.argmax() == golden[key].argmax()
+            np.testing.assert_allclose(cam, golden[key], atol=2e-5)
+        cam = O.gradcam_v2(sb, x[4:5], c, 5000).numpy()
+        np.testing.assert_allclose(cam, golden[f"cam/v2_base_s4_c{c}"], atol=2e-5)
+    np.testing.assert_allclose(O.gradcam_v2(sa, x[7:8], 0, 5000).numpy(), golden["cam/v2_af_s7"], atol=2e-5)
+    for j in (0, 5):
+        for c in (0, 3):
+            cam = O.gradcam_v2(sm, x[3 + j:4 + j], c, 5000, demo=d[j:j + 1], eps=1e-8).numpy()
+            np.testing.assert_allclose(cam, golden[f"cam/v3_mm_j{j}_c{c}"], atol=2e-5)
+            imp = O.demo_importance(sm, x[3 + j:4 + j], d[j:j + 1], c).numpy()
+            np.testing.assert_allclose(imp, golden[f"imp/mm_j{j}_c{c}"], atol=1e-5)
+
+
+def test_closed_form_matches_autograd(demo_inputs):
+    x, d = demo_inputs
+    sb = load_ckpt("ecg_baseline_best.pth")
+    cams = O.gradcam_batched(sb, x[:2], signal_length=5000, variant="v1")
+    for n in range(2):
+        for c in range(5):
+            ref = O.gradcam_v1(sb, x[n:n + 1], c, 5000)
+            assert int(cams[n, c].argmax()) == int(ref.argmax())
+            assert float((cams[n, c] - ref).abs().max()) < 1e-5
+
+
+def test_explicit_forms():
+    g = torch.Generator().manual_seed(3)
+    lo = torch.randn(64, 5, generator=g) * 4; y = (torch.rand(64, 5, generator=g) < 0.3).float()
+    assert abs(float(O.bce_with_logits(lo, y) - O.bce_with_logits_explicit(lo, y))) < 1e-6
+    cam = torch.rand(3, 125, generator=g)
+    np.testing.assert_allclose(O.linear_upsample(cam, 1000).numpy(),
+                               O.linear_upsample_explicit(cam, 1000).numpy(), atol=1e-6)
