@@ -1,0 +1,165 @@
+/* ecgb200.h -- C ABI of libecgb200.so: sm_100a kernels for the PTB-XL 1D-CNN ECG
+ * train / infer / Grad-CAM step.
+ *
+ * The reference (cyu0330/ptbxl-multimodal) has no FFI of its own: every FLOP of
+ * its hot path is a PyTorch ATen op reached from src/models/ecg_cnn.py,
+ * src/models/ecg_multimodal.py, src/training/loop*.py and
+ * src/interpretability/grad_cam_1d.py.  Each entry point below names the
+ * reference call site (path:line under /root/reference) whose ATen op it
+ * replaces.  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller; nothing is
+ *     allocated, freed or synchronised inside the library;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *     all work is enqueued on it, so calls are CUDA-graph capturable;
+ *   - return value 0 = ok, <0 = ECGB200_E* argument error, >0 = cudaError_t of
+ *     the launch; nothing throws across the boundary;
+ *   - fp32 tensors use the reference's layouts: activations (B, C, L)
+ *     contiguous, Conv1d weight (Co, Ci, 15), Linear weight (out, in);
+ *   - `ws` arguments are caller-provided scratch; the matching *_ws_bytes()
+ *     query returns the size needed for a given shape.
+ */
+#ifndef ECGB200_H_
+#define ECGB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ECGB200_KSIZE 15          /* Conv1d kernel_size, ecg_cnn.py:10 */
+#define ECGB200_EINVAL (-1)       /* bad shape / null pointer            */
+#define ECGB200_EUNSUPPORTED (-2) /* shape outside the kernels' envelope */
+
+/* library / build identification; also the cheapest "is it loaded" probe */
+int ecgb200_version(void);
+/* compiled-for architecture as an integer (1000 = sm_100a) */
+int ecgb200_arch(void);
+
+/* ---------------------------------------------------------------- Conv1d --
+ * Weight re-layout done once per optimizer step.
+ *   w      (Co, Ci, 15)  reference layout (nn.Conv1d.weight, ecg_cnn.py:13)
+ *   w_fwd  (Ci, 15, Co)  operand of ecgb200_conv1d_fwd_f32
+ *   w_dgr  (Co, 15, Ci)  tap-flipped transpose: operand of the same kernel when
+ *                        it computes the input gradient (dgrad).  May be NULL. */
+int ecgb200_conv1d_prep_weights_f32(const float* w, float* w_fwd, float* w_dgr,
+                                    int Co, int Ci, void* stream);
+
+/* y[b,o,t] = bias[o] + sum_{c,k} w[o,c,k] * x[b,c,t+k-7]   (zero padded)
+ * replaces aten::convolution called from nn.Conv1d, src/models/ecg_cnn.py:13.
+ *   x (B,Ci,L)  wt (Ci,15,Co) from prep_weights  bias (Co) or NULL  y (B,Co,L)
+ *   stat_part: NULL, or float[2*Co*ntiles] receiving per-(channel, tile)
+ *              {sum, centred M2} of y for the train-mode BatchNorm that follows
+ *              (ntiles = ecgb200_conv1d_stat_tiles(B, L)).
+ * Co must be a multiple of 32. */
+int ecgb200_conv1d_fwd_f32(const float* x, const float* wt, const float* bias, float* y,
+                           float* stat_part, int B, int Ci, int Co, int L, void* stream);
+int ecgb200_conv1d_stat_tiles(int B, int L);
+
+/* dW[o,c,k] = sum_{b,t} dy[b,o,t] * x[b,c,t+k-7];  db[o] = sum_{b,t} dy[b,o,t]
+ * replaces the wgrad / bias-grad half of aten::convolution_backward (autograd of
+ * ecg_cnn.py:13 reached from loss.backward(), src/training/loop.py:33).
+ *   ws: ecgb200_conv1d_wgrad_ws_bytes(B,Ci,Co,L) bytes of scratch (split-K partials,
+ *       reduced in a fixed order => run-to-run deterministic). */
+int ecgb200_conv1d_wgrad_f32(const float* dy, const float* x, float* dw, float* db, void* ws,
+                             int B, int Ci, int Co, int L, void* stream);
+size_t ecgb200_conv1d_wgrad_ws_bytes(int B, int Ci, int Co, int L);
+
+/* ------------------------------------------- BatchNorm1d + ReLU + MaxPool1d --
+ * Train-mode statistics from the conv epilogue partials (or from y itself when
+ * stat_part == NULL): mean, biased var -> rstd; scale = gamma*rstd,
+ * shift = beta - mean*scale; running stats updated with momentum 0.1 and the
+ * UNBIASED variance; *num_batches_tracked += 1.   nn.BatchNorm1d, ecg_cnn.py:14.
+ *   bn_state: float[4*Co] = {mean, rstd, scale, shift} (saved for backward).
+ *   ws: scratch of ecgb200_bn_stats_ws_bytes(B, Co, L) bytes (used when stat_part==NULL). */
+int ecgb200_bn_train_stats_f32(const float* y, const float* stat_part, const float* gamma,
+                               const float* beta, float* running_mean, float* running_var,
+                               int64_t* num_batches_tracked, float* bn_state, void* ws,
+                               int B, int Co, int L, float momentum, float eps, void* stream);
+size_t ecgb200_bn_stats_ws_bytes(int B, int Co, int L);
+/* Eval mode: bn_state from the running statistics (no update). */
+int ecgb200_bn_eval_state_f32(const float* gamma, const float* beta, const float* running_mean,
+                              const float* running_var, float* bn_state, int Co, float eps,
+                              void* stream);
+
+/* p[b,c,j] = max_{i in {2j,2j+1}} relu(y[b,c,i]*scale[c] + shift[c]),  Lp = floor(L/2)
+ * (BatchNorm apply + ReLU(inplace) + MaxPool1d(2), ecg_cnn.py:14-16).
+ * If p == NULL only the global average pool is produced:
+ * gap[b,c] = mean_j p[b,c,j]   (AdaptiveAvgPool1d(1)+squeeze, ecg_cnn.py:46,62). */
+int ecgb200_bn_relu_pool_fwd_f32(const float* y, const float* bn_state, float* p, float* gap,
+                                 int B, int Co, int L, void* stream);
+
+/* Backward of the block above through train-mode (batch-statistics) BatchNorm.
+ *   dp (B,Co,Lp) gradient w.r.t. the pooled output, or NULL with dgap (B,Co) given
+ *   (then dp[b,c,j] = dgap[b,c]/Lp).  Produces dy (B,Co,L), dgamma, dbeta.
+ * With train == 0 the BN is affine with fixed statistics (eval mode; Grad-CAM):
+ *   dy = scale * g.   ws: ecgb200_bn_bwd_ws_bytes(B,Co) bytes. */
+int ecgb200_bn_relu_pool_bwd_f32(const float* y, const float* bn_state, const float* gamma,
+                                 const float* dp, const float* dgap, float* dy, float* dgamma,
+                                 float* dbeta, void* ws, int B, int Co, int L, int train,
+                                 void* stream);
+size_t ecgb200_bn_bwd_ws_bytes(int B, int Co);
+
+/* ----------------------------------------------------------------- Linear --
+ * y = act(x W^T + b);  x (M,K), W (N,K), b (N) or NULL, y (M,N); act: 0 none, 1 relu.
+ * nn.Linear at ecg_cnn.py:47,50 and ecg_multimodal.py:52-54,85,86. */
+int ecgb200_linear_fwd_f32(const float* x, const float* w, const float* b, float* y,
+                           int M, int K, int N, int act, void* stream);
+/* dx = dy W (M,K) [NULL to skip]; dw = dy^T x (N,K); db = colsum(dy) (N) [NULL to skip].
+ * If relu_out != NULL, dy is first masked by relu_out > 0 IN PLACE (ReLU(inplace) bwd). */
+int ecgb200_linear_bwd_f32(const float* x, const float* w, float* dy, const float* relu_out,
+                           float* dx, float* dw, float* db, int M, int K, int N, void* stream);
+
+/* FiLM: zc = (1 + tanh(film[:, :F])) * z + film[:, F:]   (ecg_multimodal.py:92-96) */
+int ecgb200_film_fwd_f32(const float* z, const float* film, float* zc, int B, int F, void* stream);
+/* dz = dzc*(1+tanh g);  dfilm[:, :F] = dzc*z*(1-tanh^2 g);  dfilm[:, F:] = dzc */
+int ecgb200_film_bwd_f32(const float* z, const float* film, const float* dzc, float* dz,
+                         float* dfilm, int B, int F, void* stream);
+
+/* loss = mean_{b,c} [max(x,0) - x*y + log1p(exp(-|x|))]; dlogits = (sigmoid(x)-y)*gscale/(n)
+ * F.binary_cross_entropy_with_logits, src/training/loop.py:32; loop_demo.py:10,33.
+ * prob (sigmoid, loop.py:63) and dlogits may be NULL.  n = B*C elements. */
+int ecgb200_bce_logits_f32(const float* logits, const float* target, float* loss,
+                           float* dlogits, float* prob, int n, float gscale, void* stream);
+
+/* ------------------------------------------------------------------ AdamW --
+ * torch.optim.AdamW.step (scripts/03_train_ecg_baseline.py:133, loop.py:34):
+ *   p *= 1-lr*wd; m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
+ *   p -= (lr/(1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps);   g is first scaled by gscale.
+ * One launch over up to 64 tensors given as device-visible pointer tables passed BY VALUE
+ * from host arrays (the arrays themselves are host memory). */
+int ecgb200_adamw_f32(int ntensors, float* const* p, const float* const* g, float* const* m,
+                      float* const* v, const int64_t* numel, float lr, float beta1, float beta2,
+                      float eps, float weight_decay, int step, float gscale, void* stream);
+
+/* --------------------------------------------------------------- Grad-CAM --
+ * All-class batched Grad-CAM from the raw 4th-conv output A (B,C,L') in eval mode,
+ * closed form of GradCAM1D.generate_cam (src/interpretability/grad_cam_1d.py:53-103):
+ *   w[n,k,ch] = v[n or 0,k,ch] * s[ch] * count[n,ch] / (Lp*L'),  cam = relu(sum_ch w A)
+ *   variant 1: (cam-min)/max at L' then linear upsample to T (grad_cam_1d.py:92-101)
+ *   variant 2: upsample then (cam-min)/(max+eps)  (scripts/00_demo_inference.py:39-61,
+ *              12_grad_cam_ecg_demo.py:44-75, 13_grad_cam_af.py:51-76)
+ *   A (B,C,L'), bn_state of block 4 (eval), v (K,C) shared (v_per_sample=0) or (B,K,C)
+ *   cam_lo (B,K,L') may be NULL; cam_hi (B,K,T) may be NULL (T==0); argmax (B,K) int32 of
+ *   the final map (first maximal index), may be NULL.
+ * With bn_state == NULL, v holds the final channel weights mean_t dY/dA themselves
+ * (grad_cam_1d.py:85) as captured by backward hooks, and no mask count is applied. */
+int ecgb200_gradcam_f32(const float* A, const float* bn_state, const float* v, int v_per_sample,
+                        float* cam_lo, float* cam_hi, int32_t* argmax, int B, int C, int Lq,
+                        int K, int T, int variant, float eps, void* stream);
+
+/* out[r] = mean_t x[r,t]   (weights = dYdA.mean(dim=2), grad_cam_1d.py:85) */
+int ecgb200_row_mean_f32(const float* x, float* out, int rows, int L, void* stream);
+
+/* ------------------------------------------------------- input pipeline (N1) --
+ * per-lead z-score (x-mean)/(std+1e-6), population std, over time
+ * (src/datasets/ptbxl.py:122-127).  x, out (B, C, T). */
+int ecgb200_zscore_f32(const float* x, float* out, int rows, int T, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ECGB200_H_ */

@@ -1,0 +1,92 @@
+"""ctypes binding of libecgb200.so (the C ABI declared in include/ecgb200.h).
+
+There is NO fallback: if the shared library cannot be loaded (or built in-tree
+with nvcc) importing this module raises, and every op raises on non-CUDA
+tensors.  PyTorch is used only for device memory and streams."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch  # noqa: F401  (loads libcudart.so.12 that the library links against)
+
+from . import _build
+
+_P = C.c_void_p
+_I = C.c_int
+_F = C.c_float
+_Z = C.c_size_t
+
+_SIGS = {
+    "ecgb200_version": (_I, []),
+    "ecgb200_arch": (_I, []),
+    "ecgb200_conv1d_prep_weights_f32": (_I, [_P, _P, _P, _I, _I, _P]),
+    "ecgb200_conv1d_fwd_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "ecgb200_conv1d_stat_tiles": (_I, [_I, _I]),
+    "ecgb200_conv1d_wgrad_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "ecgb200_conv1d_wgrad_ws_bytes": (_Z, [_I, _I, _I, _I]),
+    "ecgb200_bn_train_stats_f32": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _P]),
+    "ecgb200_bn_stats_ws_bytes": (_Z, [_I, _I, _I]),
+    "ecgb200_bn_eval_state_f32": (_I, [_P, _P, _P, _P, _P, _I, _F, _P]),
+    "ecgb200_bn_relu_pool_fwd_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+    "ecgb200_bn_relu_pool_bwd_f32": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "ecgb200_bn_bwd_ws_bytes": (_Z, [_I, _I]),
+    "ecgb200_linear_fwd_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "ecgb200_linear_bwd_f32": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "ecgb200_film_fwd_f32": (_I, [_P, _P, _P, _I, _I, _P]),
+    "ecgb200_film_bwd_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _P]),
+    "ecgb200_bce_logits_f32": (_I, [_P, _P, _P, _P, _P, _I, _F, _P]),
+    "ecgb200_adamw_f32": (_I, [_I, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _I, _F, _P]),
+    "ecgb200_gradcam_f32": (_I, [_P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P]),
+    "ecgb200_zscore_f32": (_I, [_P, _P, _I, _I, _P]),
+    "ecgb200_row_mean_f32": (_I, [_P, _P, _I, _I, _P]),
+}
+
+EXPORTED = tuple(_SIGS)
+
+
+def _load() -> C.CDLL:
+    path = _build.LIB
+    if _build.needs_build():
+        try:
+            _build.build()
+        except Exception as e:  # no nvcc / compile error: only fatal if no prebuilt library
+            if not os.path.exists(path):
+                raise ImportError(
+                    f"libecgb200.so is missing and could not be built ({e}); "
+                    "run `python -c 'import __graft_entry__ as g; g.build()'`") from e
+    lib = C.CDLL(path)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)           # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+class EcgB200Error(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        if rc > 0:
+            raise EcgB200Error(f"{what}: CUDA error {rc} ({torch.cuda.get_device_name() if torch.cuda.is_available() else 'no device'})")
+        raise EcgB200Error(f"{what}: invalid/unsupported arguments (code {rc})")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL).  Refuses anything not on CUDA."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise EcgB200Error("ecgb200 ops run on CUDA tensors only (no CPU fallback)")
+    if not t.is_contiguous():
+        raise EcgB200Error("ecgb200 ops need contiguous tensors")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,320 @@
+// BatchNorm1d (train / eval) + ReLU + MaxPool1d(2) [+ global average pool], forward and
+// backward, fp32.  Memory-bound: every kernel streams y once with coalesced accesses.
+//
+// Replaces aten::native_batch_norm(+_backward), relu_/threshold_backward,
+// max_pool2d_with_indices(+_backward), adaptive_avg_pool1d reached from
+// /root/reference/src/models/ecg_cnn.py:14-16,46,62.
+#include "common.cuh"
+
+// bn_state layout: [0:C) mean, [C:2C) rstd, [2C:3C) scale = gamma*rstd, [3C:4C) shift = beta - mean*scale
+
+// ---------------------------------------------------------------- statistics
+// One warp per (b, c) row: {sum, centred M2}.  Output layout [2][C][B] (tile == sample).
+__global__ void bn_row_stats_kernel(const float* __restrict__ y, float* __restrict__ part,
+                                    int B, int C, int L) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= B * C) return;
+    const int lane = threadIdx.x & 31;
+    const float* yr = y + (size_t)row * L;
+    float s = 0.f;
+    for (int t = lane; t < L; t += 32) s += __ldg(yr + t);
+    s = warp_sum(s);
+    const float mean = s / (float)L;
+    float m2 = 0.f;
+    for (int t = lane; t < L; t += 32) { const float d = __ldg(yr + t) - mean; m2 = fmaf(d, d, m2); }
+    m2 = warp_sum(m2);
+    if (lane == 0) {
+        const int b = row / C, c = row - b * C;
+        part[(size_t)c * B + b] = s;
+        part[((size_t)C + c) * B + b] = m2;
+    }
+}
+
+// One block per channel: merge per-tile {sum, M2} (Chan et al.) in double, in a fixed order.
+// cnt(tile) = min(tile_len, L - (tile % tiles_per_row) * tile_len).
+__global__ void bn_finalize_kernel(const float* __restrict__ part, int ntiles, int tiles_per_row,
+                                   int tile_len, int L, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, int64_t* __restrict__ nbt,
+                                   float* __restrict__ bn_state, int C, float momentum, float eps) {
+    __shared__ double sh[33];
+    const int c = blockIdx.x;
+    const float* ps = part + (size_t)c * ntiles;
+    const float* pm = part + ((size_t)C + c) * ntiles;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < ntiles; i += blockDim.x) s += (double)ps[i];
+    s = block_sum_d(s, sh);
+    const double n = (double)(ntiles / tiles_per_row) * (double)L;
+    const double mean = s / n;
+    double m2 = 0.0;
+    for (int i = threadIdx.x; i < ntiles; i += blockDim.x) {
+        const int tt = i % tiles_per_row;
+        const double cnt = (double)min(tile_len, L - tt * tile_len);
+        const double d = (double)ps[i] / cnt - mean;
+        m2 += (double)pm[i] + cnt * d * d;
+    }
+    m2 = block_sum_d(m2, sh);
+    if (threadIdx.x == 0) {
+        const double var = m2 / n;                                   // biased
+        const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+        const float meanf = (float)mean;
+        const float scale = gamma[c] * rstd;
+        bn_state[c] = meanf;
+        bn_state[C + c] = rstd;
+        bn_state[2 * C + c] = scale;
+        bn_state[3 * C + c] = beta[c] - meanf * scale;
+        if (running_mean != nullptr) {
+            const double unbiased = n > 1.0 ? m2 / (n - 1.0) : var;
+            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * meanf;
+            running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+        }
+        if (c == 0 && nbt != nullptr) *nbt += 1;
+    }
+}
+
+__global__ void bn_eval_state_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     const float* __restrict__ rm, const float* __restrict__ rv,
+                                     float* __restrict__ bn_state, int C, float eps) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float rstd = 1.0f / sqrtf(rv[c] + eps);
+    const float scale = gamma[c] * rstd;
+    bn_state[c] = rm[c];
+    bn_state[C + c] = rstd;
+    bn_state[2 * C + c] = scale;
+    bn_state[3 * C + c] = beta[c] - rm[c] * scale;
+}
+
+extern "C" size_t ecgb200_bn_stats_ws_bytes(int B, int Co, int L) {
+    (void)L;
+    return (size_t)2 * Co * B * sizeof(float);
+}
+
+extern "C" int ecgb200_bn_train_stats_f32(const float* y, const float* stat_part, const float* gamma,
+                                          const float* beta, float* running_mean, float* running_var,
+                                          int64_t* nbt, float* bn_state, void* ws, int B, int Co,
+                                          int L, float momentum, float eps, void* stream) {
+    if (!gamma || !beta || !bn_state || B <= 0 || Co <= 0 || L <= 0) return ECGB200_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (stat_part != nullptr) {
+        const int tpr = ecg_cdiv(L, 128);
+        bn_finalize_kernel<<<Co, 256, 0, st>>>(stat_part, B * tpr, tpr, 128, L, gamma, beta,
+                                               running_mean, running_var, nbt, bn_state, Co, momentum, eps);
+    } else {
+        if (!y || !ws) return ECGB200_EINVAL;
+        const int rows = B * Co;
+        bn_row_stats_kernel<<<ecg_cdiv(rows, 8), 256, 0, st>>>(y, (float*)ws, B, Co, L);
+        int rc = ecg_launch_status();
+        if (rc) return rc;
+        bn_finalize_kernel<<<Co, 256, 0, st>>>((const float*)ws, B, 1, L, L, gamma, beta, running_mean,
+                                               running_var, nbt, bn_state, Co, momentum, eps);
+    }
+    return ecg_launch_status();
+}
+
+extern "C" int ecgb200_bn_eval_state_f32(const float* gamma, const float* beta, const float* running_mean,
+                                         const float* running_var, float* bn_state, int Co, float eps,
+                                         void* stream) {
+    if (!gamma || !beta || !running_mean || !running_var || !bn_state || Co <= 0) return ECGB200_EINVAL;
+    bn_eval_state_kernel<<<ecg_cdiv(Co, 128), 128, 0, (cudaStream_t)stream>>>(gamma, beta, running_mean,
+                                                                              running_var, bn_state, Co, eps);
+    return ecg_launch_status();
+}
+
+// ---------------------------------------------------------------- forward apply
+// grid (ceil(Lp/256), B*C): thread -> one pooled output (reads 2 inputs).
+__global__ void bn_relu_pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ bn_state,
+                                        float* __restrict__ p, int C, int L, int Lp, int vec) {
+    const int row = blockIdx.y;
+    const int c = row % C;
+    const float sc = __ldg(bn_state + 2 * C + c), sh = __ldg(bn_state + 3 * C + c);
+    const float* yr = y + (size_t)row * L;
+    float* pr = p + (size_t)row * Lp;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < Lp; j += gridDim.x * blockDim.x) {
+        float a0, a1;
+        if (vec) {
+            const float2 v = __ldg(reinterpret_cast<const float2*>(yr) + j);
+            a0 = v.x; a1 = v.y;
+        } else {
+            a0 = __ldg(yr + 2 * j); a1 = __ldg(yr + 2 * j + 1);
+        }
+        const float r0 = fmaxf(fmaf(a0, sc, sh), 0.f), r1 = fmaxf(fmaf(a1, sc, sh), 0.f);
+        pr[j] = fmaxf(r0, r1);
+    }
+}
+
+// one warp per (b, c) row: gap[b,c] = mean_j pooled
+__global__ void bn_relu_pool_gap_kernel(const float* __restrict__ y, const float* __restrict__ bn_state,
+                                        float* __restrict__ p, float* __restrict__ gap,
+                                        int rows, int C, int L, int Lp) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const int c = row % C;
+    const float sc = __ldg(bn_state + 2 * C + c), sh = __ldg(bn_state + 3 * C + c);
+    const float* yr = y + (size_t)row * L;
+    float s = 0.f;
+    for (int j = lane; j < Lp; j += 32) {
+        const float r0 = fmaxf(fmaf(__ldg(yr + 2 * j), sc, sh), 0.f);
+        const float r1 = fmaxf(fmaf(__ldg(yr + 2 * j + 1), sc, sh), 0.f);
+        const float m = fmaxf(r0, r1);
+        if (p != nullptr) p[(size_t)row * Lp + j] = m;
+        s += m;
+    }
+    s = warp_sum(s);
+    if (lane == 0) gap[row] = s / (float)Lp;
+}
+
+extern "C" int ecgb200_bn_relu_pool_fwd_f32(const float* y, const float* bn_state, float* p, float* gap,
+                                            int B, int Co, int L, void* stream) {
+    if (!y || !bn_state || (!p && !gap) || B <= 0 || Co <= 0 || L < 2) return ECGB200_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int Lp = L / 2, rows = B * Co;
+    if (gap != nullptr) {
+        bn_relu_pool_gap_kernel<<<ecg_cdiv(rows, 8), 256, 0, st>>>(y, bn_state, p, gap, rows, Co, L, Lp);
+    } else {
+        if (rows > 65535 * 32) return ECGB200_EUNSUPPORTED;
+        // grid.y limit is 65535: launch in slabs of whole samples so the channel phase is kept
+        const int threads = Lp >= 256 ? 256 : (Lp >= 128 ? 128 : 64);
+        const int vec = ((L & 1) == 0) && (((uintptr_t)y & 7) == 0);
+        // slabs aligned to C rows
+        const int slab = (65535 / Co) * Co;
+        for (int r0 = 0; r0 < rows; r0 += slab) {
+            const int nr = rows - r0 < slab ? rows - r0 : slab;
+            dim3 grid(ecg_cdiv(Lp, threads), nr);
+            bn_relu_pool_fwd_kernel<<<grid, threads, 0, st>>>(y + (size_t)r0 * L, bn_state,
+                                                              p + (size_t)r0 * Lp, Co, L, Lp, vec);
+        }
+    }
+    return ecg_launch_status();
+}
+
+// ---------------------------------------------------------------- backward
+// Routed gradient g at position 2j / 2j+1 of a pool pair (first index wins ties; ReLU mask r>0):
+//   g0 = d if (r0 >= r1 && r0 > 0);  g1 = d if (r1 > r0)
+// where d = dp[b,c,j]  (or dgap[b,c]/Lp).
+struct PoolGrad { float g0, g1, xh0, xh1; };
+
+__device__ __forceinline__ PoolGrad pool_grad(float a0, float a1, float d, float mean, float rstd,
+                                              float sc, float sh) {
+    PoolGrad r;
+    const float r0 = fmaxf(fmaf(a0, sc, sh), 0.f), r1 = fmaxf(fmaf(a1, sc, sh), 0.f);
+    r.g0 = (r0 >= r1 && r0 > 0.f) ? d : 0.f;
+    r.g1 = (r1 > r0) ? d : 0.f;
+    r.xh0 = (a0 - mean) * rstd;
+    r.xh1 = (a1 - mean) * rstd;
+    return r;
+}
+
+// one warp per row -> partial {sum g, sum g*xhat}; layout [2][C][B]
+__global__ void bn_bwd_reduce_kernel(const float* __restrict__ y, const float* __restrict__ bn_state,
+                                     const float* __restrict__ dp, const float* __restrict__ dgap,
+                                     float* __restrict__ part, int B, int C, int L, int Lp) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= B * C) return;
+    const int lane = threadIdx.x & 31;
+    const int b = row / C, c = row - b * C;
+    const float mean = __ldg(bn_state + c), rstd = __ldg(bn_state + C + c);
+    const float sc = __ldg(bn_state + 2 * C + c), sh = __ldg(bn_state + 3 * C + c);
+    const float* yr = y + (size_t)row * L;
+    const float dconst = dgap != nullptr ? __ldg(dgap + row) / (float)Lp : 0.f;
+    float s1 = 0.f, s2 = 0.f;
+    for (int j = lane; j < Lp; j += 32) {
+        const float d = dp != nullptr ? __ldg(dp + (size_t)row * Lp + j) : dconst;
+        const PoolGrad r = pool_grad(__ldg(yr + 2 * j), __ldg(yr + 2 * j + 1), d, mean, rstd, sc, sh);
+        s1 += r.g0 + r.g1;
+        s2 = fmaf(r.g0, r.xh0, fmaf(r.g1, r.xh1, s2));
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+        part[(size_t)c * B + b] = s1;
+        part[((size_t)C + c) * B + b] = s2;
+    }
+}
+
+// one block per channel: sums over the batch in double, fixed order
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, float* __restrict__ sums,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                       int B, int C) {
+    __shared__ double sh[33];
+    const int c = blockIdx.x;
+    double s1 = 0.0, s2 = 0.0;
+    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+        s1 += (double)part[(size_t)c * B + i];
+        s2 += (double)part[((size_t)C + c) * B + i];
+    }
+    s1 = block_sum_d(s1, sh);
+    s2 = block_sum_d(s2, sh);
+    if (threadIdx.x == 0) {
+        sums[c] = (float)s1;
+        sums[C + c] = (float)s2;
+        if (dbeta) dbeta[c] = (float)s1;
+        if (dgamma) dgamma[c] = (float)s2;
+    }
+}
+
+// grid (ceil(Lp/threads), rows): thread -> one pool pair (+ the odd tail element)
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ y, const float* __restrict__ bn_state,
+                                    const float* __restrict__ dp, const float* __restrict__ dgap,
+                                    const float* __restrict__ sums, float* __restrict__ dy,
+                                    int C, int L, int Lp, float inv_n, int train, int vec) {
+    const int row = blockIdx.y;
+    const int c = row % C;
+    const float mean = __ldg(bn_state + c), rstd = __ldg(bn_state + C + c);
+    const float sc = __ldg(bn_state + 2 * C + c), sh = __ldg(bn_state + 3 * C + c);
+    const float m1 = train ? __ldg(sums + c) * inv_n : 0.f;
+    const float m2 = train ? __ldg(sums + C + c) * inv_n : 0.f;
+    const float* yr = y + (size_t)row * L;
+    float* dr = dy + (size_t)row * L;
+    const float dconst = dgap != nullptr ? __ldg(dgap + row) / (float)Lp : 0.f;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < Lp; j += gridDim.x * blockDim.x) {
+        const float d = dp != nullptr ? __ldg(dp + (size_t)row * Lp + j) : dconst;
+        const PoolGrad r = pool_grad(__ldg(yr + 2 * j), __ldg(yr + 2 * j + 1), d, mean, rstd, sc, sh);
+        const float o0 = sc * (r.g0 - m1 - r.xh0 * m2);
+        const float o1 = sc * (r.g1 - m1 - r.xh1 * m2);
+        if (vec) {
+            reinterpret_cast<float2*>(dr)[j] = make_float2(o0, o1);
+        } else {
+            dr[2 * j] = o0; dr[2 * j + 1] = o1;
+        }
+        if (j == Lp - 1 && (L & 1)) {
+            const float xh = (__ldg(yr + L - 1) - mean) * rstd;
+            dr[L - 1] = sc * (0.f - m1 - xh * m2);
+        }
+    }
+}
+
+extern "C" size_t ecgb200_bn_bwd_ws_bytes(int B, int Co) {
+    return ((size_t)2 * Co * B + 2 * Co) * sizeof(float);
+}
+
+extern "C" int ecgb200_bn_relu_pool_bwd_f32(const float* y, const float* bn_state, const float* gamma,
+                                            const float* dp, const float* dgap, float* dy, float* dgamma,
+                                            float* dbeta, void* ws, int B, int Co, int L, int train,
+                                            void* stream) {
+    (void)gamma;
+    if (!y || !bn_state || (!dp && !dgap) || !dy || !ws || B <= 0 || Co <= 0 || L < 2) return ECGB200_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int Lp = L / 2, rows = B * Co;
+    float* part = (float*)ws;
+    float* sums = part + (size_t)2 * Co * B;
+    bn_bwd_reduce_kernel<<<ecg_cdiv(rows, 8), 256, 0, st>>>(y, bn_state, dp, dgap, part, B, Co, L, Lp);
+    int rc = ecg_launch_status();
+    if (rc) return rc;
+    bn_bwd_finalize_kernel<<<Co, 128, 0, st>>>(part, sums, dgamma, dbeta, B, Co);
+    rc = ecg_launch_status();
+    if (rc) return rc;
+    const int threads = Lp >= 256 ? 256 : (Lp >= 128 ? 128 : 64);
+    const float inv_n = 1.0f / ((float)B * (float)L);
+    const int vec = ((L & 1) == 0) && (((uintptr_t)dy & 7) == 0);
+    const int slab = (65535 / Co) * Co;
+    for (int r0 = 0; r0 < rows; r0 += slab) {
+        const int nr = rows - r0 < slab ? rows - r0 : slab;
+        dim3 grid(ecg_cdiv(Lp, threads), nr);
+        bn_bwd_apply_kernel<<<grid, threads, 0, st>>>(
+            y + (size_t)r0 * L, bn_state, dp ? dp + (size_t)r0 * Lp : nullptr,
+            dgap ? dgap + r0 : nullptr, sums, dy + (size_t)r0 * L, Co, L, Lp, inv_n, train, vec);
+    }
+    return ecg_launch_status();
+}

@@ -1,0 +1,227 @@
+// Batched all-class Grad-CAM in closed form (no autograd, no backward pass), plus the
+// per-lead z-score of the input pipeline.
+//
+// Replaces the per-(sample, class) forward + full backward of
+// /root/reference/src/interpretability/grad_cam_1d.py:53-103 and its script clones
+// (scripts/00_demo_inference.py:39-61, 12_grad_cam_ecg_demo.py:44-75, 13_grad_cam_af.py:51-76).
+// In eval mode dScore_k/dA[ch,t] = v_k[ch] * s[ch] * mask[ch,t] / Lp, with
+// mask = relu-active & first-argmax of its pool pair, so the channel weights are
+// w_k[ch] = v_k[ch] * s[ch] * count[ch] / (Lp * L') and every class shares count[].
+#include "common.cuh"
+
+constexpr int GC_MAXK = 8;
+
+__device__ __forceinline__ float upsample_at(const float* __restrict__ cam, int Lq, int d, float scale) {
+    // F.interpolate(mode='linear', align_corners=False): src = max((d+0.5)*scale-0.5, 0)
+    float src = fmaf((float)d + 0.5f, scale, -0.5f);
+    src = fmaxf(src, 0.f);
+    const int i0 = min((int)src, Lq - 1);
+    const int i1 = min(i0 + 1, Lq - 1);
+    const float lam = src - (float)i0;
+    return (1.0f - lam) * cam[i0] + lam * cam[i1];
+}
+
+// (value, index) block arg-reductions; ties -> smallest index
+__device__ __forceinline__ void block_minmax(float& mn, float& mx, int& amax, float* shf, int* shi) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float omn = __shfl_xor_sync(0xffffffffu, mn, o);
+        const float omx = __shfl_xor_sync(0xffffffffu, mx, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, amax, o);
+        mn = fminf(mn, omn);
+        if (omx > mx || (omx == mx && oi < amax)) { mx = omx; amax = oi; }
+    }
+    __syncthreads();
+    if (lane == 0) { shf[w] = mn; shf[32 + w] = mx; shi[w] = amax; }
+    __syncthreads();
+    if (w == 0) {
+        float a = lane < nw ? shf[lane] : INFINITY;
+        float b = lane < nw ? shf[32 + lane] : -INFINITY;
+        int ai = lane < nw ? shi[lane] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float oa = __shfl_xor_sync(0xffffffffu, a, o);
+            const float ob = __shfl_xor_sync(0xffffffffu, b, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, ai, o);
+            a = fminf(a, oa);
+            if (ob > b || (ob == b && oi < ai)) { b = ob; ai = oi; }
+        }
+        if (lane == 0) { shf[64] = a; shf[65] = b; shi[32] = ai; }
+    }
+    __syncthreads();
+    mn = shf[64]; mx = shf[65]; amax = shi[32];
+}
+
+// One block (256 threads) per sample.  dynamic smem: wk[K][C] | cnt[C] | cam[K][Lq]
+__global__ void __launch_bounds__(256)
+gradcam_kernel(const float* __restrict__ A, const float* __restrict__ bn_state,
+               const float* __restrict__ v, int v_per_sample, float* __restrict__ cam_lo,
+               float* __restrict__ cam_hi, int32_t* __restrict__ argmax_out, int C, int Lq, int K,
+               int T, int variant, float eps) {
+    extern __shared__ float smem[];
+    __shared__ float shf[66];
+    __shared__ int shi[33];
+    float* wk = smem;                  // K*C
+    float* cnt = wk + K * C;           // C
+    float* cam = cnt + C;              // K*Lq
+    const int n = blockIdx.x;
+    const float* An = A + (size_t)n * C * Lq;
+    const int Lp = Lq / 2;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+
+    // phase 1: per-channel count of positions that receive gradient through ReLU+MaxPool
+    // (skipped when bn_state == NULL: v already holds the final channel weights mean_t dY/dA)
+    for (int ch = w; bn_state != nullptr && ch < C; ch += nw) {
+        const float sc = __ldg(bn_state + 2 * C + ch), sh = __ldg(bn_state + 3 * C + ch);
+        const float* ar = An + (size_t)ch * Lq;
+        int c = 0;
+        for (int j = lane; j < Lp; j += 32) {
+            const float r0 = fmaxf(fmaf(__ldg(ar + 2 * j), sc, sh), 0.f);
+            const float r1 = fmaxf(fmaf(__ldg(ar + 2 * j + 1), sc, sh), 0.f);
+            c += ((r0 >= r1 && r0 > 0.f) ? 1 : 0) + ((r1 > r0) ? 1 : 0);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0) cnt[ch] = (float)c;
+    }
+    __syncthreads();
+    // phase 2: channel weights per class
+    const float* vn = v + (v_per_sample ? (size_t)n * K * C : 0);
+    const float inv = 1.0f / ((float)Lp * (float)Lq);
+    for (int i = threadIdx.x; i < K * C; i += blockDim.x) {
+        const int ch = i % C;
+        wk[i] = bn_state != nullptr ? __ldg(vn + i) * __ldg(bn_state + 2 * C + ch) * cnt[ch] * inv
+                                    : __ldg(vn + i);
+    }
+    __syncthreads();
+    // phase 3: cam[k][t] = relu(sum_ch wk[k][ch] * A[ch][t])   (coalesced over t)
+    for (int t = threadIdx.x; t < Lq; t += blockDim.x) {
+        float acc[GC_MAXK];
+#pragma unroll
+        for (int k = 0; k < GC_MAXK; ++k) acc[k] = 0.f;
+        for (int ch = 0; ch < C; ++ch) {
+            const float a = __ldg(An + (size_t)ch * Lq + t);
+#pragma unroll
+            for (int k = 0; k < GC_MAXK; ++k)
+                if (k < K) acc[k] = fmaf(wk[k * C + ch], a, acc[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < GC_MAXK; ++k)
+            if (k < K) cam[k * Lq + t] = fmaxf(acc[k], 0.f);
+    }
+    __syncthreads();
+    // phase 4: normalise / upsample / argmax per class
+    const bool up = (T > 0 && T != Lq);
+    const float scale = up ? (float)Lq / (float)T : 1.f;
+    for (int k = 0; k < K; ++k) {
+        float* ck = cam + k * Lq;
+        if (variant == 1) {
+            float mn = INFINITY, mx = -INFINITY; int am = 0x7fffffff;
+            for (int t = threadIdx.x; t < Lq; t += blockDim.x) {
+                const float x = ck[t];
+                mn = fminf(mn, x);
+                if (x > mx) { mx = x; am = t; }
+            }
+            block_minmax(mn, mx, am, shf, shi);
+            const float rng = mx - mn;
+            for (int t = threadIdx.x; t < Lq; t += blockDim.x) {
+                float x = ck[t] - mn;
+                if (rng > 0.f) x = x / rng;
+                ck[t] = x;
+                if (cam_lo != nullptr) cam_lo[((size_t)n * K + k) * Lq + t] = x;
+            }
+            __syncthreads();
+            if (up) {
+                float mn2 = INFINITY, mx2 = -INFINITY; int am2 = 0x7fffffff;
+                for (int d = threadIdx.x; d < T; d += blockDim.x) {
+                    const float x = upsample_at(ck, Lq, d, scale);
+                    if (cam_hi != nullptr) cam_hi[((size_t)n * K + k) * T + d] = x;
+                    if (x > mx2) { mx2 = x; am2 = d; }
+                    mn2 = fminf(mn2, x);
+                }
+                block_minmax(mn2, mx2, am2, shf, shi);
+                am = am2;
+            }
+            if (threadIdx.x == 0 && argmax_out != nullptr) argmax_out[(size_t)n * K + k] = am;
+        } else {
+            // variant 2: upsample first, then (cam - min) / (max + eps) over the upsampled map
+            const int Lout = up ? T : Lq;
+            float mn = INFINITY, mx = -INFINITY; int am = 0x7fffffff;
+            for (int d = threadIdx.x; d < Lout; d += blockDim.x) {
+                const float x = up ? upsample_at(ck, Lq, d, scale) : ck[d];
+                mn = fminf(mn, x);
+                if (x > mx) { mx = x; am = d; }
+            }
+            block_minmax(mn, mx, am, shf, shi);
+            const float den = (mx - mn) + eps;
+            for (int d = threadIdx.x; d < Lout; d += blockDim.x) {
+                const float x = ((up ? upsample_at(ck, Lq, d, scale) : ck[d]) - mn) / den;
+                if (up) { if (cam_hi != nullptr) cam_hi[((size_t)n * K + k) * T + d] = x; }
+                else if (cam_lo != nullptr) cam_lo[((size_t)n * K + k) * Lq + d] = x;
+            }
+            if (threadIdx.x == 0 && argmax_out != nullptr) argmax_out[(size_t)n * K + k] = am;
+        }
+        __syncthreads();
+    }
+}
+
+extern "C" int ecgb200_gradcam_f32(const float* A, const float* bn_state, const float* v,
+                                   int v_per_sample, float* cam_lo, float* cam_hi, int32_t* argmax,
+                                   int B, int C, int Lq, int K, int T, int variant, float eps,
+                                   void* stream) {
+    if (!A || !v || B <= 0 || C <= 0 || Lq < 2 || K <= 0) return ECGB200_EINVAL;
+    if (K > GC_MAXK || (variant != 1 && variant != 2)) return ECGB200_EUNSUPPORTED;
+    const size_t smem = ((size_t)K * C + C + (size_t)K * Lq) * sizeof(float);
+    if (smem > 200 * 1024) return ECGB200_EUNSUPPORTED;
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(gradcam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    gradcam_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(A, bn_state, v, v_per_sample, cam_lo, cam_hi,
+                                                          argmax, C, Lq, K, T, variant, eps);
+    return ecg_launch_status();
+}
+
+// ---------------------------------------------------------------- per-lead z-score (N1)
+// out = (x - mean) / (std + 1e-6), population std over time; one block per (sample, lead) row.
+// /root/reference/src/datasets/ptbxl.py:122-127.
+__global__ void __launch_bounds__(256)
+zscore_kernel(const float* __restrict__ x, float* __restrict__ out, int T) {
+    __shared__ double sh[33];
+    const float* xr = x + (size_t)blockIdx.x * T;
+    float* orow = out + (size_t)blockIdx.x * T;
+    double s = 0.0;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) s += (double)xr[t];
+    const double mean = block_sum_d(s, sh) / (double)T;
+    double m2 = 0.0;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) { const double d = (double)xr[t] - mean; m2 += d * d; }
+    const double var = block_sum_d(m2, sh) / (double)T;
+    const float mf = (float)mean;
+    const float inv = 1.0f / ((float)sqrt(var) + 1e-6f);
+    for (int t = threadIdx.x; t < T; t += blockDim.x) orow[t] = (xr[t] - mf) * inv;
+}
+
+extern "C" int ecgb200_zscore_f32(const float* x, float* out, int rows, int T, void* stream) {
+    if (!x || !out || rows <= 0 || T <= 0) return ECGB200_EINVAL;
+    zscore_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(x, out, T);
+    return ecg_launch_status();
+}
+
+// out[r] = mean_t x[r, t]; one warp per row (channel weights = mean_t dY/dA, grad_cam_1d.py:85)
+__global__ void row_mean_kernel(const float* __restrict__ x, float* __restrict__ out, int rows, int L) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    float s = 0.f;
+    for (int t = lane; t < L; t += 32) s += __ldg(x + (size_t)row * L + t);
+    s = warp_sum(s);
+    if (lane == 0) out[row] = s / (float)L;
+}
+
+extern "C" int ecgb200_row_mean_f32(const float* x, float* out, int rows, int L, void* stream) {
+    if (!x || !out || rows <= 0 || L <= 0) return ECGB200_EINVAL;
+    row_mean_kernel<<<ecg_cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, out, rows, L);
+    return ecg_launch_status();
+}
+
+extern "C" int ecgb200_version(void) { return 100; }
+extern "C" int ecgb200_arch(void) { return 1000; }

@@ -1,0 +1,50 @@
+"""Training / evaluation loops for single-input ECG models: same signatures and return
+values as the reference's src/training/loop.py (train_one_epoch :14-38,
+eval_one_epoch :41-73), with the BCE / sigmoid running as ecgb200 kernels and the
+per-step ``loss.item()`` host sync deferred to one read per epoch."""
+from typing import Dict
+
+import numpy as np
+import torch
+
+from . import functional as Fn
+from .metrics import compute_metrics
+
+
+def _logits(out):
+    return out[0] if isinstance(out, tuple) else out
+
+
+def train_one_epoch(model, loader, optimizer, device) -> float:
+    model.train()
+    total = torch.zeros((), dtype=torch.float64, device=device)
+    for x, y in loader:
+        x = x.to(device, non_blocking=True)
+        y = y.to(device, non_blocking=True)
+        optimizer.zero_grad()
+        logits = _logits(model(x))
+        loss = Fn.binary_cross_entropy_with_logits(logits, y)
+        loss.backward()
+        optimizer.step()
+        total += loss.detach().double() * x.size(0)         # stays on device: no per-step sync
+    return float(total.item()) / len(loader.dataset)
+
+
+def eval_one_epoch(model, loader, device) -> Dict[str, float]:
+    model.eval()
+    all_targets, all_probs = [], []
+    total = torch.zeros((), dtype=torch.float64, device=device)
+    with torch.no_grad():
+        for x, y in loader:
+            x = x.to(device, non_blocking=True)
+            y = y.to(device, non_blocking=True)
+            logits = _logits(model(x))
+            loss = Fn.binary_cross_entropy_with_logits(logits, y)
+            total += loss.double() * x.size(0)
+            all_targets.append(y)
+            all_probs.append(Fn.sigmoid(logits))
+    y_true = torch.cat(all_targets).cpu().numpy()
+    y_prob = torch.cat(all_probs).cpu().numpy()
+    metrics = compute_metrics(y_true, y_prob, threshold=0.5)
+    metrics["bce_loss"] = float(total.item()) / len(loader.dataset)
+    return metrics

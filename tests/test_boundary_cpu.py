@@ -1,0 +1,97 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads and exports every symbol
+include/ecgb200.h declares; the nn.Module tree / state_dict / init order match the
+reference (checked through the shipped checkpoints and the oracle's seeded init);
+there is no CPU fallback."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import ptbxl_multimodal_b200 as P
+from oracle import ecg_oracle as O
+from conftest import ROOT, load_ckpt
+
+
+def test_header_symbols_exported():
+    hdr = open(os.path.join(ROOT, "include", "ecgb200.h")).read()
+    declared = set(re.findall(r"\b(ecgb200_\w+)\s*\(", hdr))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(os.path.join(ROOT, "ptbxl_multimodal_b200", "libecgb200.so"))
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in ecgb200.h but not exported"
+    assert declared == set(P.EXPORTED), declared ^ set(P.EXPORTED)
+    assert lib.ecgb200_arch() == 1000
+
+
+def test_argument_errors_without_gpu():
+    from ptbxl_multimodal_b200._lib import lib
+    assert lib.ecgb200_conv1d_fwd_f32(None, None, None, None, None, 1, 12, 32, 100, None) == -1
+    assert lib.ecgb200_gradcam_f32(None, None, None, 0, None, None, None, 1, 256, 125, 5, 0, 1, 0.0, None) == -1
+    assert lib.ecgb200_conv1d_stat_tiles(256, 1000) == 256 * 8
+    assert lib.ecgb200_conv1d_wgrad_ws_bytes(256, 128, 256, 125) > 0
+
+
+@pytest.mark.parametrize("ckpt,ctor", [
+    ("ecg_baseline_best.pth", lambda: P.ECGCNN(12, 256, 5)),
+    ("af_binary_best.pth", lambda: P.ECGCNN(12, 256, 1)),
+    ("ecg_multimodal_best.pth", lambda: P.ECGMultimodal()),
+])
+def test_shipped_checkpoints_load_strict(ckpt, ctor):
+    sd = load_ckpt(ckpt)
+    model = ctor()
+    assert list(model.state_dict().keys()) == list(sd.keys())
+    model.load_state_dict(sd, strict=True)
+    for k, v in model.state_dict().items():
+        assert v.dtype == sd[k].dtype and v.shape == sd[k].shape and torch.equal(v, sd[k])
+
+
+def test_backbone_submodule_load():
+    # scripts/04_train_multimodal_prototype.py:149-156: baseline ckpt into model.ecg_backbone, strict=False
+    mm = P.ECGMultimodal()
+    res = mm.ecg_backbone.load_state_dict(load_ckpt("ecg_baseline_best.pth"), strict=False)
+    assert set(res.unexpected_keys) == {"head.weight", "head.bias"} and not res.missing_keys
+
+
+@pytest.mark.parametrize("kind,nl", [("cnn", 5), ("cnn", 1), ("mm", 5)])
+def test_seeded_init_matches_reference_order(kind, nl):
+    torch.manual_seed(42)
+    model = P.ECGCNN(12, 256, nl) if kind == "cnn" else P.ECGMultimodal(num_labels=nl)
+    sd = O.init_state_dict(kind, nl, seed=42)
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+
+
+def test_attribute_tree():
+    m = P.ECGCNN(12, 256, 5)
+    assert isinstance(m.backbone[-1].net[0], torch.nn.Conv1d)
+    last = None
+    for mod in m.modules():                       # scripts/00_demo_inference.py:64-71
+        if isinstance(mod, torch.nn.Conv1d):
+            last = mod
+    assert last is m.backbone[-1].net[0]
+    mm = P.ECGMultimodal(ecg_feat_dim=128, demo_hidden_dim=32)
+    assert mm.head.in_features == 128 and mm.film_gen.out_features == 256
+    assert isinstance(mm.ecg_backbone.backbone[-1].net[0], torch.nn.Conv1d)
+
+
+def test_no_cpu_fallback():
+    m = P.ECGCNN(12, 256, 5)
+    with pytest.raises(P.EcgB200Error):
+        m(torch.randn(2, 12, 256))
+    with pytest.raises(P.EcgB200Error):
+        P.functional.binary_cross_entropy_with_logits(torch.zeros(2, 5), torch.zeros(2, 5))
+    opt = P.FusedAdamW(m.parameters(), lr=1e-3)
+    for p in m.parameters():
+        p.grad = torch.zeros_like(p)
+    with pytest.raises(P.EcgB200Error):
+        opt.step()
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "ptbxl_multimodal_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("# oracle", ""), fn
