@@ -381,6 +381,34 @@ def synth_batch(batch: int, t: int, num_labels: int = 5, seed: int = 0,
     return x, demo, y
 
 
+def decision_margin(sd: StateDict, x: Tensor, kind: str = "cnn", train: bool = True) -> float:
+    """Smallest distance of any activation from a ReLU / MaxPool decision boundary in a
+    forward pass: min over blocks of min(|bn_out|, |r0 - r1| over pool pairs with a positive
+    max).  Two correct fp32 implementations agree on every routing decision only when this
+    margin exceeds their rounding difference (~1e-7 * |activation|); tests pick seeds whose
+    margin is > 1e-6 and report it."""
+    prefix = "" if kind == "cnn" else "ecg_backbone."
+    work = clone_sd(sd)
+    h = x
+    margin = float("inf")
+    with torch.no_grad():
+        for i in range(len(CHANNELS)):
+            p = f"{prefix}backbone.{i}."
+            a = F.conv1d(h, work[p + "net.0.weight"], work[p + "net.0.bias"], padding=KSIZE // 2)
+            bn = F.batch_norm(a, work[p + "net.1.running_mean"].clone(), work[p + "net.1.running_var"].clone(),
+                              work[p + "net.1.weight"], work[p + "net.1.bias"], training=train,
+                              momentum=BN_MOMENTUM, eps=BN_EPS)
+            margin = min(margin, float(bn.abs().min()))
+            r = F.relu(bn)
+            lp = r.shape[-1] // 2
+            r0, r1 = r[..., 0:2 * lp:2], r[..., 1:2 * lp:2]
+            live = torch.maximum(r0, r1) > 0
+            if live.any():
+                margin = min(margin, float((r0 - r1).abs()[live].min()))
+            h = F.max_pool1d(r, 2)
+    return margin
+
+
 def init_state_dict(kind: str = "cnn", num_labels: int = 5, seed: int = 42,
                     feat_dim: int = 256, in_leads: int = 12) -> StateDict:
     """PyTorch default init in the reference's module construction order

@@ -51,8 +51,11 @@ class GradCAM1D:
         self.gradients = grad_output[0].detach()
 
     def _register_hooks(self):
+        import warnings
         self.target_layer.register_forward_hook(self._forward_hook)
-        self.target_layer.register_full_backward_hook(self._backward_hook)
+        with warnings.catch_warnings():           # same (legacy) hook kind as the reference, :36
+            warnings.simplefilter("ignore")
+            self.target_layer.register_backward_hook(self._backward_hook)
 
     def generate_cam(self, input_tensor, class_idx, signal_length=None):
         """input_tensor (1, C, L) -> CAM (signal_length,) or (L',): normalise at L', then

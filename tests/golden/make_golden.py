@@ -146,7 +146,17 @@ def main():
         for k, v in model.state_dict().items():
             assert torch.equal(v, sd0[k]), k
         sdo = O.clone_sd(sd0)
-        batch = O.synth_batch(B, T, num_labels, seed=0, with_demo=(kind == "mm"))
+        # pick the first batch seed whose ReLU / MaxPool decision margin is > 1e-6, so that
+        # two correct fp32 implementations take identical routing decisions at step 0
+        for bseed in range(400):
+            batch = O.synth_batch(B, T, num_labels, seed=bseed, with_demo=(kind == "mm"))
+            mg = O.decision_margin(sd0, batch[0], kind)
+            if mg > 1.5e-6:
+                break
+        else:
+            raise RuntimeError("no margin-safe seed found")
+        out[f"{tag}/margin"] = np.array([mg, bseed])
+        print(tag, "batch seed", bseed, "decision margin", mg)
         x, y = batch[0], batch[-1]
         demo = batch[1] if kind == "mm" else None
         opt = torch.optim.AdamW(model.parameters(), lr=lr, weight_decay=wd)
@@ -178,10 +188,10 @@ def main():
                               if not k.endswith("num_batches_tracked")}, out)
         print(tag, "ok: loss", [float(out[f"{tag}/step{s}/loss"]) for s in range(steps)])
 
-    run_train("cnn", 5, 6, 1000, 1.5e-3, 1e-4, 3, "train_cnn")
-    run_train("mm", 5, 5, 1000, 1e-4, 1e-4, 3, "train_mm")
-    run_train("cnn", 1, 2, 5000, 1e-3, 1e-4, 2, "train_af")
-    run_train("cnn", 5, 3, 250, 1.5e-3, 1e-4, 2, "train_cnn_t250")   # L4=31 (odd), Lp=15
+    run_train("cnn", 5, 3, 1000, 1.5e-3, 1e-4, 3, "train_cnn")
+    run_train("mm", 5, 3, 1000, 1e-4, 1e-4, 3, "train_mm")
+    run_train("cnn", 1, 1, 5000, 1e-3, 1e-4, 2, "train_af")
+    run_train("cnn", 5, 5, 250, 1.5e-3, 1e-4, 2, "train_cnn_t250")   # L4=31 (odd), Lp=15
 
     # 2c. Grad-CAM variants, live
     gc = GradCAM1D(base, base.backbone[-1].net[0])
