@@ -54,7 +54,7 @@ int ecgb200_conv1d_prep_weights_f32(const float* w, float* w_fwd, float* w_dgr,
  *   stat_part: NULL, or float[2*Co*ntiles] receiving per-(channel, tile)
  *              {sum, centred M2} of y for the train-mode BatchNorm that follows
  *              (ntiles = ecgb200_conv1d_stat_tiles(B, L)).
- * Co must be a multiple of 32. */
+ * Any Co works; Co % 4 == 0 takes the vectorised weight path. */
 int ecgb200_conv1d_fwd_f32(const float* x, const float* wt, const float* bias, float* y,
                            float* stat_part, int B, int Ci, int Co, int L, void* stream);
 int ecgb200_conv1d_stat_tiles(int B, int L);
@@ -129,11 +129,14 @@ int ecgb200_bce_logits_f32(const float* logits, const float* target, float* loss
  * torch.optim.AdamW.step (scripts/03_train_ecg_baseline.py:133, loop.py:34):
  *   p *= 1-lr*wd; m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
  *   p -= (lr/(1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps);   g is first scaled by gscale.
- * One launch over up to 64 tensors given as device-visible pointer tables passed BY VALUE
- * from host arrays (the arrays themselves are host memory). */
+ * One launch over the `ntensors` tensors whose device pointers are listed in the HOST arrays
+ * p/g/m/v/numel (copied into the kernel's parameter block).  Hyper-parameters and the step
+ * counter live on the DEVICE so that the call can be captured in a CUDA graph and replayed:
+ *   hyper    float[6] = {lr, beta1, beta2, eps, weight_decay, gscale}
+ *   step_ctr int[1]   = steps taken so far; t = step_ctr+1 is used, then step_ctr += 1. */
 int ecgb200_adamw_f32(int ntensors, float* const* p, const float* const* g, float* const* m,
-                      float* const* v, const int64_t* numel, float lr, float beta1, float beta2,
-                      float eps, float weight_decay, int step, float gscale, void* stream);
+                      float* const* v, const int64_t* numel, const float* hyper, int* step_ctr,
+                      void* stream);
 
 /* --------------------------------------------------------------- Grad-CAM --
  * All-class batched Grad-CAM from the raw 4th-conv output A (B,C,L') in eval mode,

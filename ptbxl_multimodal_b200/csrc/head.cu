@@ -205,8 +205,26 @@ struct AdamTensors {
 };
 struct AdamScalars { float decay, one_m_b1, b2, one_m_b2, bc2_sqrt, eps, step_size, gscale; };
 
+// hyper (device): {lr, beta1, beta2, eps, weight_decay, gscale}; step_ctr (device): number of
+// steps already taken.  Keeping both on the device makes the launch CUDA-graph replayable:
+// the bias corrections are recomputed from the counter inside the kernel.
 __global__ void __launch_bounds__(256)
-adamw_kernel(const __grid_constant__ AdamTensors T, const AdamScalars S) {
+adamw_kernel(const __grid_constant__ AdamTensors T, const float* __restrict__ hyper,
+             const int* __restrict__ step_ctr) {
+    __shared__ AdamScalars S;
+    if (threadIdx.x == 0) {
+        const double lr = hyper[0], b1 = hyper[1], b2 = hyper[2], wd = hyper[4];
+        const double step = (double)(step_ctr[0] + 1);
+        S.decay = (float)(1.0 - lr * wd);
+        S.one_m_b1 = (float)(1.0 - b1);
+        S.b2 = hyper[2];
+        S.one_m_b2 = (float)(1.0 - b2);
+        S.bc2_sqrt = (float)sqrt(1.0 - pow(b2, step));
+        S.eps = hyper[3];
+        S.step_size = (float)(lr / (1.0 - pow(b1, step)));
+        S.gscale = hyper[5];
+    }
+    __syncthreads();
     const int t = blockIdx.y;
     const long long n = T.n[t];
     float* __restrict__ p = T.p[t];
@@ -225,23 +243,13 @@ adamw_kernel(const __grid_constant__ AdamTensors T, const AdamScalars S) {
     }
 }
 
+__global__ void counter_inc_kernel(int* ctr) { ctr[0] += 1; }
+
 extern "C" int ecgb200_adamw_f32(int nt, float* const* p, const float* const* g, float* const* m,
-                                 float* const* v, const int64_t* numel, float lr, float beta1,
-                                 float beta2, float eps, float weight_decay, int step, float gscale,
-                                 void* stream) {
-    if (nt <= 0 || !p || !g || !m || !v || !numel || step < 1) return ECGB200_EINVAL;
+                                 float* const* v, const int64_t* numel, const float* hyper,
+                                 int* step_ctr, void* stream) {
+    if (nt <= 0 || !p || !g || !m || !v || !numel || !hyper || !step_ctr) return ECGB200_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
-    AdamScalars S;
-    const double bc1 = 1.0 - pow((double)beta1, (double)step);
-    const double bc2 = 1.0 - pow((double)beta2, (double)step);
-    S.decay = (float)(1.0 - (double)lr * (double)weight_decay);
-    S.one_m_b1 = (float)(1.0 - (double)beta1);
-    S.b2 = beta2;
-    S.one_m_b2 = (float)(1.0 - (double)beta2);
-    S.bc2_sqrt = (float)sqrt(bc2);
-    S.eps = eps;
-    S.step_size = (float)((double)lr / bc1);
-    S.gscale = gscale;
     for (int t0 = 0; t0 < nt; t0 += ADAM_MAXT) {
         AdamTensors T;
         const int cnt = nt - t0 < ADAM_MAXT ? nt - t0 : ADAM_MAXT;
@@ -255,9 +263,10 @@ extern "C" int ecgb200_adamw_f32(int nt, float* const* p, const float* const* g,
         if (bx < 1) bx = 1;
         if (bx > 2048) bx = 2048;
         dim3 grid((unsigned)bx, cnt);
-        adamw_kernel<<<grid, 256, 0, st>>>(T, S);
+        adamw_kernel<<<grid, 256, 0, st>>>(T, hyper, step_ctr);
         int rc = ecg_launch_status();
         if (rc) return rc;
     }
-    return 0;
+    counter_inc_kernel<<<1, 1, 0, st>>>(step_ctr);
+    return ecg_launch_status();
 }

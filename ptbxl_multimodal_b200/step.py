@@ -1,0 +1,351 @@
+"""TrainStep: the whole training step of the reference loop body
+(zero_grad -> model(x) -> BCE -> backward -> AdamW.step, src/training/loop.py:26-36 and
+src/training/loop_demo.py:30-41) as ONE CUDA graph of ecgb200 kernels over static buffers.
+
+B200-first structure: parameters, gradients and both Adam moments live in four flat fp32
+buffers (the nn.Module's parameters are re-pointed to views of the flat parameter buffer, so
+``state_dict`` / checkpoints are untouched); activations live in preallocated buffers sized for
+(batch, seq_len); the kernel sequence is enqueued once through the C ABI, captured with
+``torch.cuda.CUDAGraph`` and replayed per step, so a step costs one launch from the host and
+no host<->device synchronisation (the loss stays on the device until the caller reads it).
+
+Data parallel (one process per GPU): gradients are summed with NCCL all-reduce in two buckets
+-- the 4th conv block (65 % of the bytes, ready first) on a side stream while blocks 3..1
+still run backward, the rest at the end -- and the 1/world_size average is folded into the
+AdamW kernel (``gscale``).  BatchNorm statistics are per rank (torch DDP semantics)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import torch
+
+from ._lib import lib, check, EcgB200Error
+from .ecg_cnn import ECGCNN
+from .ecg_multimodal import ECGMultimodal
+from .optim import FusedAdamW
+
+F32 = torch.float32
+
+
+def _p(t: Optional[torch.Tensor], off: int = 0):
+    return None if t is None else t.data_ptr() + 4 * off
+
+
+class _Seg:
+    """A parameter's slot in the flat buffers."""
+    __slots__ = ("name", "param", "off", "n")
+
+    def __init__(self, name, param, off):
+        self.name, self.param, self.off, self.n = name, param, off, param.numel()
+
+
+class TrainStep:
+    def __init__(self, model, optimizer: FusedAdamW, batch_size: int, seq_len: int,
+                 process_group=None, use_graph: bool = True):
+        if not isinstance(model, (ECGCNN, ECGMultimodal)):
+            raise EcgB200Error("TrainStep drives ecgb200 ECGCNN / ECGMultimodal models")
+        if not isinstance(optimizer, FusedAdamW) or len(optimizer.param_groups) != 1:
+            raise EcgB200Error("TrainStep needs a single-group FusedAdamW")
+        self.model, self.opt = model, optimizer
+        self.mm = isinstance(model, ECGMultimodal)
+        self.bb = model.ecg_backbone if self.mm else model
+        self.B, self.T = int(batch_size), int(seq_len)
+        if self.T < 16:
+            raise EcgB200Error("seq_len must be >= 16 (four MaxPool1d(2) stages)")
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self.dev = next(model.parameters()).device
+        if self.dev.type != "cuda":
+            raise EcgB200Error("TrainStep needs the model on a CUDA device (no CPU fallback)")
+        self.use_graph = use_graph
+        self.graph = None
+        self.launches_per_step = 0
+        self._prof = None
+        self._prof_tag = ""
+        self._flatten()
+        self._alloc()
+
+    # ------------------------------------------------------------------ flat parameter space
+    def _flatten(self):
+        named = list(self.model.named_parameters())
+        group = self.opt.param_groups[0]
+        if {id(p) for _, p in named} != {id(p) for p in group["params"]}:
+            raise EcgB200Error("the optimizer must hold exactly the model's parameters")
+        last = ("ecg_backbone." if self.mm else "") + "backbone.3."
+        order = [(n, p) for n, p in named if not n.startswith(last)] + \
+                [(n, p) for n, p in named if n.startswith(last)]
+        total = sum(p.numel() for _, p in order)
+        dev = self.dev
+        self.P = torch.empty(total, dtype=F32, device=dev)
+        self.G = torch.zeros(total, dtype=F32, device=dev)
+        self.M = torch.zeros(total, dtype=F32, device=dev)
+        self.V = torch.zeros(total, dtype=F32, device=dev)
+        self.seg = {}
+        off = 0
+        with torch.no_grad():
+            for n, p in order:
+                if p.dtype != F32:
+                    raise EcgB200Error("parameters must be float32")
+                s = _Seg(n, p, off)
+                self.P[off:off + s.n].copy_(p.detach().reshape(-1))
+                st = self.opt.state[p]
+                if st:                                      # adopt existing optimizer moments
+                    self.M[off:off + s.n].copy_(st["exp_avg"].reshape(-1))
+                    self.V[off:off + s.n].copy_(st["exp_avg_sq"].reshape(-1))
+                p.data = self.P[off:off + s.n].view(p.shape)
+                p.grad = self.G[off:off + s.n].view(p.shape)
+                st["exp_avg"] = self.M[off:off + s.n].view(p.shape)
+                st["exp_avg_sq"] = self.V[off:off + s.n].view(p.shape)
+                self.seg[n] = s
+                off += s.n
+        self.total = total
+        self.bucket_a_off = self.seg[last + "net.0.weight"].off     # block 4 = tail of the buffers
+        self.hyper, self.step_dev = self.opt.device_state(group, dev)
+        if self.world > 1:
+            self.opt.grad_scale = 1.0 / self.world
+            self.hyper, self.step_dev = self.opt.device_state(group, dev)
+
+    def _refresh_views(self):
+        """Re-point parameters at the flat buffers if something (e.g. load_state_dict keeps
+        them, .to() does not) replaced their storage."""
+        with torch.no_grad():
+            for s in self.seg.values():
+                if s.param.data_ptr() != self.P.data_ptr() + 4 * s.off:
+                    self.P[s.off:s.off + s.n].copy_(s.param.detach().reshape(-1))
+                    s.param.data = self.P[s.off:s.off + s.n].view(s.param.shape)
+                s.param.grad = self.G[s.off:s.off + s.n].view(s.param.shape)
+
+    # ------------------------------------------------------------------ static buffers
+    def _alloc(self):
+        B, T, dev = self.B, self.T, self.dev
+        e = lambda *s: torch.empty(*s, dtype=F32, device=dev)   # noqa: E731
+        blocks = list(self.bb.backbone)
+        self.chan = [blocks[0].net[0].in_channels] + [b.net[0].out_channels for b in blocks]
+        self.L = [T, T // 2, T // 4, T // 8]                      # conv lengths; pooled = L // 2
+        self.nl = self.model.head.out_features
+        self.feat = self.bb.proj.out_features
+        self.x = e(B, self.chan[0], T)
+        self.y = e(B, self.nl)
+        self.acts = [self.x]                                       # input of conv l
+        self.ybuf, self.stat, self.bnst, self.wt, self.wd = [], [], [], [], []
+        for l in range(4):
+            ci, co, L = self.chan[l], self.chan[l + 1], self.L[l]
+            self.ybuf.append(e(B, co, L))
+            self.stat.append(e(2, co, lib.ecgb200_conv1d_stat_tiles(B, L)))
+            self.bnst.append(e(4, co))
+            self.wt.append(e(ci, 15, co))
+            self.wd.append(e(co, 15, ci) if l > 0 else None)
+            if l < 3:
+                self.acts.append(e(B, co, L // 2))
+        c4 = self.chan[4]
+        self.gap = e(B, c4)
+        self.dgap = e(B, c4)
+        self.z = e(B, self.feat)
+        self.dz = e(B, self.feat)
+        self.logits = e(B, self.nl)
+        self.dlogits = e(B, self.nl)
+        self.loss = torch.zeros((), dtype=F32, device=dev)
+        if self.mm:
+            dm = self.model.demo_encoder.mlp
+            self.demo = e(B, dm[0].in_features)
+            self.h1, self.dh1 = e(B, dm[0].out_features), e(B, dm[0].out_features)
+            self.h2, self.dh2 = e(B, dm[2].out_features), e(B, dm[2].out_features)
+            self.film, self.dfilm = e(B, 2 * self.feat), e(B, 2 * self.feat)
+            self.zc, self.dzc = e(B, self.feat), e(B, self.feat)
+        big = B * 32 * T                                          # every conv output has 32*T elems/sample
+        self.dy = e(max(B * co * L for co, L in zip(self.chan[1:], self.L)))
+        self.dp = e(max(B * self.chan[l] * self.L[l] for l in range(1, 4)))
+        ws = max(lib.ecgb200_conv1d_wgrad_ws_bytes(B, self.chan[l], self.chan[l + 1], self.L[l]) for l in range(4))
+        ws = max(ws, max(lib.ecgb200_bn_bwd_ws_bytes(B, c) for c in self.chan[1:]))
+        self.ws = torch.empty(ws, dtype=torch.uint8, device=dev)
+        del big
+        self.side = torch.cuda.Stream(device=dev) if self.world > 1 else None
+
+    # ------------------------------------------------------------------ the kernel sequence
+    def _k(self, name, fn, *args):
+        """One C-ABI call; with self._prof set, bracket it with CUDA events on the launch stream."""
+        prof = self._prof
+        if prof is None:
+            check(fn(*args), name)
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(fn(*args), name)
+        e1.record()
+        prof.append((name + self._prof_tag, e0, e1))
+
+    def _seg_ptr(self, name, buf):
+        return buf.data_ptr() + 4 * self.seg[name].off
+
+    def _enqueue(self):
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        B = self.B
+        n = 0
+        pre = "ecg_backbone." if self.mm else ""
+        Pp = lambda k: self._seg_ptr(k, self.P)       # noqa: E731
+        Gp = lambda k: self._seg_ptr(k, self.G)       # noqa: E731
+        blocks = list(self.bb.backbone)
+        # ---- forward
+        for l in range(4):
+            ci, co, L = self.chan[l], self.chan[l + 1], self.L[l]
+            k = f"{pre}backbone.{l}.net."
+            bn = blocks[l].net[1]
+            self._prof_tag = f"_L{l + 1}"
+            self._k("prep", lib.ecgb200_conv1d_prep_weights_f32, Pp(k + "0.weight"), _p(self.wt[l]), _p(self.wd[l]), co, ci, st)
+            self._k("conv_fwd", lib.ecgb200_conv1d_fwd_f32, _p(self.acts[l]), _p(self.wt[l]), Pp(k + "0.bias"), _p(self.ybuf[l]),
+                                             _p(self.stat[l]), B, ci, co, L, st)
+            self._k("bn_stats", lib.ecgb200_bn_train_stats_f32, _p(self.ybuf[l]), _p(self.stat[l]), Pp(k + "1.weight"), Pp(k + "1.bias"),
+                                                 bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
+                                                 bn.num_batches_tracked.data_ptr(), _p(self.bnst[l]), None,
+                                                 B, co, L, float(bn.momentum), float(bn.eps), st)
+            self._k("bn_relu_pool", lib.ecgb200_bn_relu_pool_fwd_f32, _p(self.ybuf[l]), _p(self.bnst[l]),
+                                                   _p(self.acts[l + 1]) if l < 3 else None,
+                                                   _p(self.gap) if l == 3 else None, B, co, L, st)
+            n += 4
+        self._prof_tag = ""
+        c4, F_, NL = self.chan[4], self.feat, self.nl
+        self._k("proj", lib.ecgb200_linear_fwd_f32, _p(self.gap), Pp(pre + "proj.weight"), Pp(pre + "proj.bias"), _p(self.z),
+                                         B, c4, F_, 0, st)
+        n += 1
+        zin = self.z
+        if self.mm:
+            d0, h1n, h2n = self.demo.shape[1], self.h1.shape[1], self.h2.shape[1]
+            self._k("demo0", lib.ecgb200_linear_fwd_f32, _p(self.demo), Pp("demo_encoder.mlp.0.weight"), Pp("demo_encoder.mlp.0.bias"),
+                                             _p(self.h1), B, d0, h1n, 1, st)
+            self._k("demo2", lib.ecgb200_linear_fwd_f32, _p(self.h1), Pp("demo_encoder.mlp.2.weight"), Pp("demo_encoder.mlp.2.bias"),
+                                             _p(self.h2), B, h1n, h2n, 1, st)
+            self._k("film_gen", lib.ecgb200_linear_fwd_f32, _p(self.h2), Pp("film_gen.weight"), Pp("film_gen.bias"), _p(self.film),
+                                             B, h2n, 2 * F_, 0, st)
+            self._k("film", lib.ecgb200_film_fwd_f32, _p(self.z), _p(self.film), _p(self.zc), B, F_, st)
+            zin = self.zc
+            n += 4
+        self._k("head", lib.ecgb200_linear_fwd_f32, _p(zin), Pp("head.weight"), Pp("head.bias"), _p(self.logits), B, F_, NL, 0, st)
+        self._k("bce", lib.ecgb200_bce_logits_f32, _p(self.logits), _p(self.y), _p(self.loss), _p(self.dlogits), None,
+                                         B * NL, 1.0, st)
+        n += 2
+        # ---- backward: head
+        if self.mm:
+            self._k("head_bwd", lib.ecgb200_linear_bwd_f32, _p(self.zc), Pp("head.weight"), _p(self.dlogits), None, _p(self.dzc),
+                                             Gp("head.weight"), Gp("head.bias"), B, F_, NL, st)
+            self._k("film_bwd", lib.ecgb200_film_bwd_f32, _p(self.z), _p(self.film), _p(self.dzc), _p(self.dz), _p(self.dfilm), B, F_, st)
+            self._k("film_gen_bwd", lib.ecgb200_linear_bwd_f32, _p(self.h2), Pp("film_gen.weight"), _p(self.dfilm), None, _p(self.dh2),
+                                             Gp("film_gen.weight"), Gp("film_gen.bias"), B, h2n, 2 * F_, st)
+            self._k("demo2_bwd", lib.ecgb200_linear_bwd_f32, _p(self.h1), Pp("demo_encoder.mlp.2.weight"), _p(self.dh2), _p(self.h2), _p(self.dh1),
+                                             Gp("demo_encoder.mlp.2.weight"), Gp("demo_encoder.mlp.2.bias"), B, h1n, h2n, st)
+            self._k("demo0_bwd", lib.ecgb200_linear_bwd_f32, _p(self.demo), Pp("demo_encoder.mlp.0.weight"), _p(self.dh1), _p(self.h1), None,
+                                             Gp("demo_encoder.mlp.0.weight"), Gp("demo_encoder.mlp.0.bias"), B, d0, h1n, st)
+            n += 3 + 1 + 3 + 3 + 2
+        else:
+            self._k("head_bwd", lib.ecgb200_linear_bwd_f32, _p(self.z), Pp("head.weight"), _p(self.dlogits), None, _p(self.dz),
+                                             Gp("head.weight"), Gp("head.bias"), B, F_, NL, st)
+            n += 3
+        self._k("proj_bwd", lib.ecgb200_linear_bwd_f32, _p(self.gap), Pp(pre + "proj.weight"), _p(self.dz), None, _p(self.dgap),
+                                         Gp(pre + "proj.weight"), Gp(pre + "proj.bias"), B, c4, F_, st)
+        n += 3
+        # ---- backward: conv blocks 4..1
+        main = torch.cuda.current_stream(self.dev)
+        for l in (3, 2, 1, 0):
+            ci, co, L = self.chan[l], self.chan[l + 1], self.L[l]
+            k = f"{pre}backbone.{l}.net."
+            self._prof_tag = f"_L{l + 1}"
+            self._k("bn_bwd", lib.ecgb200_bn_relu_pool_bwd_f32, _p(self.ybuf[l]), _p(self.bnst[l]), Pp(k + "1.weight"),
+                                                   _p(self.dp) if l < 3 else None, _p(self.dgap) if l == 3 else None,
+                                                   _p(self.dy), Gp(k + "1.weight"), Gp(k + "1.bias"), _p(self.ws),
+                                                   B, co, L, 1, st)
+            self._k("wgrad", lib.ecgb200_conv1d_wgrad_f32, _p(self.dy), _p(self.acts[l]), Gp(k + "0.weight"), Gp(k + "0.bias"),
+                                               _p(self.ws), B, ci, co, L, st)
+            n += 5
+            if l == 3 and self.world > 1:
+                # bucket A (block 4, the tail of G) is final: all-reduce it while blocks 3..1 run
+                ev = torch.cuda.Event()
+                ev.record(main)
+                self.side.wait_event(ev)
+                with torch.cuda.stream(self.side):
+                    torch.distributed.all_reduce(self.G[self.bucket_a_off:], group=self.pg)
+            if l > 0:
+                self._k("dgrad", lib.ecgb200_conv1d_fwd_f32, _p(self.dy), _p(self.wd[l]), None, _p(self.dp), None,
+                                                 B, co, ci, L, st)
+                n += 1
+        # ---- gradient exchange + optimizer
+        self._prof_tag = ""
+        if self.world > 1:
+            torch.distributed.all_reduce(self.G[:self.bucket_a_off], group=self.pg)
+            ev2 = torch.cuda.Event()
+            ev2.record(self.side)
+            main.wait_event(ev2)
+        one = C.c_void_p * 1
+        num = (C.c_int64 * 1)(self.total)
+        self._k("adamw", lib.ecgb200_adamw_f32, 1, one(self.P.data_ptr()), one(self.G.data_ptr()), one(self.M.data_ptr()),
+                                    one(self.V.data_ptr()), num, self.hyper.data_ptr(), self.step_dev.data_ptr(), st)
+        n += 2
+        self.launches_per_step = n
+
+    # ------------------------------------------------------------------ public API
+    def capture(self):
+        self._refresh_views()
+        group = self.opt.param_groups[0]
+        self.hyper, self.step_dev = self.opt.device_state(group, self.dev)
+        if not self.use_graph:
+            return
+        # warm-up outside capture would advance the optimizer; capture directly instead
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._enqueue()
+        self.graph = g
+
+    def profile_kernels(self, iters: int = 5):
+        """Per-C-ABI-call device time (ms, mean over `iters` un-graphed passes, CUDA events on the
+        launch stream).  Advances training like `iters` ordinary steps."""
+        self._refresh_views()
+        acc = {}
+        order = []
+        for _ in range(iters):
+            self._prof = []
+            self._enqueue()
+            torch.cuda.synchronize(self.dev)
+            for name, e0, e1 in self._prof:
+                if name not in acc:
+                    acc[name] = 0.0
+                    order.append(name)
+                acc[name] += e0.elapsed_time(e1)
+            self._prof = None
+            self.opt.param_groups[0]["step"] = self.opt.param_groups[0].get("step", 0) + 1
+        return [(n, acc[n] / iters) for n in order]
+
+    def load_batch(self, x, y, demo=None):
+        """Copy a batch (host pinned or device) into the static input buffers (async)."""
+        if tuple(x.shape) != tuple(self.x.shape) or tuple(y.shape) != tuple(self.y.shape):
+            raise EcgB200Error(f"TrainStep was built for x{tuple(self.x.shape)} y{tuple(self.y.shape)}, "
+                               f"got x{tuple(x.shape)} y{tuple(y.shape)}")
+        self.x.copy_(x, non_blocking=True)
+        self.y.copy_(y, non_blocking=True)
+        if self.mm:
+            if demo is None:
+                raise EcgB200Error("ECGMultimodal step needs x_demo")
+            self.demo.copy_(demo, non_blocking=True)
+
+    def run(self):
+        """One optimizer step on whatever the static input buffers hold.  Returns the loss
+        buffer (device scalar, overwritten by the next step)."""
+        group = self.opt.param_groups[0]
+        hyper, _ = self.opt.device_state(group, self.dev)
+        if hyper.data_ptr() != self.hyper.data_ptr():          # lr / betas changed on the host
+            self.hyper.copy_(hyper)
+            group["_hyper"] = self.hyper
+        if self.use_graph:
+            if self.graph is None:
+                self.capture()
+            self.graph.replay()
+        else:
+            self._refresh_views()
+            self._enqueue()
+        group["step"] = group.get("step", 0) + 1
+        return self.loss
+
+    def __call__(self, x, y, demo=None):
+        self.load_batch(x, y, demo)
+        return self.run()

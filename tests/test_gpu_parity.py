@@ -424,7 +424,10 @@ def test_gradcam_synthetic_config5_slice():
     assert torch.equal(arg.cpu().long()[clear], ref.argmax(dim=2)[clear])
     dead = ref.max(dim=2).values == 0                     # ReLU killed the whole map: argmax is index 0
     assert torch.equal(arg.cpu().long()[dead], torch.zeros_like(arg.cpu().long()[dead]))
-    assert (clear | dead).float().mean() > 0.95
+    # remaining maps have a (near-)tie at the top: our value at the oracle's peak must equal our max
+    ours_at_ref = cam.cpu().gather(2, ref.argmax(dim=2, keepdim=True)).squeeze(2)
+    assert float((cam.cpu().max(dim=2).values - ours_at_ref).abs().max()) < 1e-5
+    assert (clear | dead).float().mean() > 0.6
 
 
 def test_demo_importance(demo_inputs, golden):
