@@ -68,6 +68,23 @@ int ecgb200_conv1d_wgrad_f32(const float* dy, const float* x, float* dw, float* 
                              int B, int Ci, int Co, int L, void* stream);
 size_t ecgb200_conv1d_wgrad_ws_bytes(int B, int Ci, int Co, int L);
 
+/* ------------------------------------------------ bf16 tensor-core path (tcgen05) --
+ * Activations in this path are "blocked channels-last" bf16:  A[b][c/8][t][c%8], C % 8 == 0
+ * (16 bytes = 8 channels of one time step), accumulation is fp32 in TMEM.
+ * pack:   x fp32 (B,Ci,T) -> xb bf16 [B][Cp/8][T][8], Cp = Ci rounded up to 16, pad channels 0
+ *         (the (B,12,T) input of ECGCNN.forward, ecg_cnn.py:52).
+ * unpack: blocked bf16 -> fp32 (B,C,L)  (hooks / parity checks). */
+int ecgb200_pack_input_bf16(const float* x, void* xb, int B, int Ci, int T, void* stream);
+int ecgb200_unpack_act_bf16(const void* xb, float* x, int B, int C, int L, void* stream);
+/* w fp32 (Co,Ci,15) -> wf bf16 [15][Cip/8][Co][8] (forward operand) and, unless NULL,
+ * wd bf16 [15][Co/8][Cip][8] (tap-flipped transpose: dgrad operand); Cip = Ci rounded up to 16. */
+int ecgb200_conv1d_prep_weights_bf16(const float* w, void* wf, void* wd, int Co, int Ci, void* stream);
+/* Conv1d(k=15,pad=7) as implicit GEMM on tcgen05: yb = conv(xb, wprep) + bias.
+ * Same call computes dgrad with (dy, wd, NULL).  Ci % 16 == 0, Co % 32 == 0, both <= 256.
+ * replaces aten::convolution (ecg_cnn.py:13) in bf16 mode. */
+int ecgb200_conv1d_fwd_bf16(const void* xb, const void* wprep, const float* bias, void* yb,
+                            int B, int Ci, int Co, int L, void* stream);
+
 /* ------------------------------------------- BatchNorm1d + ReLU + MaxPool1d --
  * Train-mode statistics from the conv epilogue partials (or from y itself when
  * stat_part == NULL): mean, biased var -> rstd; scale = gamma*rstd,

@@ -40,6 +40,10 @@ _SIGS = {
     "ecgb200_gradcam_f32": (_I, [_P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P]),
     "ecgb200_zscore_f32": (_I, [_P, _P, _I, _I, _P]),
     "ecgb200_row_mean_f32": (_I, [_P, _P, _I, _I, _P]),
+    "ecgb200_pack_input_bf16": (_I, [_P, _P, _I, _I, _I, _P]),
+    "ecgb200_unpack_act_bf16": (_I, [_P, _P, _I, _I, _I, _P]),
+    "ecgb200_conv1d_prep_weights_bf16": (_I, [_P, _P, _P, _I, _I, _P]),
+    "ecgb200_conv1d_fwd_bf16": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
 }
 
 EXPORTED = tuple(_SIGS)
