@@ -85,6 +85,25 @@ int ecgb200_conv1d_prep_weights_bf16(const float* w, void* wf, void* wd, int Co,
 int ecgb200_conv1d_fwd_bf16(const void* xb, const void* wprep, const float* bias, void* yb,
                             int B, int Ci, int Co, int L, void* stream);
 
+/* dW (Co,Ci,15) fp32 and db (Co) fp32 from blocked-bf16 dy [B][Co/8][L][8] and x [B][Cip/8][L][8]
+ * (Cip = Ci rounded up to 16) on tcgen05, accumulators resident in TMEM across the whole batch
+ * share of a CTA; split-K partials in ws (ecgb200_conv1d_wgrad_bf16_ws_bytes) are reduced in a
+ * fixed order.  db = sum over db_part[Co][ndb] (per-sample sums of dy written by
+ * ecgb200_bn_relu_pool_bwd_bf16) or 0 when db_part == NULL.  Co % 8 == 0, Co <= 256. */
+int ecgb200_conv1d_wgrad_bf16(const void* dyb, const void* xb, float* dw, float* db, const float* db_part,
+                              int ndb, void* ws, int B, int Ci, int Co, int L, void* stream);
+size_t ecgb200_conv1d_wgrad_bf16_ws_bytes(int B, int Ci, int Co, int L);
+/* Blocked-bf16 versions of the BatchNorm + ReLU + MaxPool (+GAP) block (ecg_cnn.py:14-16,46,62);
+ * statistics, bn_state, gap, dgap, dgamma, dbeta stay fp32.  ws: ecgb200_bn_bwd_ws_bytes(B,C). */
+int ecgb200_bn_train_stats_bf16(const void* yb, const float* gamma, const float* beta, float* running_mean,
+                                float* running_var, int64_t* num_batches_tracked, float* bn_state, void* ws,
+                                int B, int C, int L, float momentum, float eps, void* stream);
+int ecgb200_bn_relu_pool_fwd_bf16(const void* yb, const float* bn_state, void* pb, float* gap,
+                                  int B, int C, int L, void* stream);
+int ecgb200_bn_relu_pool_bwd_bf16(const void* yb, const float* bn_state, const void* dpb, const float* dgap,
+                                  void* dyb, float* dgamma, float* dbeta, float* db_part, void* ws,
+                                  int B, int C, int L, int train, void* stream);
+
 /* ------------------------------------------- BatchNorm1d + ReLU + MaxPool1d --
  * Train-mode statistics from the conv epilogue partials (or from y itself when
  * stat_part == NULL): mean, biased var -> rstd; scale = gamma*rstd,

@@ -44,6 +44,11 @@ _SIGS = {
     "ecgb200_unpack_act_bf16": (_I, [_P, _P, _I, _I, _I, _P]),
     "ecgb200_conv1d_prep_weights_bf16": (_I, [_P, _P, _P, _I, _I, _P]),
     "ecgb200_conv1d_fwd_bf16": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "ecgb200_conv1d_wgrad_bf16": (_I, [_P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _P]),
+    "ecgb200_conv1d_wgrad_bf16_ws_bytes": (_Z, [_I, _I, _I, _I]),
+    "ecgb200_bn_train_stats_bf16": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _P]),
+    "ecgb200_bn_relu_pool_fwd_bf16": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+    "ecgb200_bn_relu_pool_bwd_bf16": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
 }
 
 EXPORTED = tuple(_SIGS)

@@ -318,3 +318,273 @@ extern "C" int ecgb200_bn_relu_pool_bwd_f32(const float* y, const float* bn_stat
     }
     return ecg_launch_status();
 }
+
+// =====================================================================================
+// bf16 "blocked channels-last" variants  A[b][c/8][t][c%8]  (16 B = 8 channels of one step).
+// One block per (sample, channel chunk): every access is a coalesced 16-byte vector; the 8
+// per-channel BN constants sit in registers.  Statistics / reductions stay fp32 (+double merge).
+// =====================================================================================
+#include <cuda_bf16.h>
+
+__device__ __forceinline__ void bf8_unpack(const uint4 u, float* v) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+__device__ __forceinline__ uint4 bf8_pack(const float* v) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    return u;
+}
+
+// block-wide sum of NV floats per thread; result valid in thread 0 (and all of warp 0)
+template <int NV>
+__device__ __forceinline__ void block_sum_vec(float* v, float* sh /* [8][NV] */) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+    __syncthreads();
+    if (lane == 0)
+#pragma unroll
+        for (int i = 0; i < NV; ++i) sh[w * NV + i] = v[i];
+    __syncthreads();
+    if (w == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            float t = 0.f;
+            for (int j = 0; j < nw; ++j) t += sh[j * NV + i];
+            v[i] = t;
+        }
+    }
+    __syncthreads();
+}
+
+// {sum, centred M2} per (channel, sample): part[c][b], part[C + c][b]
+__global__ void __launch_bounds__(256)
+bn_stats_bf16_kernel(const uint4* __restrict__ y, float* __restrict__ part, int B, int C, int L) {
+    __shared__ float sh[8 * 8];
+    __shared__ float mean_s[8];
+    const int cc = blockIdx.x, b = blockIdx.y;
+    const uint4* yr = y + ((size_t)b * (C / 8) + cc) * L;
+    float s[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = 0.f;
+    for (int t = threadIdx.x; t < L; t += blockDim.x) {
+        float v[8];
+        bf8_unpack(__ldg(yr + t), v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] += v[i];
+    }
+    block_sum_vec<8>(s, sh);
+    if (threadIdx.x < 8) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (i == threadIdx.x) t = s[i];
+        mean_s[threadIdx.x] = t / (float)L;
+        part[(size_t)(cc * 8 + threadIdx.x) * B + b] = t;
+    }
+    __syncthreads();
+    float m[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { m[i] = mean_s[i]; q[i] = 0.f; }
+    for (int t = threadIdx.x; t < L; t += blockDim.x) {
+        float v[8];
+        bf8_unpack(__ldg(yr + t), v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float d = v[i] - m[i]; q[i] = fmaf(d, d, q[i]); }
+    }
+    block_sum_vec<8>(q, sh);
+    if (threadIdx.x < 8) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (i == threadIdx.x) t = q[i];
+        part[((size_t)C + cc * 8 + threadIdx.x) * B + b] = t;
+    }
+}
+
+extern "C" int ecgb200_bn_train_stats_bf16(const void* yb, const float* gamma, const float* beta,
+                                           float* running_mean, float* running_var, int64_t* nbt,
+                                           float* bn_state, void* ws, int B, int C, int L, float momentum,
+                                           float eps, void* stream) {
+    if (!yb || !gamma || !beta || !bn_state || !ws || B <= 0 || C <= 0 || (C & 7) || L <= 0) return ECGB200_EINVAL;
+    if (B > 65535) return ECGB200_EUNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int threads = L >= 256 ? 256 : (L >= 128 ? 128 : 64);
+    bn_stats_bf16_kernel<<<dim3(C / 8, B), threads, 0, st>>>((const uint4*)yb, (float*)ws, B, C, L);
+    int rc = ecg_launch_status();
+    if (rc) return rc;
+    bn_finalize_kernel<<<C, 256, 0, st>>>((const float*)ws, B, 1, L, L, gamma, beta, running_mean, running_var,
+                                          nbt, bn_state, C, momentum, eps);
+    return ecg_launch_status();
+}
+
+// p = maxpool2(relu(bn(y))) in the blocked layout; optional gap[b][c] = mean_j p
+__global__ void __launch_bounds__(256)
+bn_relu_pool_fwd_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__ bn_state,
+                             uint4* __restrict__ p, float* __restrict__ gap, int C, int L, int Lp) {
+    __shared__ float sh[8 * 8];
+    const int cc = blockIdx.x, b = blockIdx.y;
+    const uint4* yr = y + ((size_t)b * (C / 8) + cc) * L;
+    float sc[8], sf[8], acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        sc[i] = __ldg(bn_state + 2 * C + cc * 8 + i);
+        sf[i] = __ldg(bn_state + 3 * C + cc * 8 + i);
+        acc[i] = 0.f;
+    }
+    for (int j = threadIdx.x; j < Lp; j += blockDim.x) {
+        float a0[8], a1[8], m[8];
+        bf8_unpack(__ldg(yr + 2 * j), a0);
+        bf8_unpack(__ldg(yr + 2 * j + 1), a1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float r0 = fmaxf(fmaf(a0[i], sc[i], sf[i]), 0.f), r1 = fmaxf(fmaf(a1[i], sc[i], sf[i]), 0.f);
+            m[i] = fmaxf(r0, r1);
+            acc[i] += m[i];
+        }
+        if (p != nullptr) p[((size_t)b * (C / 8) + cc) * Lp + j] = bf8_pack(m);
+    }
+    if (gap != nullptr) {
+        block_sum_vec<8>(acc, sh);
+        if (threadIdx.x < 8) {
+            float t = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) if (i == threadIdx.x) t = acc[i];
+            gap[(size_t)b * C + cc * 8 + threadIdx.x] = t / (float)Lp;
+        }
+    }
+}
+
+extern "C" int ecgb200_bn_relu_pool_fwd_bf16(const void* yb, const float* bn_state, void* pb, float* gap,
+                                             int B, int C, int L, void* stream) {
+    if (!yb || !bn_state || (!pb && !gap) || B <= 0 || C <= 0 || (C & 7) || L < 2) return ECGB200_EINVAL;
+    if (B > 65535) return ECGB200_EUNSUPPORTED;
+    const int Lp = L / 2;
+    const int threads = Lp >= 256 ? 256 : (Lp >= 128 ? 128 : 64);
+    bn_relu_pool_fwd_bf16_kernel<<<dim3(C / 8, B), threads, 0, (cudaStream_t)stream>>>(
+        (const uint4*)yb, bn_state, (uint4*)pb, gap, C, L, Lp);
+    return ecg_launch_status();
+}
+
+// backward pass 1: partial {sum g, sum g*xhat} per (channel, sample) -> part[c][b], part[C+c][b]
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__ bn_state,
+                          const uint4* __restrict__ dp, const float* __restrict__ dgap,
+                          float* __restrict__ part, int B, int C, int L, int Lp) {
+    __shared__ float sh[8 * 16];
+    const int cc = blockIdx.x, b = blockIdx.y;
+    const uint4* yr = y + ((size_t)b * (C / 8) + cc) * L;
+    float mean[8], rstd[8], sc[8], sf[8], dc[8], s[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = cc * 8 + i;
+        mean[i] = __ldg(bn_state + c); rstd[i] = __ldg(bn_state + C + c);
+        sc[i] = __ldg(bn_state + 2 * C + c); sf[i] = __ldg(bn_state + 3 * C + c);
+        dc[i] = dgap != nullptr ? __ldg(dgap + (size_t)b * C + c) / (float)Lp : 0.f;
+        s[i] = 0.f; s[8 + i] = 0.f;
+    }
+    for (int j = threadIdx.x; j < Lp; j += blockDim.x) {
+        float a0[8], a1[8], d[8];
+        bf8_unpack(__ldg(yr + 2 * j), a0);
+        bf8_unpack(__ldg(yr + 2 * j + 1), a1);
+        if (dp != nullptr) bf8_unpack(__ldg(dp + ((size_t)b * (C / 8) + cc) * Lp + j), d);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const PoolGrad r = pool_grad(a0[i], a1[i], dp != nullptr ? d[i] : dc[i], mean[i], rstd[i], sc[i], sf[i]);
+            s[i] += r.g0 + r.g1;
+            s[8 + i] = fmaf(r.g0, r.xh0, fmaf(r.g1, r.xh1, s[8 + i]));
+        }
+    }
+    block_sum_vec<16>(s, sh);
+    if (threadIdx.x < 8) {
+        float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (i == threadIdx.x) { t1 = s[i]; t2 = s[8 + i]; }
+        part[(size_t)(cc * 8 + threadIdx.x) * B + b] = t1;
+        part[((size_t)C + cc * 8 + threadIdx.x) * B + b] = t2;
+    }
+}
+
+// backward pass 2: dy (blocked bf16) and per-(channel, sample) sums of dy for the conv-bias gradient
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__ bn_state,
+                         const uint4* __restrict__ dp, const float* __restrict__ dgap,
+                         const float* __restrict__ sums, uint4* __restrict__ dy, float* __restrict__ db_part,
+                         int B, int C, int L, int Lp, float inv_n, int train) {
+    __shared__ float sh[8 * 8];
+    const int cc = blockIdx.x, b = blockIdx.y;
+    const uint4* yr = y + ((size_t)b * (C / 8) + cc) * L;
+    uint4* dr = dy + ((size_t)b * (C / 8) + cc) * L;
+    float mean[8], rstd[8], sc[8], sf[8], dc[8], m1[8], m2[8], sdy[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = cc * 8 + i;
+        mean[i] = __ldg(bn_state + c); rstd[i] = __ldg(bn_state + C + c);
+        sc[i] = __ldg(bn_state + 2 * C + c); sf[i] = __ldg(bn_state + 3 * C + c);
+        dc[i] = dgap != nullptr ? __ldg(dgap + (size_t)b * C + c) / (float)Lp : 0.f;
+        m1[i] = train ? __ldg(sums + c) * inv_n : 0.f;
+        m2[i] = train ? __ldg(sums + C + c) * inv_n : 0.f;
+        sdy[i] = 0.f;
+    }
+    for (int j = threadIdx.x; j < Lp; j += blockDim.x) {
+        float a0[8], a1[8], d[8], o0[8], o1[8];
+        bf8_unpack(__ldg(yr + 2 * j), a0);
+        bf8_unpack(__ldg(yr + 2 * j + 1), a1);
+        if (dp != nullptr) bf8_unpack(__ldg(dp + ((size_t)b * (C / 8) + cc) * Lp + j), d);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const PoolGrad r = pool_grad(a0[i], a1[i], dp != nullptr ? d[i] : dc[i], mean[i], rstd[i], sc[i], sf[i]);
+            o0[i] = sc[i] * (r.g0 - m1[i] - r.xh0 * m2[i]);
+            o1[i] = sc[i] * (r.g1 - m1[i] - r.xh1 * m2[i]);
+            sdy[i] += o0[i] + o1[i];
+        }
+        dr[2 * j] = bf8_pack(o0);
+        dr[2 * j + 1] = bf8_pack(o1);
+        if (j == Lp - 1 && (L & 1)) {
+            float a[8], o[8];
+            bf8_unpack(__ldg(yr + L - 1), a);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                o[i] = sc[i] * (0.f - m1[i] - (a[i] - mean[i]) * rstd[i] * m2[i]);
+                sdy[i] += o[i];
+            }
+            dr[L - 1] = bf8_pack(o);
+        }
+    }
+    if (db_part != nullptr) {
+        block_sum_vec<8>(sdy, sh);
+        if (threadIdx.x < 8) {
+            float t = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) if (i == threadIdx.x) t = sdy[i];
+            db_part[(size_t)(cc * 8 + threadIdx.x) * B + b] = t;
+        }
+    }
+}
+
+// yb, dpb, dyb blocked bf16; dgap fp32 (B,C) [layer 4]; db_part fp32 [C][B] or NULL; ws as fp32 path.
+extern "C" int ecgb200_bn_relu_pool_bwd_bf16(const void* yb, const float* bn_state, const void* dpb,
+                                             const float* dgap, void* dyb, float* dgamma, float* dbeta,
+                                             float* db_part, void* ws, int B, int C, int L, int train,
+                                             void* stream) {
+    if (!yb || !bn_state || (!dpb && !dgap) || !dyb || !ws || B <= 0 || C <= 0 || (C & 7) || L < 2) return ECGB200_EINVAL;
+    if (B > 65535) return ECGB200_EUNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int Lp = L / 2;
+    float* part = (float*)ws;
+    float* sums = part + (size_t)2 * C * B;
+    const int threads = Lp >= 256 ? 256 : (Lp >= 128 ? 128 : 64);
+    bn_bwd_reduce_bf16_kernel<<<dim3(C / 8, B), threads, 0, st>>>((const uint4*)yb, bn_state, (const uint4*)dpb,
+                                                                 dgap, part, B, C, L, Lp);
+    int rc = ecg_launch_status();
+    if (rc) return rc;
+    bn_bwd_finalize_kernel<<<C, 128, 0, st>>>(part, sums, dgamma, dbeta, B, C);
+    rc = ecg_launch_status();
+    if (rc) return rc;
+    const float inv_n = 1.0f / ((float)B * (float)L);
+    bn_bwd_apply_bf16_kernel<<<dim3(C / 8, B), threads, 0, st>>>((const uint4*)yb, bn_state, (const uint4*)dpb, dgap,
+                                                                sums, (uint4*)dyb, db_part, B, C, L, Lp, inv_n, train);
+    return ecg_launch_status();
+}

@@ -59,7 +59,8 @@ def test_conv1d_fwd_bf16(B, Ci, Co, L):
     check(lib.ecgb200_conv1d_prep_weights_bf16(ptr(wg), ptr(wf), ptr(wd), Co, Ci, stream()), "prep")
     assert torch.equal(wf.cpu(), wr.permute(2, 1, 0).reshape(15, Ci // 8, 8, Co).permute(0, 1, 3, 2).contiguous().to(BF))
     yb = torch.full((B, Co // 8, L, 8), float("nan"), dtype=BF, device=DEV)
-    check(lib.ecgb200_conv1d_fwd_bf16(ptr(xb), ptr(wf), ptr(bias.to(DEV)), ptr(yb), B, Ci, Co, L, stream()), "conv_tc")
+    bias_g = bias.to(DEV)
+    check(lib.ecgb200_conv1d_fwd_bf16(ptr(xb), ptr(wf), ptr(bias_g), ptr(yb), B, Ci, Co, L, stream()), "conv_tc")
     torch.cuda.synchronize()
     y = from_blocked(yb.cpu(), Co)
     assert torch.isfinite(y).all()
@@ -72,6 +73,79 @@ def test_conv1d_fwd_bf16(B, Ci, Co, L):
     xr_ = xr.clone().requires_grad_(True)
     F.conv1d(xr_, wr, None, padding=7).backward(dyr)
     dxb = torch.full((B, Ci // 8, L, 8), float("nan"), dtype=BF, device=DEV)
-    check(lib.ecgb200_conv1d_fwd_bf16(ptr(to_blocked(dy).to(DEV)), ptr(wd), None, ptr(dxb), B, Co, Ci, L, stream()), "dgrad_tc")
+    dyb = to_blocked(dy).to(DEV)
+    check(lib.ecgb200_conv1d_fwd_bf16(ptr(dyb), ptr(wd), None, ptr(dxb), B, Co, Ci, L, stream()), "dgrad_tc")
     torch.cuda.synchronize()
     assert rel_inf(from_blocked(dxb.cpu(), Ci), xr_.grad) < 1e-2
+
+
+@pytest.mark.parametrize("B,Ci,Co,L", [(4, 12, 32, 1000), (3, 32, 64, 500), (5, 64, 128, 250), (6, 128, 256, 125),
+                                       (2, 128, 256, 625), (1, 32, 64, 40)])
+def test_conv1d_wgrad_bf16(B, Ci, Co, L):
+    Cip = (Ci + 15) // 16 * 16
+    x = torch.zeros(B, Cip, L); x[:, :Ci] = gen(B, Ci, L, seed=6)
+    dy = gen(B, Co, L, seed=7)
+    xr = x.to(BF).float()[:, :Ci]
+    dyr = dy.to(BF).float()
+    w = torch.zeros(Co, Ci, 15, requires_grad=True)
+    F.conv1d(xr, w, None, padding=7).backward(dyr)
+    ws = torch.empty(lib.ecgb200_conv1d_wgrad_bf16_ws_bytes(B, Ci, Co, L), dtype=torch.uint8, device=DEV)
+    dw = torch.full((Co, Ci, 15), float("nan"), device=DEV)
+    db = torch.full((Co,), float("nan"), device=DEV)
+    dbp = dyr.sum(dim=2).t().contiguous().to(DEV)                  # [Co][B] per-sample sums of dy
+    dyb, xb = to_blocked(dy).to(DEV), to_blocked(x).to(DEV)         # keep alive: the call is asynchronous
+    check(lib.ecgb200_conv1d_wgrad_bf16(ptr(dyb), ptr(xb), ptr(dw), ptr(db),
+                                        ptr(dbp), B, ptr(ws), B, Ci, Co, L, stream()), "wgrad_tc")
+    torch.cuda.synchronize()
+    assert rel_inf(dw, w.grad) < 2e-3, rel_inf(dw, w.grad)       # fp32 accumulation of exact bf16 products
+    assert rel_inf(db, dyr.sum(dim=(0, 2))) < 1e-4
+
+
+def _bn_ref(y, gamma, beta, train, use_gap, dout_seed=10):
+    C = y.shape[1]
+    rm, rv = torch.zeros(C), torch.ones(C)
+    h = F.batch_norm(y, rm, rv, gamma, beta, training=train, momentum=0.1, eps=1e-5)
+    p = F.max_pool1d(F.relu(h), 2)
+    out = p.mean(dim=2) if use_gap else p
+    dout = gen(*out.shape, seed=dout_seed)
+    if not use_gap:
+        dout = dout.to(BF).float()
+    out.backward(dout)
+    return p, out, dout, rm, rv
+
+
+@pytest.mark.parametrize("B,C,L", [(4, 32, 1000), (3, 64, 250), (5, 256, 125), (2, 128, 31)])
+@pytest.mark.parametrize("use_gap", [False, True])
+def test_bn_relu_pool_bf16(B, C, L, use_gap):
+    y = (gen(B, C, L, seed=5) * 1.7 + 0.3).to(BF).float().requires_grad_(True)      # exactly representable
+    gamma = (1 + 0.2 * gen(C, seed=6)).requires_grad_(True)
+    beta = (0.1 * gen(C, seed=7)).requires_grad_(True)
+    p_ref, out_ref, dout, rm, rv = _bn_ref(y, gamma, beta, True, use_gap)
+    yb = to_blocked(y.detach()).to(DEV)
+    gg, bg = gamma.detach().to(DEV), beta.detach().to(DEV)
+    rmg, rvg = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    nbt = torch.zeros((), dtype=torch.int64, device=DEV)
+    st = torch.empty(4, C, device=DEV)
+    ws = torch.empty(lib.ecgb200_bn_bwd_ws_bytes(B, C), dtype=torch.uint8, device=DEV)
+    check(lib.ecgb200_bn_train_stats_bf16(ptr(yb), ptr(gg), ptr(bg), ptr(rmg), ptr(rvg), ptr(nbt), ptr(st), ptr(ws),
+                                          B, C, L, 0.1, 1e-5, stream()), "bn_stats_bf16")
+    assert rel_inf(rmg, rm) < 1e-5 and rel_inf(rvg, rv) < 1e-5 and int(nbt) == 1
+    Lp = L // 2
+    pb = torch.empty(B, C // 8, Lp, 8, dtype=BF, device=DEV)
+    gap = torch.empty(B, C, device=DEV) if use_gap else None
+    check(lib.ecgb200_bn_relu_pool_fwd_bf16(ptr(yb), ptr(st), ptr(pb), ptr(gap), B, C, L, stream()), "bn_fwd_bf16")
+    assert rel_inf(from_blocked(pb.cpu(), C), p_ref) < 6e-3          # one bf16 rounding of the output
+    if use_gap:
+        assert rel_inf(gap, out_ref) < 1e-5                          # gap accumulates the unrounded fp32 values
+    dyb = torch.empty(B, C // 8, L, 8, dtype=BF, device=DEV)
+    dgm, dbt = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+    dbp = torch.empty(C, B, device=DEV)
+    dpb = None if use_gap else to_blocked(dout).to(DEV)
+    dgap = dout.to(DEV) if use_gap else None
+    check(lib.ecgb200_bn_relu_pool_bwd_bf16(ptr(yb), ptr(st), ptr(dpb), ptr(dgap), ptr(dyb), ptr(dgm), ptr(dbt),
+                                            ptr(dbp), ptr(ws), B, C, L, 1, stream()), "bn_bwd_bf16")
+    torch.cuda.synchronize()
+    assert rel_inf(dgm, gamma.grad) < 1e-4 and rel_inf(dbt, beta.grad) < 1e-4
+    dy = from_blocked(dyb.cpu(), C)
+    assert rel_inf(dy, y.grad) < 6e-3
+    assert float((dbp.sum(dim=1).cpu() - dy.sum(dim=(0, 2))).abs().max()) < 1e-2 * float(dy.abs().max()) * (B * L) ** 0.5
