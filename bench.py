@@ -152,14 +152,14 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------- roofline helpers
-def kernel_model(name: str, B: int, chan, Ls, dtype_bytes: int = 4):
+def kernel_model(name: str, B: int, chan, Ls, dtype_bytes: int = 4, cin_pad: int = 0):
     """Algorithmic FLOPs and HBM bytes of one C-ABI call of the step (SURVEY 8d model)."""
     if "_L" not in name:
         return None
     base, l = name.rsplit("_L", 1)
     l = int(l) - 1
     ci, co, L = chan[l], chan[l + 1], Ls[l]
-    flops = 2.0 * B * L * co * ci * 15
+    flops = 2.0 * B * L * co * ci * 15                    # algorithmic: real input channels only
     xin, yout = B * ci * L * dtype_bytes, B * co * L * dtype_bytes
     if base in ("conv_fwd", "wgrad", "dgrad"):
         return {"flops": flops, "bytes": xin + yout}
@@ -192,12 +192,12 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, T, K, W = args.batch, args.seq_len, args.steps, max(args.warmup, 3)
-    precision = "fp32" if args.precision == "auto" else args.precision
+    precision = "bf16" if args.precision == "auto" else args.precision      # BASELINE metric is quoted in bf16
 
     torch.manual_seed(42)
     model = P.ECGCNN(12, 256, 5).to(dev).train()
     opt = P.FusedAdamW(model.parameters(), lr=1.5e-3, weight_decay=1e-4)
-    eng = TrainStep(model, opt, B, T)
+    eng = TrainStep(model, opt, B, T, precision=precision)
 
     # synthetic data: NB distinct batches, resident on device and in pinned host memory
     NB = 8
@@ -286,7 +286,7 @@ def main():
         prof = eng.profile_kernels(iters=5)
         tot = sum(t for _, t in prof)
         name, t_ms = max(prof, key=lambda kv: kv[1])
-        km = kernel_model(name, B, eng.chan, eng.L)
+        km = kernel_model(name, B, eng.chan, eng.L, dtype_bytes=2 if precision == "bf16" else 4)
         ridge = pk["tf_burst"] * 1e12 / (pk["hbm_gbs"] * 1e9)
         if km and km["flops"] > 0 and km["flops"] / max(km["bytes"], 1.0) > ridge:
             ach = km["flops"] / (t_ms * 1e-3) / 1e12

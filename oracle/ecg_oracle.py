@@ -205,6 +205,65 @@ def train_step(sd: StateDict, x: Tensor, y: Tensor, st: Optional[AdamWState],
 
 
 # --------------------------------------------------------------------------
+# bf16 compute mode.  The reference is fp32-only (configs/*.yaml `amp: true` is never read,
+# SURVEY D5), so bf16 has no reference semantics to restate; this is the DEFINITION the CUDA
+# path is held to: the fp32 algorithm above with values rounded to bf16 (round-to-nearest-even)
+# exactly where the tensor-core path stores bf16 -- the network input, the conv weights
+# (straight-through to the fp32 master weights), every conv output and every pooled output
+# that feeds another conv -- and with the gradients rounded to bf16 at the same two points.
+# Everything else (accumulation, BN statistics, head, loss, optimizer) is fp32.
+# --------------------------------------------------------------------------
+class _RoundBF16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t, round_grad):
+        ctx.round_grad = round_grad
+        return t.to(torch.bfloat16).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.round_grad:
+            g = g.to(torch.bfloat16).to(torch.float32)
+        return g, None
+
+
+def _rb(t, round_grad=True):
+    return _RoundBF16.apply(t, round_grad)
+
+
+def bf16_train_step(sd: StateDict, x: Tensor, y: Tensor, demo: Optional[Tensor] = None):
+    """One forward + backward in the emulated bf16 mode (no optimizer, running stats untouched).
+    Returns dict(loss, logits, grads) like train_step."""
+    keys = param_keys(sd)
+    leaves = {k: sd[k].detach().clone().requires_grad_(True) for k in keys}
+    work = dict(sd)
+    work.update(leaves)
+    prefix = "" if demo is None else "ecg_backbone."
+    h = _rb(x, False)
+    g = None
+    for i in range(len(CHANNELS)):
+        p = f"{prefix}backbone.{i}."
+        a = F.conv1d(h, _rb(work[p + "net.0.weight"], False), work[p + "net.0.bias"], padding=KSIZE // 2)
+        a = _rb(a)                                                # conv output stored as bf16; dy rounded
+        bn = F.batch_norm(a, work[p + "net.1.running_mean"].clone(), work[p + "net.1.running_var"].clone(),
+                          work[p + "net.1.weight"], work[p + "net.1.bias"], training=True,
+                          momentum=BN_MOMENTUM, eps=BN_EPS)
+        pooled = F.max_pool1d(F.relu(bn), 2)
+        if i < len(CHANNELS) - 1:
+            h = _rb(pooled)                                       # next conv's input; dp rounded
+        else:
+            g = pooled.mean(dim=2)                                # gap from the unrounded fp32 values
+    z = F.linear(g, work[prefix + "proj.weight"], work[prefix + "proj.bias"])
+    if demo is not None:
+        film = F.linear(demo_encoder(work, demo), work["film_gen.weight"], work["film_gen.bias"])
+        gamma, beta = torch.chunk(film, 2, dim=-1)
+        z = (1.0 + torch.tanh(gamma)) * z + beta
+    logits = F.linear(z, work["head.weight"], work["head.bias"])
+    loss = bce_with_logits(logits, y)
+    gs = torch.autograd.grad(loss, [leaves[k] for k in keys])
+    return {"loss": loss.detach(), "logits": logits.detach(), "grads": dict(zip(keys, gs))}
+
+
+# --------------------------------------------------------------------------
 # Grad-CAM.  V1 = src/interpretability/grad_cam_1d.py:53-103;
 # V2 = scripts/00_demo_inference.py:39-61 and scripts/13_grad_cam_af.py:51-76;
 # V3 = scripts/12_grad_cam_ecg_demo.py:44-75.

@@ -29,7 +29,7 @@ F32 = torch.float32
 
 
 def _p(t: Optional[torch.Tensor], off: int = 0):
-    return None if t is None else t.data_ptr() + 4 * off
+    return None if t is None else t.data_ptr() + t.element_size() * off
 
 
 class _Seg:
@@ -42,7 +42,7 @@ class _Seg:
 
 class TrainStep:
     def __init__(self, model, optimizer: FusedAdamW, batch_size: int, seq_len: int,
-                 process_group=None, use_graph: bool = True):
+                 process_group=None, use_graph: bool = True, precision: str = "fp32"):
         if not isinstance(model, (ECGCNN, ECGMultimodal)):
             raise EcgB200Error("TrainStep drives ecgb200 ECGCNN / ECGMultimodal models")
         if not isinstance(optimizer, FusedAdamW) or len(optimizer.param_groups) != 1:
@@ -51,6 +51,10 @@ class TrainStep:
         self.mm = isinstance(model, ECGMultimodal)
         self.bb = model.ecg_backbone if self.mm else model
         self.B, self.T = int(batch_size), int(seq_len)
+        if precision not in ("fp32", "bf16"):
+            raise EcgB200Error("precision must be 'fp32' (CUDA-core exact path) or 'bf16' (tcgen05 path)")
+        self.bf16 = precision == "bf16"
+        self.precision = precision
         if self.T < 16:
             raise EcgB200Error("seq_len must be >= 16 (four MaxPool1d(2) stages)")
         self.pg = process_group
@@ -133,13 +137,27 @@ class TrainStep:
         self.ybuf, self.stat, self.bnst, self.wt, self.wd = [], [], [], [], []
         for l in range(4):
             ci, co, L = self.chan[l], self.chan[l + 1], self.L[l]
+            self.bnst.append(e(4, co))
+            if self.bf16:
+                continue
             self.ybuf.append(e(B, co, L))
             self.stat.append(e(2, co, lib.ecgb200_conv1d_stat_tiles(B, L)))
-            self.bnst.append(e(4, co))
             self.wt.append(e(ci, 15, co))
             self.wd.append(e(co, 15, ci) if l > 0 else None)
             if l < 3:
                 self.acts.append(e(B, co, L // 2))
+        if self.bf16:
+            eb = lambda *s: torch.empty(*s, dtype=torch.bfloat16, device=dev)   # noqa: E731
+            if any(c % 32 for c in self.chan[1:]) or max(self.chan[1:]) > 256:
+                raise EcgB200Error("bf16 path needs conv widths that are multiples of 32 and <= 256")
+            self.cip = [(self.chan[0] + 15) // 16 * 16] + self.chan[1:4]          # padded input widths
+            # blocked channels-last bf16 activations  [B][C/8][L][8]
+            self.acts = [eb(B, self.cip[0] // 8, T, 8)] + [eb(B, self.chan[l + 1] // 8, self.L[l] // 2, 8) for l in range(3)]
+            self.ybuf = [eb(B, self.chan[l + 1] // 8, self.L[l], 8) for l in range(4)]
+            self.wt = [eb(15, self.cip[l] // 8, self.chan[l + 1], 8) for l in range(4)]
+            self.wd = [None] + [eb(15, self.chan[l + 1] // 8, self.cip[l], 8) for l in range(1, 4)]
+            self.dbpart = [e(self.chan[l + 1], B) for l in range(4)]
+            self.stat = [None] * 4
         c4 = self.chan[4]
         self.gap = e(B, c4)
         self.dgap = e(B, c4)
@@ -156,9 +174,14 @@ class TrainStep:
             self.film, self.dfilm = e(B, 2 * self.feat), e(B, 2 * self.feat)
             self.zc, self.dzc = e(B, self.feat), e(B, self.feat)
         big = B * 32 * T                                          # every conv output has 32*T elems/sample
-        self.dy = e(max(B * co * L for co, L in zip(self.chan[1:], self.L)))
-        self.dp = e(max(B * self.chan[l] * self.L[l] for l in range(1, 4)))
-        ws = max(lib.ecgb200_conv1d_wgrad_ws_bytes(B, self.chan[l], self.chan[l + 1], self.L[l]) for l in range(4))
+        act_dt = torch.bfloat16 if self.bf16 else F32
+        self.dy = torch.empty(max(B * co * L for co, L in zip(self.chan[1:], self.L)), dtype=act_dt, device=dev)
+        self.dp = torch.empty(max(B * self.chan[l] * self.L[l] for l in range(1, 4)), dtype=act_dt, device=dev)
+        wsfn = lib.ecgb200_conv1d_wgrad_bf16_ws_bytes if self.bf16 else lib.ecgb200_conv1d_wgrad_ws_bytes
+        ws = max(wsfn(B, self.chan[l], self.chan[l + 1], self.L[l]) for l in range(4))
+        if self.bf16:
+            ws = max(ws, max(lib.ecgb200_bn_bwd_ws_bytes(B, c) for c in self.chan[1:]))
+            self.ws2 = torch.empty(max(lib.ecgb200_bn_bwd_ws_bytes(B, c) for c in self.chan[1:]), dtype=torch.uint8, device=dev)
         ws = max(ws, max(lib.ecgb200_bn_bwd_ws_bytes(B, c) for c in self.chan[1:]))
         self.ws = torch.empty(ws, dtype=torch.uint8, device=dev)
         del big
@@ -180,15 +203,9 @@ class TrainStep:
     def _seg_ptr(self, name, buf):
         return buf.data_ptr() + 4 * self.seg[name].off
 
-    def _enqueue(self):
-        st = torch.cuda.current_stream(self.dev).cuda_stream
+    def _fwd_blocks_fp32(self, st, pre, Pp, blocks):
         B = self.B
         n = 0
-        pre = "ecg_backbone." if self.mm else ""
-        Pp = lambda k: self._seg_ptr(k, self.P)       # noqa: E731
-        Gp = lambda k: self._seg_ptr(k, self.G)       # noqa: E731
-        blocks = list(self.bb.backbone)
-        # ---- forward
         for l in range(4):
             ci, co, L = self.chan[l], self.chan[l + 1], self.L[l]
             k = f"{pre}backbone.{l}.net."
@@ -205,6 +222,84 @@ class TrainStep:
                                                    _p(self.acts[l + 1]) if l < 3 else None,
                                                    _p(self.gap) if l == 3 else None, B, co, L, st)
             n += 4
+        return n
+
+    def _fwd_blocks_bf16(self, st, pre, Pp, blocks):
+        """tcgen05 path: pack the fp32 (B,12,T) input once, then per block
+        weight re-layout -> implicit-GEMM conv -> batch statistics -> BN+ReLU+pool, all on
+        blocked channels-last bf16 activations."""
+        B = self.B
+        n = 0
+        self._prof_tag = ""
+        self._k("pack_input", lib.ecgb200_pack_input_bf16, _p(self.x), _p(self.acts[0]), B, self.chan[0], self.T, st)
+        n += 1
+        for l in range(4):
+            ci, cip, co, L = self.chan[l], self.cip[l], self.chan[l + 1], self.L[l]
+            k = f"{pre}backbone.{l}.net."
+            bn = blocks[l].net[1]
+            self._prof_tag = f"_L{l + 1}"
+            self._k("prep", lib.ecgb200_conv1d_prep_weights_bf16, Pp(k + "0.weight"), _p(self.wt[l]), _p(self.wd[l]), co, ci, st)
+            self._k("conv_fwd", lib.ecgb200_conv1d_fwd_bf16, _p(self.acts[l]), _p(self.wt[l]), Pp(k + "0.bias"),
+                    _p(self.ybuf[l]), B, cip, co, L, st)
+            self._k("bn_stats", lib.ecgb200_bn_train_stats_bf16, _p(self.ybuf[l]), Pp(k + "1.weight"), Pp(k + "1.bias"),
+                    bn.running_mean.data_ptr(), bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(),
+                    _p(self.bnst[l]), _p(self.ws2), B, co, L, float(bn.momentum), float(bn.eps), st)
+            self._k("bn_relu_pool", lib.ecgb200_bn_relu_pool_fwd_bf16, _p(self.ybuf[l]), _p(self.bnst[l]),
+                    _p(self.acts[l + 1]) if l < 3 else None, _p(self.gap) if l == 3 else None, B, co, L, st)
+            n += 5
+        return n
+
+    def _bwd_blocks(self, st, pre, Pp, Gp):
+        B = self.B
+        n = 0
+        main = torch.cuda.current_stream(self.dev)
+        for l in (3, 2, 1, 0):
+            ci, co, L = self.chan[l], self.chan[l + 1], self.L[l]
+            k = f"{pre}backbone.{l}.net."
+            self._prof_tag = f"_L{l + 1}"
+            if self.bf16:
+                self._k("bn_bwd", lib.ecgb200_bn_relu_pool_bwd_bf16, _p(self.ybuf[l]), _p(self.bnst[l]),
+                        _p(self.dp) if l < 3 else None, _p(self.dgap) if l == 3 else None, _p(self.dy),
+                        Gp(k + "1.weight"), Gp(k + "1.bias"), _p(self.dbpart[l]), _p(self.ws2), B, co, L, 1, st)
+                self._k("wgrad", lib.ecgb200_conv1d_wgrad_bf16, _p(self.dy), _p(self.acts[l]), Gp(k + "0.weight"),
+                        Gp(k + "0.bias"), _p(self.dbpart[l]), B, _p(self.ws), B, ci, co, L, st)
+            else:
+                self._k("bn_bwd", lib.ecgb200_bn_relu_pool_bwd_f32, _p(self.ybuf[l]), _p(self.bnst[l]), Pp(k + "1.weight"),
+                        _p(self.dp) if l < 3 else None, _p(self.dgap) if l == 3 else None,
+                        _p(self.dy), Gp(k + "1.weight"), Gp(k + "1.bias"), _p(self.ws), B, co, L, 1, st)
+                self._k("wgrad", lib.ecgb200_conv1d_wgrad_f32, _p(self.dy), _p(self.acts[l]), Gp(k + "0.weight"),
+                        Gp(k + "0.bias"), _p(self.ws), B, ci, co, L, st)
+            n += 5
+            if l == 3 and self.world > 1:
+                # bucket A (block 4, the tail of G) is final: all-reduce it while blocks 3..1 run
+                ev = torch.cuda.Event()
+                ev.record(main)
+                self.side.wait_event(ev)
+                with torch.cuda.stream(self.side):
+                    torch.distributed.all_reduce(self.G[self.bucket_a_off:], group=self.pg)
+            if l > 0:
+                if self.bf16:
+                    self._k("dgrad", lib.ecgb200_conv1d_fwd_bf16, _p(self.dy), _p(self.wd[l]), None, _p(self.dp),
+                            B, co, ci, L, st)
+                else:
+                    self._k("dgrad", lib.ecgb200_conv1d_fwd_f32, _p(self.dy), _p(self.wd[l]), None, _p(self.dp), None,
+                            B, co, ci, L, st)
+                n += 1
+        return n
+
+    def _enqueue(self):
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        B = self.B
+        n = 0
+        pre = "ecg_backbone." if self.mm else ""
+        Pp = lambda k: self._seg_ptr(k, self.P)       # noqa: E731
+        Gp = lambda k: self._seg_ptr(k, self.G)       # noqa: E731
+        blocks = list(self.bb.backbone)
+        # ---- forward
+        if self.bf16:
+            n += self._fwd_blocks_bf16(st, pre, Pp, blocks)
+        else:
+            n += self._fwd_blocks_fp32(st, pre, Pp, blocks)
         self._prof_tag = ""
         c4, F_, NL = self.chan[4], self.feat, self.nl
         self._k("proj", lib.ecgb200_linear_fwd_f32, _p(self.gap), Pp(pre + "proj.weight"), Pp(pre + "proj.bias"), _p(self.z),
@@ -246,29 +341,7 @@ class TrainStep:
                                          Gp(pre + "proj.weight"), Gp(pre + "proj.bias"), B, c4, F_, st)
         n += 3
         # ---- backward: conv blocks 4..1
-        main = torch.cuda.current_stream(self.dev)
-        for l in (3, 2, 1, 0):
-            ci, co, L = self.chan[l], self.chan[l + 1], self.L[l]
-            k = f"{pre}backbone.{l}.net."
-            self._prof_tag = f"_L{l + 1}"
-            self._k("bn_bwd", lib.ecgb200_bn_relu_pool_bwd_f32, _p(self.ybuf[l]), _p(self.bnst[l]), Pp(k + "1.weight"),
-                                                   _p(self.dp) if l < 3 else None, _p(self.dgap) if l == 3 else None,
-                                                   _p(self.dy), Gp(k + "1.weight"), Gp(k + "1.bias"), _p(self.ws),
-                                                   B, co, L, 1, st)
-            self._k("wgrad", lib.ecgb200_conv1d_wgrad_f32, _p(self.dy), _p(self.acts[l]), Gp(k + "0.weight"), Gp(k + "0.bias"),
-                                               _p(self.ws), B, ci, co, L, st)
-            n += 5
-            if l == 3 and self.world > 1:
-                # bucket A (block 4, the tail of G) is final: all-reduce it while blocks 3..1 run
-                ev = torch.cuda.Event()
-                ev.record(main)
-                self.side.wait_event(ev)
-                with torch.cuda.stream(self.side):
-                    torch.distributed.all_reduce(self.G[self.bucket_a_off:], group=self.pg)
-            if l > 0:
-                self._k("dgrad", lib.ecgb200_conv1d_fwd_f32, _p(self.dy), _p(self.wd[l]), None, _p(self.dp), None,
-                                                 B, co, ci, L, st)
-                n += 1
+        n += self._bwd_blocks(st, pre, Pp, Gp)
         # ---- gradient exchange + optimizer
         self._prof_tag = ""
         if self.world > 1:

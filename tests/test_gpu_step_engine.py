@@ -80,3 +80,61 @@ def test_engine_rejects_wrong_shapes_and_cpu():
         eng(torch.zeros(3, 12, 256, device=DEV), torch.zeros(3, 5, device=DEV))
     with pytest.raises(P.EcgB200Error):
         TrainStep(P.ECGCNN(12, 256, 5), P.FusedAdamW(P.ECGCNN(12, 256, 5).parameters()), 4, 256)
+
+
+def _cos(a, b):
+    a = a.detach().double().cpu().flatten(); b = b.detach().double().cpu().flatten()
+    return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-300))
+
+
+@pytest.mark.parametrize("kind,nl,B,T,lr", [("cnn", 5, 8, 1000, 1.5e-3), ("mm", 5, 6, 1000, 1e-4), ("cnn", 1, 2, 5000, 1e-3)])
+def test_bf16_engine(kind, nl, B, T, lr):
+    """bf16 tensor-core mode (tcgen05 convs, bf16 activations/gradients in HBM, fp32 master
+    weights, fp32 BN statistics / head / loss / optimizer).  The reference has no bf16 mode
+    (SURVEY D5); its definition is oracle.bf16_train_step (fp32 algorithm + bf16 rounding at the
+    storage points).  Stated tolerances:
+      vs the bf16 definition : logits rel_inf <= 5e-3, loss <= 1e-3 rel,
+                               every gradient tensor 1-cos <= 3e-3 and rel_inf <= 0.15
+      vs the fp32 oracle     : logits rel_inf <= 3e-2, loss <= 2e-2 rel, gradient 1-cos <= 3e-2
+    Element-wise agreement of conv gradients cannot be tighter: a conv output that lands within
+    fp32 accumulation error of a bf16 rounding boundary rounds differently in two correct
+    implementations, and the 1-ulp (0.4 %) difference can flip ReLU / MaxPool routing downstream.
+    Measured on B200: 1-cos ~8e-4 vs the definition, while the definition itself sits at
+    1-cos ~1e-2 from fp32.  (conv-bias grads are ~0 on both sides: absolute bound only)."""
+    batch = O.synth_batch(B, T, nl, seed=5, with_demo=(kind == "mm"))
+    x, y = batch[0], batch[-1]
+    demo = batch[1] if kind == "mm" else None
+    sd = O.init_state_dict(kind, nl, seed=42)
+    ref32 = O.train_step(O.clone_sd(sd), x, y, None, demo=demo)
+    ref16 = O.bf16_train_step(sd, x, y, demo=demo)
+    model = _mk(kind, nl)
+    opt = P.FusedAdamW(model.parameters(), lr=lr, weight_decay=1e-4)
+    eng = TrainStep(model, opt, B, T, precision="bf16", use_graph=False)
+    loss = float(eng(x.to(DEV), y.to(DEV), demo.to(DEV) if demo is not None else None))
+    assert rel_inf(eng.logits, ref16["logits"]) < 5e-3, rel_inf(eng.logits, ref16["logits"])
+    assert abs(loss - float(ref16["loss"])) < 1e-3 * float(ref16["loss"])
+    assert rel_inf(eng.logits, ref32["logits"]) < 3e-2
+    assert abs(loss - float(ref32["loss"])) < 2e-2 * float(ref32["loss"])
+    gmax = max(float(g.abs().max()) for g in ref32["grads"].values())
+    w16 = wcos = 0.0
+    for k, p in model.named_parameters():
+        if k.endswith("net.0.bias"):
+            assert float(p.grad.abs().max()) < 1e-2 * gmax, k
+            continue
+        r = rel_inf(p.grad, ref16["grads"][k])
+        c = _cos(p.grad, ref32["grads"][k])
+        c16 = _cos(p.grad, ref16["grads"][k])
+        print(f"   {k:40s} rel_inf(def) {r:.2e}  1-cos(def) {1 - c16:.2e}  1-cos(fp32) {1 - c:.2e}  "
+              f"[def vs fp32: 1-cos {1 - _cos(ref16['grads'][k], ref32['grads'][k]):.2e}]")
+        w16, wcos = max(w16, r), max(wcos, 1 - c)
+        assert 1 - c16 < 3e-3 and r < 0.15, (k, r, 1 - c16)
+        assert 1 - c < 3e-2, (k, 1 - c)
+    print(f"bf16 {kind}: worst grad rel_inf vs bf16 definition {w16:.2e}; worst 1-cos vs fp32 oracle {wcos:.2e}")
+    # graph replay of the bf16 step is bit-identical to the eager enqueue
+    m2 = _mk(kind, nl)
+    o2 = P.FusedAdamW(m2.parameters(), lr=lr, weight_decay=1e-4)
+    e2 = TrainStep(m2, o2, B, T, precision="bf16", use_graph=True)
+    l2 = float(e2(x.to(DEV), y.to(DEV), demo.to(DEV) if demo is not None else None))
+    assert l2 == loss
+    for (k, a), (_, b) in zip(model.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
