@@ -268,10 +268,16 @@ extern "C" int ecgb200_conv1d_fwd_bf16(const void* xb, const void* wprep, const 
 
 // ---------------------------------------------------------------- wgrad implicit GEMM
 // dW_k[o, c] = sum_{b,t} dY[b, t, o] * X[b, t+k-7, c]        (K = time, both operands MN-major)
-// CTA tile: 128 output channels (TMEM lanes) x NCB input channels x all 15 taps
-// (15*NCB <= 480 TMEM columns), accumulated IN TMEM over the CTA's whole share of
+//
+// "Taps as N": for ONE 8-channel chunk of X, the 16-byte rows of the staged tile are
+// [row][8 ch]; a B operand whose N-chunk stride (SBO) is 16 bytes -- one row -- makes N-chunk n
+// the same chunk shifted by n rows, i.e. tap n.  So a single tcgen05.mma with N = 128 computes
+// all 15 taps (+1 unused) of 8 input channels:  D[o][(k, c8)] += dY^T[o][t] * X[t + k][c8].
+// That is 8x fewer MMA instructions than one instruction per (tap, 32 channels), which matters
+// because a single thread issues them.  CTA tile: 128 output channels (TMEM lanes) x up to 4
+// channel chunks (4 x 128 = 512 TMEM columns), accumulated IN TMEM over the CTA's whole share of
 // (sample, 128-step time tile) work items; one epilogue per CTA writes a split-K partial
-// part[z][k][o][c] that wgrad_tc_reduce_kernel sums in a fixed order (deterministic).
+// part[z][o][c/8][16][8] that wgrad_tc_reduce_kernel sums in a fixed order (deterministic).
 constexpr int WT_NST = 3;
 constexpr int WT_DY_BYTES = 16 * 128 * 16;       // [<=16 chunks][128 rows][8] bf16
 constexpr int WT_X_BYTES = 4 * TC_ROWS * 16;     // [<=4 chunks][144 rows][8] bf16
@@ -279,7 +285,7 @@ constexpr int WT_STAGE = WT_DY_BYTES + WT_X_BYTES;
 
 __global__ void __launch_bounds__(192, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant__ CUtensorMap xmap,
-                float* __restrict__ part, int Co, int Cip, int L, int B, int ncb, int ochunks) {
+                float* __restrict__ part, int Co, int Cip, int L, int B, int ncc, int ochunks) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty = full + WT_NST;
@@ -293,7 +299,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant
     const int items = B * tiles_t;
     const int nloc = (items - z + S - 1) / S;            // items z, z+S, ...   (host guarantees >= 1)
     const uint32_t dybytes = (uint32_t)ochunks * 128 * 16;
-    const uint32_t xbytes = (uint32_t)(ncb / 8) * TC_ROWS * 16;
+    const uint32_t xbytes = (uint32_t)ncc * TC_ROWS * 16;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < WT_NST; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(empty + i, 1); }
@@ -319,12 +325,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant
                 uint8_t* st = stages + (size_t)slot * WT_STAGE;
                 tc::mbar_arrive_expect_tx(full + slot, dybytes + xbytes);
                 tc::tma_load_4d(st, &dymap, full + slot, 0, t0, ob * 16, b);
-                tc::tma_load_4d(st + WT_DY_BYTES, &xmap, full + slot, 0, t0 - ECG_PAD, cb * (ncb / 8), b);
+                tc::tma_load_4d(st + WT_DY_BYTES, &xmap, full + slot, 0, t0 - ECG_PAD, cb * ncc, b);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = tc::make_idesc_bf16(128, ncb, 1, 1);
+            const uint32_t idesc = tc::make_idesc_bf16(128, 128, 1, 1);
             const uint32_t st_addr = tc::smem_u32(stages);
             for (int n = 0; n < nloc; ++n) {
                 const int slot = n % WT_NST;
@@ -333,14 +339,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant
                 const uint32_t dy_addr = st_addr + slot * WT_STAGE;
                 const uint32_t x_addr = dy_addr + WT_DY_BYTES;
 #pragma unroll 1
-                for (int k = 0; k < ECG_KS; ++k) {
+                for (int i = 0; i < ncc; ++i) {
 #pragma unroll
                     for (int j = 0; j < TC_TILE_M / 16; ++j) {
                         // A = dY^T: M (o) chunks 128*16 B apart, K (t) 8-row groups 128 B apart
                         const uint64_t ad = tc::make_desc(dy_addr + (uint32_t)j * 256, 128, 128 * 16);
-                        // B = X:    N (c) chunks 144*16 B apart, K (t) groups 128 B apart, tap shift k rows
-                        const uint64_t bd = tc::make_desc(x_addr + (uint32_t)(16 * j + k) * 16, 128, TC_ROWS * 16);
-                        tc::mma_bf16(tmem_base + (uint32_t)(k * ncb), ad, bd, idesc, (n > 0 || j > 0) ? 1u : 0u);
+                        // B = X chunk i: N chunk n = tap n = the chunk shifted by n rows (SBO = 16 B)
+                        const uint64_t bd = tc::make_desc(x_addr + (uint32_t)i * (TC_ROWS * 16) + (uint32_t)j * 256, 128, 16);
+                        tc::mma_bf16(tmem_base + (uint32_t)(i * 128), ad, bd, idesc, (n > 0 || j > 0) ? 1u : 0u);
                     }
                 }
                 tc::mma_commit(empty + slot);
@@ -353,15 +359,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant
         tc::mbar_wait(accfull, 0);
         tc::fence_after_sync();
         const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16);
-        for (int k = 0; k < ECG_KS; ++k) {
-            float v[32];
-            if (ncb == 32) tc::tmem_ld32(taddr + (uint32_t)(k * 32), v);
-            else tc::tmem_ld16(taddr + (uint32_t)(k * 16), v);
-            tc::tmem_ld_wait();
-            if (o < Co) {
-                float* dst = part + (((size_t)z * ECG_KS + k) * Co + o) * Cip + (size_t)cb * ncb;
-                for (int i = 0; i < ncb; i += 4)
-                    *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        for (int i = 0; i < ncc; ++i) {
+#pragma unroll 1
+            for (int g = 0; g < 4; ++g) {
+                float v[32];
+                tc::tmem_ld32(taddr + (uint32_t)(i * 128 + g * 32), v);
+                tc::tmem_ld_wait();
+                if (o < Co) {
+                    float* dst = part + ((((size_t)z * Co + o) * (Cip / 8) + cb * ncc + i) * 16 + 4 * g) * 8;
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4)
+                        *reinterpret_cast<float4*>(dst + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+                }
             }
         }
     }
@@ -370,21 +379,30 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant
     if (warp == 2) tc::tmem_dealloc(tmem_base, 512);
 }
 
-// dW[o][c][k] = sum_z part[z][k][o][c]  (c < Ci);  db[o] = sum_j db_part[o][j]
+// dW[o][c][k] = sum_z part[z][o][c/8][k][c%8]  (c < Ci, k < 15);  db[o] = sum_j db_part[o][j]
 __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ part, const float* __restrict__ db_part,
                                        float* __restrict__ dw, float* __restrict__ db, int S, int Co,
                                        int Ci, int Cip, int ndb) {
-    const int n = ECG_KS * Co * Cip;
+    const int nout = Co * Ci * ECG_KS;
+    const size_t zstride = (size_t)Co * Cip * 16;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        const int c = i % Cip;
-        const int o = (i / Cip) % Co;
-        const int k = i / (Cip * Co);
-        float s = 0.f;
-        for (int z = 0; z < S; ++z) s += part[(size_t)z * n + i];
-        if (c < Ci) dw[((size_t)o * Ci + c) * ECG_KS + k] = s;
-    } else if (i < n + Co && db != nullptr) {
-        const int o = i - n;
+    if (i < nout) {
+        const int k = i % ECG_KS;
+        const int c = (i / ECG_KS) % Ci;
+        const int o = i / (ECG_KS * Ci);
+        const float* src = part + (((size_t)o * (Cip / 8) + (c >> 3)) * 16 + k) * 8 + (c & 7);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int z = 0;
+        for (; z + 4 <= S; z += 4) {
+            s0 += src[(size_t)z * zstride];
+            s1 += src[(size_t)(z + 1) * zstride];
+            s2 += src[(size_t)(z + 2) * zstride];
+            s3 += src[(size_t)(z + 3) * zstride];
+        }
+        for (; z < S; ++z) s0 += src[(size_t)z * zstride];
+        dw[i] = (s0 + s1) + (s2 + s3);
+    } else if (i < nout + Co && db != nullptr) {
+        const int o = i - nout;
         float s = 0.f;
         if (db_part != nullptr)
             for (int j = 0; j < ndb; ++j) s += db_part[(size_t)o * ndb + j];
@@ -392,9 +410,9 @@ __global__ void wgrad_tc_reduce_kernel(const float* __restrict__ part, const flo
     }
 }
 
-static void wgrad_tc_cfg(int B, int Cip, int Co, int L, int* ncb, int* S) {
-    *ncb = Cip >= 32 ? 32 : 16;
-    const int blocks_oc = (Cip / *ncb) * ecg_cdiv(Co, 128);
+static void wgrad_tc_cfg(int B, int Cip, int Co, int L, int* ncc, int* S) {
+    *ncc = Cip / 8 < 4 ? Cip / 8 : 4;
+    const int blocks_oc = (Cip / 8 / *ncc) * ecg_cdiv(Co, 128);
     const int items = B * ecg_cdiv(L, TC_TILE_M);
     int s = 148 / blocks_oc;
     if (s < 1) s = 1;
@@ -404,9 +422,9 @@ static void wgrad_tc_cfg(int B, int Cip, int Co, int L, int* ncb, int* S) {
 
 extern "C" size_t ecgb200_conv1d_wgrad_bf16_ws_bytes(int B, int Ci, int Co, int L) {
     const int Cip = (Ci + 15) / 16 * 16;
-    int ncb, S;
-    wgrad_tc_cfg(B, Cip, Co, L, &ncb, &S);
-    return (size_t)S * ECG_KS * Co * Cip * sizeof(float);
+    int ncc, S;
+    wgrad_tc_cfg(B, Cip, Co, L, &ncc, &S);
+    return (size_t)S * Co * Cip * 16 * sizeof(float);
 }
 
 // dyb [B][Co/8][L][8], xb [B][Cip/8][L][8] bf16 -> dw fp32 (Co, Ci, 15), db fp32 (Co) [NULL to skip].
@@ -417,13 +435,13 @@ extern "C" int ecgb200_conv1d_wgrad_bf16(const void* dyb, const void* xb, float*
     if (!dyb || !xb || !dw || !ws || B <= 0 || Ci <= 0 || L <= 0) return ECGB200_EINVAL;
     const int Cip = (Ci + 15) / 16 * 16;
     if (Co <= 0 || (Co & 7) || Co > 256 || Cip > 256 || (Cip > 16 && (Cip & 31))) return ECGB200_EUNSUPPORTED;
-    int ncb, S;
-    wgrad_tc_cfg(B, Cip, Co, L, &ncb, &S);
+    int ncc, S;
+    wgrad_tc_cfg(B, Cip, Co, L, &ncc, &S);
     const int ochunks = Co >= 128 ? 16 : Co / 8;
     CUtensorMap dymap, xmap;
     int rc = ecg_make_act_tmap(&dymap, dyb, B, Co, L, TC_TILE_M, ochunks);
     if (rc) return rc;
-    rc = ecg_make_act_tmap(&xmap, xb, B, Cip, L, TC_ROWS, ncb / 8);
+    rc = ecg_make_act_tmap(&xmap, xb, B, Cip, L, TC_ROWS, ncc);
     if (rc) return rc;
     const size_t smem = TC_HDR + (size_t)WT_NST * WT_STAGE;
     static bool attr_set = false;
@@ -433,11 +451,11 @@ extern "C" int ecgb200_conv1d_wgrad_bf16(const void* dyb, const void* xb, float*
         attr_set = true;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid(Cip / ncb, ecg_cdiv(Co, 128), S);
-    wgrad_tc_kernel<<<grid, 192, smem, st>>>(dymap, xmap, (float*)ws, Co, Cip, L, B, ncb, ochunks);
+    dim3 grid(Cip / 8 / ncc, ecg_cdiv(Co, 128), S);
+    wgrad_tc_kernel<<<grid, 192, smem, st>>>(dymap, xmap, (float*)ws, Co, Cip, L, B, ncc, ochunks);
     rc = ecg_launch_status();
     if (rc) return rc;
-    const int n = ECG_KS * Co * Cip;
+    const int n = Co * Ci * ECG_KS;
     wgrad_tc_reduce_kernel<<<ecg_cdiv(n + Co, 256), 256, 0, st>>>((const float*)ws, db_part, dw, db, S, Co, Ci, Cip, ndb);
     return ecg_launch_status();
 }

@@ -7,42 +7,65 @@
 #include "common.cuh"
 
 // ------------------------------------------------------------------ small strided SGEMM
-// C[m][n] = act( sum_k A[m*sam + k*sak] * Bm[k*sbk + n*sbn] + bias[n] ), C row-major (ldc = N).
-// 32x32 tile, 256 threads, 2x2 outputs per thread, K step 32.  Deterministic (no split-K).
+// C[m][n] = act( sum_k A(m,k) * Bm(k,n) + bias[n] ), C row-major (ldc = N), with
+// A(m,k) = A[m*sam + k*sak], Bm(k,n) = Bm[k*sbk + n*sbn]; each operand has one unit stride.
+// 32x32 output tile, 256 threads (2x2 outputs each), K step 32.  Operand tiles are fetched
+// with ONE 16-byte load per thread per operand (scalar fallback when shape/alignment forbid)
+// and prefetched into registers one K-step ahead.  Deterministic (no split-K, fixed order).
 constexpr int SG_T = 32, SG_K = 32;
+
+// Tile fetch: `u` selects which index is unit-stride (1: the K index, 0: the M/N index).
+// Thread t owns 4 consecutive elements along the unit-stride index.
+struct SgTile { float v[4]; };
+
+__device__ __forceinline__ SgTile sg_fetch(const float* __restrict__ P, int r0, int k0, int R, int K,
+                                           long sr, long sk, int kunit, bool vec, int tid) {
+    // r = row (M or N) index inside the tile, k = K index inside the tile
+    SgTile t;
+    int r, k;
+    if (kunit) { r = tid >> 3; k = (tid & 7) * 4; } else { k = tid >> 3; r = (tid & 7) * 4; }
+    const float* src = P + (long)(r0 + r) * sr + (long)(k0 + k) * sk;
+    if (vec && r0 + r + (kunit ? 0 : 3) < R && k0 + k + (kunit ? 3 : 0) < K) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(src));
+        t.v[0] = f.x; t.v[1] = f.y; t.v[2] = f.z; t.v[3] = f.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int rr = r + (kunit ? 0 : i), kk = k + (kunit ? i : 0);
+            t.v[i] = (r0 + rr < R && k0 + kk < K) ? __ldg(P + (long)(r0 + rr) * sr + (long)(k0 + kk) * sk) : 0.f;
+        }
+    }
+    return t;
+}
+
+__device__ __forceinline__ void sg_store(float (*S)[SG_T + 1], const SgTile& t, int kunit, int tid) {
+    int r, k;
+    if (kunit) { r = tid >> 3; k = (tid & 7) * 4; } else { k = tid >> 3; r = (tid & 7) * 4; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) S[k + (kunit ? i : 0)][r + (kunit ? 0 : i)] = t.v[i];
+}
 
 __global__ void __launch_bounds__(256)
 sgemm_small_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
-                   const float* __restrict__ bias, const float* __restrict__ mask_src,
-                   float* __restrict__ C, int M, int N, int K, long sam, long sak, long sbk,
-                   long sbn, int act) {
+                   const float* __restrict__ bias, float* __restrict__ C, int M, int N, int K,
+                   long sam, long sak, long sbk, long sbn, int act, int avec, int bvec) {
     __shared__ float As[SG_K][SG_T + 1];
     __shared__ float Bs[SG_K][SG_T + 1];
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.y * SG_T, n0 = blockIdx.x * SG_T;
+    const int akunit = sak == 1, bkunit = sbk == 1;
     float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    SgTile ta = sg_fetch(A, m0, 0, M, K, sam, sak, akunit, avec, tid);
+    SgTile tb = sg_fetch(Bm, n0, 0, N, K, sbn, sbk, bkunit, bvec, tid);
     for (int k0 = 0; k0 < K; k0 += SG_K) {
-        for (int i = tid; i < SG_T * SG_K; i += 256) {
-            // choose the faster-varying index to follow the unit stride of each operand
-            int mm, kk;
-            if (sak == 1) { kk = i % SG_K; mm = i / SG_K; } else { mm = i % SG_T; kk = i / SG_T; }
-            float v = 0.f;
-            if (m0 + mm < M && k0 + kk < K) {
-                v = __ldg(A + (long)(m0 + mm) * sam + (long)(k0 + kk) * sak);
-                // optional ReLU mask on the A operand (A is dy masked by relu_out > 0)
-                if (mask_src != nullptr && !(__ldg(mask_src + (long)(m0 + mm) * sam + (long)(k0 + kk) * sak) > 0.f)) v = 0.f;
-            }
-            As[kk][mm] = v;
-        }
-        for (int i = tid; i < SG_T * SG_K; i += 256) {
-            int nn, kk;
-            if (sbk == 1) { kk = i % SG_K; nn = i / SG_K; } else { nn = i % SG_T; kk = i / SG_T; }
-            float v = 0.f;
-            if (n0 + nn < N && k0 + kk < K) v = __ldg(Bm + (long)(k0 + kk) * sbk + (long)(n0 + nn) * sbn);
-            Bs[kk][nn] = v;
-        }
+        sg_store(As, ta, akunit, tid);
+        sg_store(Bs, tb, bkunit, tid);
         __syncthreads();
+        if (k0 + SG_K < K) {                       // prefetch the next K-step under the math
+            ta = sg_fetch(A, m0, k0 + SG_K, M, K, sam, sak, akunit, avec, tid);
+            tb = sg_fetch(Bm, n0, k0 + SG_K, N, K, sbn, sbk, bkunit, bvec, tid);
+        }
 #pragma unroll
         for (int kk = 0; kk < SG_K; ++kk) {
             const float a0 = As[kk][ty], a1 = As[kk][ty + 16];
@@ -68,8 +91,12 @@ sgemm_small_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
 static int sgemm_small(const float* A, const float* Bm, const float* bias, const float* mask_src,
                        float* C, int M, int N, int K, long sam, long sak, long sbk, long sbn,
                        int act, cudaStream_t st) {
+    (void)mask_src;
+    // 16-byte vector path: the non-unit stride must keep rows 16 B aligned
+    const int avec = (((uintptr_t)A & 15) == 0) && ((sak == 1 ? sam : sak) % 4 == 0);
+    const int bvec = (((uintptr_t)Bm & 15) == 0) && ((sbk == 1 ? sbn : sbk) % 4 == 0);
     dim3 grid(ecg_cdiv(N, SG_T), ecg_cdiv(M, SG_T));
-    sgemm_small_kernel<<<grid, 256, 0, st>>>(A, Bm, bias, mask_src, C, M, N, K, sam, sak, sbk, sbn, act);
+    sgemm_small_kernel<<<grid, 256, 0, st>>>(A, Bm, bias, C, M, N, K, sam, sak, sbk, sbn, act, avec, bvec);
     return ecg_launch_status();
 }
 
