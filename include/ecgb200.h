@@ -103,6 +103,8 @@ int ecgb200_bn_relu_pool_fwd_bf16(const void* yb, const float* bn_state, void* p
 int ecgb200_bn_relu_pool_bwd_bf16(const void* yb, const float* bn_state, const void* dpb, const float* dgap,
                                   void* dyb, float* dgamma, float* dbeta, float* db_part, void* ws,
                                   int B, int C, int L, int train, void* stream);
+/* number of per-channel partials the bf16 BN kernels produce (second dim of db_part) */
+int ecgb200_bn_nsplit(int B, int C);
 
 /* ------------------------------------------- BatchNorm1d + ReLU + MaxPool1d --
  * Train-mode statistics from the conv epilogue partials (or from y itself when

@@ -49,6 +49,7 @@ _SIGS = {
     "ecgb200_bn_train_stats_bf16": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _P]),
     "ecgb200_bn_relu_pool_fwd_bf16": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "ecgb200_bn_relu_pool_bwd_bf16": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "ecgb200_bn_nsplit": (_I, [_I, _I]),
 }
 
 EXPORTED = tuple(_SIGS)

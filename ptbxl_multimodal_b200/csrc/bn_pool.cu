@@ -361,19 +361,34 @@ __device__ __forceinline__ void block_sum_vec(float* v, float* sh /* [8][NV] */)
     __syncthreads();
 }
 
-// {sum, centred M2} per (channel, sample): part[c][b], part[C + c][b]
+// Work split: grid (C/8, NS); block (cc, s) owns samples [s*tile_b, min(B, (s+1)*tile_b)) of channel
+// chunk cc and walks the flattened (sample, time) index space with 256 threads, so that every
+// block has a few thousand 16-byte vectors to stream and exactly ONE block reduction at the end.
+__host__ __device__ inline int bnb_tile_b(int B, int C) {
+    int ns = (592 + C / 8 - 1) / (C / 8);          // ~4 blocks per SM over the whole grid
+    if (ns > B) ns = B;
+    if (ns < 1) ns = 1;
+    return (B + ns - 1) / ns;
+}
+extern "C" int ecgb200_bn_nsplit(int B, int C) { const int tb = bnb_tile_b(B, C); return (B + tb - 1) / tb; }
+
+// {sum, centred M2} per (channel, split): part[c][s], part[C + c][s]
 __global__ void __launch_bounds__(256)
-bn_stats_bf16_kernel(const uint4* __restrict__ y, float* __restrict__ part, int B, int C, int L) {
+bn_stats_bf16_kernel(const uint4* __restrict__ y, float* __restrict__ part, int B, int C, int L, int tile_b) {
     __shared__ float sh[8 * 8];
     __shared__ float mean_s[8];
-    const int cc = blockIdx.x, b = blockIdx.y;
-    const uint4* yr = y + ((size_t)b * (C / 8) + cc) * L;
+    const int cc = blockIdx.x, NS = gridDim.y;
+    const int b0 = blockIdx.y * tile_b, nb = min(tile_b, B - b0);
+    const int n = nb * L;
+    const size_t bstride = (size_t)(C / 8) * L;
+    const uint4* y0 = y + ((size_t)b0 * (C / 8) + cc) * L;
     float s[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] = 0.f;
-    for (int t = threadIdx.x; t < L; t += blockDim.x) {
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+        const int bl = idx / L, t = idx - bl * L;
         float v[8];
-        bf8_unpack(__ldg(yr + t), v);
+        bf8_unpack(__ldg(y0 + (size_t)bl * bstride + t), v);
 #pragma unroll
         for (int i = 0; i < 8; ++i) s[i] += v[i];
     }
@@ -382,16 +397,17 @@ bn_stats_bf16_kernel(const uint4* __restrict__ y, float* __restrict__ part, int 
         float t = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) if (i == threadIdx.x) t = s[i];
-        mean_s[threadIdx.x] = t / (float)L;
-        part[(size_t)(cc * 8 + threadIdx.x) * B + b] = t;
+        mean_s[threadIdx.x] = t / (float)n;
+        part[(size_t)(cc * 8 + threadIdx.x) * NS + blockIdx.y] = t;
     }
     __syncthreads();
     float m[8], q[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { m[i] = mean_s[i]; q[i] = 0.f; }
-    for (int t = threadIdx.x; t < L; t += blockDim.x) {
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+        const int bl = idx / L, t = idx - bl * L;
         float v[8];
-        bf8_unpack(__ldg(yr + t), v);
+        bf8_unpack(__ldg(y0 + (size_t)bl * bstride + t), v);
 #pragma unroll
         for (int i = 0; i < 8; ++i) { const float d = v[i] - m[i]; q[i] = fmaf(d, d, q[i]); }
     }
@@ -400,7 +416,7 @@ bn_stats_bf16_kernel(const uint4* __restrict__ y, float* __restrict__ part, int 
         float t = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) if (i == threadIdx.x) t = q[i];
-        part[((size_t)C + cc * 8 + threadIdx.x) * B + b] = t;
+        part[((size_t)C + cc * 8 + threadIdx.x) * NS + blockIdx.y] = t;
     }
 }
 
@@ -409,50 +425,83 @@ extern "C" int ecgb200_bn_train_stats_bf16(const void* yb, const float* gamma, c
                                            float* bn_state, void* ws, int B, int C, int L, float momentum,
                                            float eps, void* stream) {
     if (!yb || !gamma || !beta || !bn_state || !ws || B <= 0 || C <= 0 || (C & 7) || L <= 0) return ECGB200_EINVAL;
-    if (B > 65535) return ECGB200_EUNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
-    const int threads = L >= 256 ? 256 : (L >= 128 ? 128 : 64);
-    bn_stats_bf16_kernel<<<dim3(C / 8, B), threads, 0, st>>>((const uint4*)yb, (float*)ws, B, C, L);
+    const int tile_b = bnb_tile_b(B, C), NS = (B + tile_b - 1) / tile_b;
+    bn_stats_bf16_kernel<<<dim3(C / 8, NS), 256, 0, st>>>((const uint4*)yb, (float*)ws, B, C, L, tile_b);
     int rc = ecg_launch_status();
     if (rc) return rc;
-    bn_finalize_kernel<<<C, 256, 0, st>>>((const float*)ws, B, 1, L, L, gamma, beta, running_mean, running_var,
-                                          nbt, bn_state, C, momentum, eps);
+    // tiles = sample ranges: "row" = all B*L samples of a channel, tile_len = tile_b*L
+    bn_finalize_kernel<<<C, 128, 0, st>>>((const float*)ws, NS, NS, tile_b * L, B * L, gamma, beta, running_mean,
+                                          running_var, nbt, bn_state, C, momentum, eps);
     return ecg_launch_status();
 }
 
-// p = maxpool2(relu(bn(y))) in the blocked layout; optional gap[b][c] = mean_j p
+// p = maxpool2(relu(bn(y))) in the blocked layout (flattened (sample, pair) walk)
 __global__ void __launch_bounds__(256)
 bn_relu_pool_fwd_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__ bn_state,
-                             uint4* __restrict__ p, float* __restrict__ gap, int C, int L, int Lp) {
-    __shared__ float sh[8 * 8];
-    const int cc = blockIdx.x, b = blockIdx.y;
-    const uint4* yr = y + ((size_t)b * (C / 8) + cc) * L;
-    float sc[8], sf[8], acc[8];
+                             uint4* __restrict__ p, int B, int C, int L, int Lp, int tile_b) {
+    const int cc = blockIdx.x;
+    const int b0 = blockIdx.y * tile_b, nb = min(tile_b, B - b0);
+    const int n = nb * Lp;
+    float sc[8], sf[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         sc[i] = __ldg(bn_state + 2 * C + cc * 8 + i);
         sf[i] = __ldg(bn_state + 3 * C + cc * 8 + i);
-        acc[i] = 0.f;
     }
-    for (int j = threadIdx.x; j < Lp; j += blockDim.x) {
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+        const int bl = idx / Lp, j = idx - bl * Lp;
+        const size_t row = (size_t)(b0 + bl) * (C / 8) + cc;
         float a0[8], a1[8], m[8];
-        bf8_unpack(__ldg(yr + 2 * j), a0);
-        bf8_unpack(__ldg(yr + 2 * j + 1), a1);
+        bf8_unpack(__ldg(y + row * L + 2 * j), a0);
+        bf8_unpack(__ldg(y + row * L + 2 * j + 1), a1);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const float r0 = fmaxf(fmaf(a0[i], sc[i], sf[i]), 0.f), r1 = fmaxf(fmaf(a1[i], sc[i], sf[i]), 0.f);
             m[i] = fmaxf(r0, r1);
-            acc[i] += m[i];
         }
-        if (p != nullptr) p[((size_t)b * (C / 8) + cc) * Lp + j] = bf8_pack(m);
+        p[row * Lp + j] = bf8_pack(m);
     }
-    if (gap != nullptr) {
-        block_sum_vec<8>(acc, sh);
-        if (threadIdx.x < 8) {
+}
+
+// variant with the global average pool: one warp per (sample, chunk) row at a time
+__global__ void __launch_bounds__(256)
+bn_relu_pool_gap_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__ bn_state,
+                             uint4* __restrict__ p, float* __restrict__ gap, int B, int C, int L, int Lp,
+                             int tile_b) {
+    const int cc = blockIdx.x;
+    const int b0 = blockIdx.y * tile_b, nb = min(tile_b, B - b0);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    float sc[8], sf[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        sc[i] = __ldg(bn_state + 2 * C + cc * 8 + i);
+        sf[i] = __ldg(bn_state + 3 * C + cc * 8 + i);
+    }
+    for (int bl = w; bl < nb; bl += nw) {
+        const size_t row = (size_t)(b0 + bl) * (C / 8) + cc;
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        for (int j = lane; j < Lp; j += 32) {
+            float a0[8], a1[8], m[8];
+            bf8_unpack(__ldg(y + row * L + 2 * j), a0);
+            bf8_unpack(__ldg(y + row * L + 2 * j + 1), a1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float r0 = fmaxf(fmaf(a0[i], sc[i], sf[i]), 0.f), r1 = fmaxf(fmaf(a1[i], sc[i], sf[i]), 0.f);
+                m[i] = fmaxf(r0, r1);
+                acc[i] += m[i];
+            }
+            if (p != nullptr) p[row * Lp + j] = bf8_pack(m);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = warp_sum(acc[i]);
+        if (lane < 8) {
             float t = 0.f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) if (i == threadIdx.x) t = acc[i];
-            gap[(size_t)b * C + cc * 8 + threadIdx.x] = t / (float)Lp;
+            for (int i = 0; i < 8; ++i) if (i == lane) t = acc[i];
+            gap[(size_t)(b0 + bl) * C + cc * 8 + lane] = t / (float)Lp;
         }
     }
 }
@@ -460,39 +509,53 @@ bn_relu_pool_fwd_bf16_kernel(const uint4* __restrict__ y, const float* __restric
 extern "C" int ecgb200_bn_relu_pool_fwd_bf16(const void* yb, const float* bn_state, void* pb, float* gap,
                                              int B, int C, int L, void* stream) {
     if (!yb || !bn_state || (!pb && !gap) || B <= 0 || C <= 0 || (C & 7) || L < 2) return ECGB200_EINVAL;
-    if (B > 65535) return ECGB200_EUNSUPPORTED;
     const int Lp = L / 2;
-    const int threads = Lp >= 256 ? 256 : (Lp >= 128 ? 128 : 64);
-    bn_relu_pool_fwd_bf16_kernel<<<dim3(C / 8, B), threads, 0, (cudaStream_t)stream>>>(
-        (const uint4*)yb, bn_state, (uint4*)pb, gap, C, L, Lp);
+    const int tile_b = bnb_tile_b(B, C), NS = (B + tile_b - 1) / tile_b;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (gap != nullptr)
+        bn_relu_pool_gap_bf16_kernel<<<dim3(C / 8, NS), 256, 0, st>>>((const uint4*)yb, bn_state, (uint4*)pb, gap,
+                                                                     B, C, L, Lp, tile_b);
+    else
+        bn_relu_pool_fwd_bf16_kernel<<<dim3(C / 8, NS), 256, 0, st>>>((const uint4*)yb, bn_state, (uint4*)pb,
+                                                                     B, C, L, Lp, tile_b);
     return ecg_launch_status();
 }
 
-// backward pass 1: partial {sum g, sum g*xhat} per (channel, sample) -> part[c][b], part[C+c][b]
+// backward pass 1: partial {sum g, sum g*xhat} per (channel, split) -> part[c][s], part[C+c][s]
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__ bn_state,
                           const uint4* __restrict__ dp, const float* __restrict__ dgap,
-                          float* __restrict__ part, int B, int C, int L, int Lp) {
+                          float* __restrict__ part, int B, int C, int L, int Lp, int tile_b) {
     __shared__ float sh[8 * 16];
-    const int cc = blockIdx.x, b = blockIdx.y;
-    const uint4* yr = y + ((size_t)b * (C / 8) + cc) * L;
-    float mean[8], rstd[8], sc[8], sf[8], dc[8], s[16];
+    const int cc = blockIdx.x, NS = gridDim.y;
+    const int b0 = blockIdx.y * tile_b, nb = min(tile_b, B - b0);
+    const int n = nb * Lp;
+    const float inv_lp = 1.0f / (float)Lp;
+    float mean[8], rstd[8], sc[8], sf[8], s[16];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int c = cc * 8 + i;
         mean[i] = __ldg(bn_state + c); rstd[i] = __ldg(bn_state + C + c);
         sc[i] = __ldg(bn_state + 2 * C + c); sf[i] = __ldg(bn_state + 3 * C + c);
-        dc[i] = dgap != nullptr ? __ldg(dgap + (size_t)b * C + c) / (float)Lp : 0.f;
         s[i] = 0.f; s[8 + i] = 0.f;
     }
-    for (int j = threadIdx.x; j < Lp; j += blockDim.x) {
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+        const int bl = idx / Lp, j = idx - bl * Lp;
+        const size_t row = (size_t)(b0 + bl) * (C / 8) + cc;
         float a0[8], a1[8], d[8];
-        bf8_unpack(__ldg(yr + 2 * j), a0);
-        bf8_unpack(__ldg(yr + 2 * j + 1), a1);
-        if (dp != nullptr) bf8_unpack(__ldg(dp + ((size_t)b * (C / 8) + cc) * Lp + j), d);
+        bf8_unpack(__ldg(y + row * L + 2 * j), a0);
+        bf8_unpack(__ldg(y + row * L + 2 * j + 1), a1);
+        if (dp != nullptr) {
+            bf8_unpack(__ldg(dp + row * Lp + j), d);
+        } else {
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(dgap + (size_t)(b0 + bl) * C + cc * 8));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(dgap + (size_t)(b0 + bl) * C + cc * 8) + 1);
+            d[0] = g0.x * inv_lp; d[1] = g0.y * inv_lp; d[2] = g0.z * inv_lp; d[3] = g0.w * inv_lp;
+            d[4] = g1.x * inv_lp; d[5] = g1.y * inv_lp; d[6] = g1.z * inv_lp; d[7] = g1.w * inv_lp;
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const PoolGrad r = pool_grad(a0[i], a1[i], dp != nullptr ? d[i] : dc[i], mean[i], rstd[i], sc[i], sf[i]);
+            const PoolGrad r = pool_grad(a0[i], a1[i], d[i], mean[i], rstd[i], sc[i], sf[i]);
             s[i] += r.g0 + r.g1;
             s[8 + i] = fmaf(r.g0, r.xh0, fmaf(r.g1, r.xh1, s[8 + i]));
         }
@@ -502,55 +565,80 @@ bn_bwd_reduce_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__
         float t1 = 0.f, t2 = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) if (i == threadIdx.x) { t1 = s[i]; t2 = s[8 + i]; }
-        part[(size_t)(cc * 8 + threadIdx.x) * B + b] = t1;
-        part[((size_t)C + cc * 8 + threadIdx.x) * B + b] = t2;
+        part[(size_t)(cc * 8 + threadIdx.x) * NS + blockIdx.y] = t1;
+        part[((size_t)C + cc * 8 + threadIdx.x) * NS + blockIdx.y] = t2;
     }
 }
 
-// backward pass 2: dy (blocked bf16) and per-(channel, sample) sums of dy for the conv-bias gradient
+// backward pass 2: every block first merges the NS partials of its 8 channels (fixed order, double),
+// block row 0 also publishes dgamma / dbeta; then dy (blocked bf16) and per-(channel, split) sums
+// of dy for the conv-bias gradient.
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__ bn_state,
                          const uint4* __restrict__ dp, const float* __restrict__ dgap,
-                         const float* __restrict__ sums, uint4* __restrict__ dy, float* __restrict__ db_part,
-                         int B, int C, int L, int Lp, float inv_n, int train) {
+                         const float* __restrict__ part, uint4* __restrict__ dy, float* __restrict__ dgamma,
+                         float* __restrict__ dbeta, float* __restrict__ db_part, int B, int C, int L, int Lp,
+                         float inv_n, int train, int tile_b) {
     __shared__ float sh[8 * 8];
-    const int cc = blockIdx.x, b = blockIdx.y;
-    const uint4* yr = y + ((size_t)b * (C / 8) + cc) * L;
-    uint4* dr = dy + ((size_t)b * (C / 8) + cc) * L;
-    float mean[8], rstd[8], sc[8], sf[8], dc[8], m1[8], m2[8], sdy[8];
+    __shared__ float msum[16];
+    const int cc = blockIdx.x, NS = gridDim.y;
+    const int b0 = blockIdx.y * tile_b, nb = min(tile_b, B - b0);
+    const int n = nb * Lp;
+    const float inv_lp = 1.0f / (float)Lp;
+    if (threadIdx.x < 16) {
+        const int which = threadIdx.x >> 3, c = cc * 8 + (threadIdx.x & 7);
+        const float* src = part + ((size_t)which * C + c) * NS;
+        double t = 0.0;
+        for (int i = 0; i < NS; ++i) t += (double)src[i];
+        msum[threadIdx.x] = (float)t;
+        if (blockIdx.y == 0) {
+            if (which == 0 && dbeta != nullptr) dbeta[c] = (float)t;
+            if (which == 1 && dgamma != nullptr) dgamma[c] = (float)t;
+        }
+    }
+    __syncthreads();
+    float mean[8], rstd[8], sc[8], sf[8], m1[8], m2[8], sdy[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int c = cc * 8 + i;
         mean[i] = __ldg(bn_state + c); rstd[i] = __ldg(bn_state + C + c);
         sc[i] = __ldg(bn_state + 2 * C + c); sf[i] = __ldg(bn_state + 3 * C + c);
-        dc[i] = dgap != nullptr ? __ldg(dgap + (size_t)b * C + c) / (float)Lp : 0.f;
-        m1[i] = train ? __ldg(sums + c) * inv_n : 0.f;
-        m2[i] = train ? __ldg(sums + C + c) * inv_n : 0.f;
+        m1[i] = train ? msum[i] * inv_n : 0.f;
+        m2[i] = train ? msum[8 + i] * inv_n : 0.f;
         sdy[i] = 0.f;
     }
-    for (int j = threadIdx.x; j < Lp; j += blockDim.x) {
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+        const int bl = idx / Lp, j = idx - bl * Lp;
+        const size_t row = (size_t)(b0 + bl) * (C / 8) + cc;
         float a0[8], a1[8], d[8], o0[8], o1[8];
-        bf8_unpack(__ldg(yr + 2 * j), a0);
-        bf8_unpack(__ldg(yr + 2 * j + 1), a1);
-        if (dp != nullptr) bf8_unpack(__ldg(dp + ((size_t)b * (C / 8) + cc) * Lp + j), d);
+        bf8_unpack(__ldg(y + row * L + 2 * j), a0);
+        bf8_unpack(__ldg(y + row * L + 2 * j + 1), a1);
+        if (dp != nullptr) {
+            bf8_unpack(__ldg(dp + row * Lp + j), d);
+        } else {
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(dgap + (size_t)(b0 + bl) * C + cc * 8));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(dgap + (size_t)(b0 + bl) * C + cc * 8) + 1);
+            d[0] = g0.x * inv_lp; d[1] = g0.y * inv_lp; d[2] = g0.z * inv_lp; d[3] = g0.w * inv_lp;
+            d[4] = g1.x * inv_lp; d[5] = g1.y * inv_lp; d[6] = g1.z * inv_lp; d[7] = g1.w * inv_lp;
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const PoolGrad r = pool_grad(a0[i], a1[i], dp != nullptr ? d[i] : dc[i], mean[i], rstd[i], sc[i], sf[i]);
+            const PoolGrad r = pool_grad(a0[i], a1[i], d[i], mean[i], rstd[i], sc[i], sf[i]);
             o0[i] = sc[i] * (r.g0 - m1[i] - r.xh0 * m2[i]);
             o1[i] = sc[i] * (r.g1 - m1[i] - r.xh1 * m2[i]);
             sdy[i] += o0[i] + o1[i];
         }
-        dr[2 * j] = bf8_pack(o0);
-        dr[2 * j + 1] = bf8_pack(o1);
+        dy[row * L + 2 * j] = bf8_pack(o0);
+        dy[row * L + 2 * j + 1] = bf8_pack(o1);
         if (j == Lp - 1 && (L & 1)) {
             float a[8], o[8];
-            bf8_unpack(__ldg(yr + L - 1), a);
+            bf8_unpack(__ldg(y + row * L + L - 1), a);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 o[i] = sc[i] * (0.f - m1[i] - (a[i] - mean[i]) * rstd[i] * m2[i]);
                 sdy[i] += o[i];
             }
-            dr[L - 1] = bf8_pack(o);
+            dy[row * L + L - 1] = bf8_pack(o);
         }
     }
     if (db_part != nullptr) {
@@ -559,32 +647,30 @@ bn_bwd_apply_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__ 
             float t = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) if (i == threadIdx.x) t = sdy[i];
-            db_part[(size_t)(cc * 8 + threadIdx.x) * B + b] = t;
+            db_part[(size_t)(cc * 8 + threadIdx.x) * NS + blockIdx.y] = t;
         }
     }
 }
 
-// yb, dpb, dyb blocked bf16; dgap fp32 (B,C) [layer 4]; db_part fp32 [C][B] or NULL; ws as fp32 path.
+// yb, dpb, dyb blocked bf16; dgap fp32 (B,C) [layer 4]; db_part fp32 [C][ecgb200_bn_nsplit(B,C)] or
+// NULL; ws: ecgb200_bn_bwd_ws_bytes(B,C).
 extern "C" int ecgb200_bn_relu_pool_bwd_bf16(const void* yb, const float* bn_state, const void* dpb,
                                              const float* dgap, void* dyb, float* dgamma, float* dbeta,
                                              float* db_part, void* ws, int B, int C, int L, int train,
                                              void* stream) {
     if (!yb || !bn_state || (!dpb && !dgap) || !dyb || !ws || B <= 0 || C <= 0 || (C & 7) || L < 2) return ECGB200_EINVAL;
-    if (B > 65535) return ECGB200_EUNSUPPORTED;
+    if (dgap != nullptr && (((uintptr_t)dgap & 15) != 0)) return ECGB200_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     const int Lp = L / 2;
+    const int tile_b = bnb_tile_b(B, C), NS = (B + tile_b - 1) / tile_b;
     float* part = (float*)ws;
-    float* sums = part + (size_t)2 * C * B;
-    const int threads = Lp >= 256 ? 256 : (Lp >= 128 ? 128 : 64);
-    bn_bwd_reduce_bf16_kernel<<<dim3(C / 8, B), threads, 0, st>>>((const uint4*)yb, bn_state, (const uint4*)dpb,
-                                                                 dgap, part, B, C, L, Lp);
+    bn_bwd_reduce_bf16_kernel<<<dim3(C / 8, NS), 256, 0, st>>>((const uint4*)yb, bn_state, (const uint4*)dpb,
+                                                              dgap, part, B, C, L, Lp, tile_b);
     int rc = ecg_launch_status();
     if (rc) return rc;
-    bn_bwd_finalize_kernel<<<C, 128, 0, st>>>(part, sums, dgamma, dbeta, B, C);
-    rc = ecg_launch_status();
-    if (rc) return rc;
     const float inv_n = 1.0f / ((float)B * (float)L);
-    bn_bwd_apply_bf16_kernel<<<dim3(C / 8, B), threads, 0, st>>>((const uint4*)yb, bn_state, (const uint4*)dpb, dgap,
-                                                                sums, (uint4*)dyb, db_part, B, C, L, Lp, inv_n, train);
+    bn_bwd_apply_bf16_kernel<<<dim3(C / 8, NS), 256, 0, st>>>((const uint4*)yb, bn_state, (const uint4*)dpb, dgap,
+                                                             part, (uint4*)dyb, dgamma, dbeta, db_part, B, C, L, Lp,
+                                                             inv_n, train, tile_b);
     return ecg_launch_status();
 }

@@ -380,33 +380,50 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant
 }
 
 // dW[o][c][k] = sum_z part[z][o][c/8][k][c%8]  (c < Ci, k < 15);  db[o] = sum_j db_part[o][j]
-__global__ void wgrad_tc_reduce_kernel(const float* __restrict__ part, const float* __restrict__ db_part,
-                                       float* __restrict__ dw, float* __restrict__ db, int S, int Co,
-                                       int Ci, int Cip, int ndb) {
-    const int nout = Co * Ci * ECG_KS;
-    const size_t zstride = (size_t)Co * Cip * 16;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nout) {
-        const int k = i % ECG_KS;
-        const int c = (i / ECG_KS) % Ci;
-        const int o = i / (ECG_KS * Ci);
-        const float* src = part + (((size_t)o * (Cip / 8) + (c >> 3)) * 16 + k) * 8 + (c & 7);
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-        int z = 0;
-        for (; z + 4 <= S; z += 4) {
-            s0 += src[(size_t)z * zstride];
-            s1 += src[(size_t)(z + 1) * zstride];
-            s2 += src[(size_t)(z + 2) * zstride];
-            s3 += src[(size_t)(z + 3) * zstride];
+// Block = 32 float4 columns of the partial layout x 8 z-lanes: every load is a coalesced 512-byte
+// row, the 8 z-lanes are combined through shared memory in a fixed order (deterministic).
+__global__ void __launch_bounds__(256)
+wgrad_tc_reduce_kernel(const float4* __restrict__ part, const float* __restrict__ db_part,
+                       float* __restrict__ dw, float* __restrict__ db, int S, int Co, int Ci, int Cip,
+                       int ndb, int nblk_w) {
+    __shared__ float4 red[8][32];
+    if ((int)blockIdx.x >= nblk_w) {                       // tail blocks: conv-bias gradient
+        const int o = (blockIdx.x - nblk_w) * blockDim.x + threadIdx.x;
+        if (o < Co && db != nullptr) {
+            float s = 0.f;
+            if (db_part != nullptr)
+                for (int j = 0; j < ndb; ++j) s += db_part[(size_t)o * ndb + j];
+            db[o] = s;
         }
-        for (; z < S; ++z) s0 += src[(size_t)z * zstride];
-        dw[i] = (s0 + s1) + (s2 + s3);
-    } else if (i < nout + Co && db != nullptr) {
-        const int o = i - nout;
-        float s = 0.f;
-        if (db_part != nullptr)
-            for (int j = 0; j < ndb; ++j) s += db_part[(size_t)o * ndb + j];
-        db[o] = s;
+        return;
+    }
+    const int n4 = Co * Cip * 4;                           // float4 columns per partial
+    const int lane = threadIdx.x & 31, zl = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + lane;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col < n4) {
+        for (int z = zl; z < S; z += 8) {
+            const float4 v = __ldg(part + (size_t)z * n4 + col);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    }
+    red[zl][lane] = acc;
+    __syncthreads();
+    if (zl == 0 && col < n4) {
+        float4 t = red[0][lane];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) { const float4 v = red[i][lane]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+        const int idx = col * 4;                           // element index in [o][c/8][16][8]
+        const int c8 = idx & 7, k = (idx >> 3) & 15;
+        const int cc = (idx >> 7) % (Cip / 8), o = idx / (Cip * 16);
+        if (k < ECG_KS) {
+            const float v[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int c = cc * 8 + c8 + e;
+                if (c < Ci) dw[((size_t)o * Ci + c) * ECG_KS + k] = v[e];
+            }
+        }
     }
 }
 
@@ -455,7 +472,8 @@ extern "C" int ecgb200_conv1d_wgrad_bf16(const void* dyb, const void* xb, float*
     wgrad_tc_kernel<<<grid, 192, smem, st>>>(dymap, xmap, (float*)ws, Co, Cip, L, B, ncc, ochunks);
     rc = ecg_launch_status();
     if (rc) return rc;
-    const int n = Co * Ci * ECG_KS;
-    wgrad_tc_reduce_kernel<<<ecg_cdiv(n + Co, 256), 256, 0, st>>>((const float*)ws, db_part, dw, db, S, Co, Ci, Cip, ndb);
+    const int nblk_w = ecg_cdiv(Co * Cip * 4, 32);
+    wgrad_tc_reduce_kernel<<<nblk_w + ecg_cdiv(Co, 256), 256, 0, st>>>((const float4*)ws, db_part, dw, db, S, Co, Ci,
+                                                                      Cip, ndb, nblk_w);
     return ecg_launch_status();
 }

@@ -156,7 +156,8 @@ class TrainStep:
             self.ybuf = [eb(B, self.chan[l + 1] // 8, self.L[l], 8) for l in range(4)]
             self.wt = [eb(15, self.cip[l] // 8, self.chan[l + 1], 8) for l in range(4)]
             self.wd = [None] + [eb(15, self.chan[l + 1] // 8, self.cip[l], 8) for l in range(1, 4)]
-            self.dbpart = [e(self.chan[l + 1], B) for l in range(4)]
+            self.ndb = [lib.ecgb200_bn_nsplit(B, self.chan[l + 1]) for l in range(4)]
+            self.dbpart = [e(self.chan[l + 1], self.ndb[l]) for l in range(4)]
             self.stat = [None] * 4
         c4 = self.chan[4]
         self.gap = e(B, c4)
@@ -262,7 +263,7 @@ class TrainStep:
                         _p(self.dp) if l < 3 else None, _p(self.dgap) if l == 3 else None, _p(self.dy),
                         Gp(k + "1.weight"), Gp(k + "1.bias"), _p(self.dbpart[l]), _p(self.ws2), B, co, L, 1, st)
                 self._k("wgrad", lib.ecgb200_conv1d_wgrad_bf16, _p(self.dy), _p(self.acts[l]), Gp(k + "0.weight"),
-                        Gp(k + "0.bias"), _p(self.dbpart[l]), B, _p(self.ws), B, ci, co, L, st)
+                        Gp(k + "0.bias"), _p(self.dbpart[l]), self.ndb[l], _p(self.ws), B, ci, co, L, st)
             else:
                 self._k("bn_bwd", lib.ecgb200_bn_relu_pool_bwd_f32, _p(self.ybuf[l]), _p(self.bnst[l]), Pp(k + "1.weight"),
                         _p(self.dp) if l < 3 else None, _p(self.dgap) if l == 3 else None,

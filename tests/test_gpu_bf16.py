@@ -139,7 +139,7 @@ def test_bn_relu_pool_bf16(B, C, L, use_gap):
         assert rel_inf(gap, out_ref) < 1e-5                          # gap accumulates the unrounded fp32 values
     dyb = torch.empty(B, C // 8, L, 8, dtype=BF, device=DEV)
     dgm, dbt = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
-    dbp = torch.empty(C, B, device=DEV)
+    dbp = torch.empty(C, lib.ecgb200_bn_nsplit(B, C), device=DEV)
     dpb = None if use_gap else to_blocked(dout).to(DEV)
     dgap = dout.to(DEV) if use_gap else None
     check(lib.ecgb200_bn_relu_pool_bwd_bf16(ptr(yb), ptr(st), ptr(dpb), ptr(dgap), ptr(dyb), ptr(dgm), ptr(dbt),

