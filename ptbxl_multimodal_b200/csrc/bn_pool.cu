@@ -521,44 +521,62 @@ extern "C" int ecgb200_bn_relu_pool_fwd_bf16(const void* yb, const float* bn_sta
     return ecg_launch_status();
 }
 
-// backward pass 1: partial {sum g, sum g*xhat} per (channel, split) -> part[c][s], part[C+c][s]
-__global__ void __launch_bounds__(256)
+// Routing of one pool pair in terms of the raw conv outputs a0, a1 (first index wins ties, ReLU mask):
+//   sel0 = relu(bn(a0)) >= relu(bn(a1)) && relu(bn(a0)) > 0 ;  sel1 = relu(bn(a1)) > relu(bn(a0))
+__device__ __forceinline__ void pool_sel(float a0, float a1, float sc, float sf, bool& sel0, bool& sel1) {
+    const float r0 = fmaxf(fmaf(a0, sc, sf), 0.f), r1 = fmaxf(fmaf(a1, sc, sf), 0.f);
+    sel0 = (r0 >= r1) && (r0 > 0.f);
+    sel1 = r1 > r0;
+}
+
+__device__ __forceinline__ void load_dgrad8(const uint4* __restrict__ dp, const float* __restrict__ dgap,
+                                            size_t row, int Lp, int j, int b, int C, int cc, float inv_lp, float* d) {
+    if (dp != nullptr) {
+        bf8_unpack(__ldg(dp + row * Lp + j), d);
+    } else {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(dgap + (size_t)b * C + cc * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(dgap + (size_t)b * C + cc * 8) + 1);
+        d[0] = g0.x * inv_lp; d[1] = g0.y * inv_lp; d[2] = g0.z * inv_lp; d[3] = g0.w * inv_lp;
+        d[4] = g1.x * inv_lp; d[5] = g1.y * inv_lp; d[6] = g1.z * inv_lp; d[7] = g1.w * inv_lp;
+    }
+}
+
+// backward pass 1: partial {sum g, sum g*a} per (channel, split) -> part[c][s], part[C+c][s]
+// (a = raw conv output; sum g*xhat = rstd * (sum g*a - mean * sum g) is formed when merging)
+__global__ void __launch_bounds__(256, 3)
 bn_bwd_reduce_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__ bn_state,
                           const uint4* __restrict__ dp, const float* __restrict__ dgap,
                           float* __restrict__ part, int B, int C, int L, int Lp, int tile_b) {
     __shared__ float sh[8 * 16];
     const int cc = blockIdx.x, NS = gridDim.y;
     const int b0 = blockIdx.y * tile_b, nb = min(tile_b, B - b0);
-    const int n = nb * Lp;
     const float inv_lp = 1.0f / (float)Lp;
-    float mean[8], rstd[8], sc[8], sf[8], s[16];
+    float sc[8], sf[8], s[16];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const int c = cc * 8 + i;
-        mean[i] = __ldg(bn_state + c); rstd[i] = __ldg(bn_state + C + c);
-        sc[i] = __ldg(bn_state + 2 * C + c); sf[i] = __ldg(bn_state + 3 * C + c);
+        sc[i] = __ldg(bn_state + 2 * C + cc * 8 + i);
+        sf[i] = __ldg(bn_state + 3 * C + cc * 8 + i);
         s[i] = 0.f; s[8 + i] = 0.f;
     }
-    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
-        const int bl = idx / Lp, j = idx - bl * Lp;
+    int bl = 0, j = threadIdx.x;
+    while (j >= Lp) { j -= Lp; ++bl; }
+    while (bl < nb) {
         const size_t row = (size_t)(b0 + bl) * (C / 8) + cc;
         float a0[8], a1[8], d[8];
-        bf8_unpack(__ldg(y + row * L + 2 * j), a0);
-        bf8_unpack(__ldg(y + row * L + 2 * j + 1), a1);
-        if (dp != nullptr) {
-            bf8_unpack(__ldg(dp + row * Lp + j), d);
-        } else {
-            const float4 g0 = __ldg(reinterpret_cast<const float4*>(dgap + (size_t)(b0 + bl) * C + cc * 8));
-            const float4 g1 = __ldg(reinterpret_cast<const float4*>(dgap + (size_t)(b0 + bl) * C + cc * 8) + 1);
-            d[0] = g0.x * inv_lp; d[1] = g0.y * inv_lp; d[2] = g0.z * inv_lp; d[3] = g0.w * inv_lp;
-            d[4] = g1.x * inv_lp; d[5] = g1.y * inv_lp; d[6] = g1.z * inv_lp; d[7] = g1.w * inv_lp;
-        }
+        const uint4 u0 = __ldg(y + row * L + 2 * j), u1 = __ldg(y + row * L + 2 * j + 1);
+        load_dgrad8(dp, dgap, row, Lp, j, b0 + bl, C, cc, inv_lp, d);
+        bf8_unpack(u0, a0);
+        bf8_unpack(u1, a1);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const PoolGrad r = pool_grad(a0[i], a1[i], d[i], mean[i], rstd[i], sc[i], sf[i]);
-            s[i] += r.g0 + r.g1;
-            s[8 + i] = fmaf(r.g0, r.xh0, fmaf(r.g1, r.xh1, s[8 + i]));
+            bool s0, s1;
+            pool_sel(a0[i], a1[i], sc[i], sf[i], s0, s1);
+            const float g = (s0 || s1) ? d[i] : 0.f;
+            s[i] += g;
+            s[8 + i] = fmaf(g, s0 ? a0[i] : a1[i], s[8 + i]);
         }
+        j += blockDim.x;
+        while (j >= Lp) { j -= Lp; ++bl; }
     }
     block_sum_vec<16>(s, sh);
     if (threadIdx.x < 8) {
@@ -571,61 +589,60 @@ bn_bwd_reduce_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__
 }
 
 // backward pass 2: every block first merges the NS partials of its 8 channels (fixed order, double),
-// block row 0 also publishes dgamma / dbeta; then dy (blocked bf16) and per-(channel, split) sums
-// of dy for the conv-bias gradient.
-__global__ void __launch_bounds__(256)
+// block row 0 also publishes dgamma / dbeta; then
+//   dy = scale*g - scale*m1 - scale*rstd*m2*(a - mean) = scale*g + A*a + Bc      (blocked bf16)
+// and per-(channel, split) sums of dy for the conv-bias gradient.
+__global__ void __launch_bounds__(256, 3)
 bn_bwd_apply_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__ bn_state,
                          const uint4* __restrict__ dp, const float* __restrict__ dgap,
                          const float* __restrict__ part, uint4* __restrict__ dy, float* __restrict__ dgamma,
                          float* __restrict__ dbeta, float* __restrict__ db_part, int B, int C, int L, int Lp,
                          float inv_n, int train, int tile_b) {
     __shared__ float sh[8 * 8];
-    __shared__ float msum[16];
+    __shared__ float cA[8], cB[8];
     const int cc = blockIdx.x, NS = gridDim.y;
     const int b0 = blockIdx.y * tile_b, nb = min(tile_b, B - b0);
-    const int n = nb * Lp;
     const float inv_lp = 1.0f / (float)Lp;
-    if (threadIdx.x < 16) {
-        const int which = threadIdx.x >> 3, c = cc * 8 + (threadIdx.x & 7);
-        const float* src = part + ((size_t)which * C + c) * NS;
-        double t = 0.0;
-        for (int i = 0; i < NS; ++i) t += (double)src[i];
-        msum[threadIdx.x] = (float)t;
+    if (threadIdx.x < 8) {
+        const int c = cc * 8 + threadIdx.x;
+        double sg = 0.0, sga = 0.0;
+        for (int i = 0; i < NS; ++i) { sg += (double)part[(size_t)c * NS + i]; sga += (double)part[((size_t)C + c) * NS + i]; }
+        const float mean = __ldg(bn_state + c), rstd = __ldg(bn_state + C + c), scl = __ldg(bn_state + 2 * C + c);
+        const double sgx = (double)rstd * (sga - (double)mean * sg);       // sum g * xhat
         if (blockIdx.y == 0) {
-            if (which == 0 && dbeta != nullptr) dbeta[c] = (float)t;
-            if (which == 1 && dgamma != nullptr) dgamma[c] = (float)t;
+            if (dbeta != nullptr) dbeta[c] = (float)sg;
+            if (dgamma != nullptr) dgamma[c] = (float)sgx;
         }
+        const float m1 = train ? (float)sg * inv_n : 0.f, m2 = train ? (float)sgx * inv_n : 0.f;
+        const float A = -scl * rstd * m2;
+        cA[threadIdx.x] = A;
+        cB[threadIdx.x] = -scl * m1 - A * mean;
     }
     __syncthreads();
-    float mean[8], rstd[8], sc[8], sf[8], m1[8], m2[8], sdy[8];
+    float sc[8], sf[8], A[8], Bc[8], sdy[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const int c = cc * 8 + i;
-        mean[i] = __ldg(bn_state + c); rstd[i] = __ldg(bn_state + C + c);
-        sc[i] = __ldg(bn_state + 2 * C + c); sf[i] = __ldg(bn_state + 3 * C + c);
-        m1[i] = train ? msum[i] * inv_n : 0.f;
-        m2[i] = train ? msum[8 + i] * inv_n : 0.f;
+        sc[i] = __ldg(bn_state + 2 * C + cc * 8 + i);
+        sf[i] = __ldg(bn_state + 3 * C + cc * 8 + i);
+        A[i] = cA[i]; Bc[i] = cB[i];
         sdy[i] = 0.f;
     }
-    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
-        const int bl = idx / Lp, j = idx - bl * Lp;
+    int bl = 0, j = threadIdx.x;
+    while (j >= Lp) { j -= Lp; ++bl; }
+    while (bl < nb) {
         const size_t row = (size_t)(b0 + bl) * (C / 8) + cc;
         float a0[8], a1[8], d[8], o0[8], o1[8];
-        bf8_unpack(__ldg(y + row * L + 2 * j), a0);
-        bf8_unpack(__ldg(y + row * L + 2 * j + 1), a1);
-        if (dp != nullptr) {
-            bf8_unpack(__ldg(dp + row * Lp + j), d);
-        } else {
-            const float4 g0 = __ldg(reinterpret_cast<const float4*>(dgap + (size_t)(b0 + bl) * C + cc * 8));
-            const float4 g1 = __ldg(reinterpret_cast<const float4*>(dgap + (size_t)(b0 + bl) * C + cc * 8) + 1);
-            d[0] = g0.x * inv_lp; d[1] = g0.y * inv_lp; d[2] = g0.z * inv_lp; d[3] = g0.w * inv_lp;
-            d[4] = g1.x * inv_lp; d[5] = g1.y * inv_lp; d[6] = g1.z * inv_lp; d[7] = g1.w * inv_lp;
-        }
+        const uint4 u0 = __ldg(y + row * L + 2 * j), u1 = __ldg(y + row * L + 2 * j + 1);
+        load_dgrad8(dp, dgap, row, Lp, j, b0 + bl, C, cc, inv_lp, d);
+        bf8_unpack(u0, a0);
+        bf8_unpack(u1, a1);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const PoolGrad r = pool_grad(a0[i], a1[i], d[i], mean[i], rstd[i], sc[i], sf[i]);
-            o0[i] = sc[i] * (r.g0 - m1[i] - r.xh0 * m2[i]);
-            o1[i] = sc[i] * (r.g1 - m1[i] - r.xh1 * m2[i]);
+            bool s0, s1;
+            pool_sel(a0[i], a1[i], sc[i], sf[i], s0, s1);
+            const float gd = sc[i] * d[i];
+            o0[i] = fmaf(A[i], a0[i], Bc[i]) + (s0 ? gd : 0.f);
+            o1[i] = fmaf(A[i], a1[i], Bc[i]) + (s1 ? gd : 0.f);
             sdy[i] += o0[i] + o1[i];
         }
         dy[row * L + 2 * j] = bf8_pack(o0);
@@ -634,12 +651,11 @@ bn_bwd_apply_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__ 
             float a[8], o[8];
             bf8_unpack(__ldg(y + row * L + L - 1), a);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                o[i] = sc[i] * (0.f - m1[i] - (a[i] - mean[i]) * rstd[i] * m2[i]);
-                sdy[i] += o[i];
-            }
+            for (int i = 0; i < 8; ++i) { o[i] = fmaf(A[i], a[i], Bc[i]); sdy[i] += o[i]; }
             dy[row * L + L - 1] = bf8_pack(o);
         }
+        j += blockDim.x;
+        while (j >= Lp) { j -= Lp; ++bl; }
     }
     if (db_part != nullptr) {
         block_sum_vec<8>(sdy, sh);

@@ -17,6 +17,7 @@
 // Warp roles: warp 0 = TMA producer (input tile once, then a 4-stage ring of weight slabs),
 // warp 1 = single-thread MMA issuer, warps 2..5 = epilogue (tcgen05.ld -> +bias -> bf16 -> HBM).
 #include "tc_common.cuh"
+#include <cstdlib>
 
 // ---------------------------------------------------------------- host: tensor maps
 ecg_tmap_encode_fn ecg_get_tmap_encode() {
@@ -132,10 +133,13 @@ constexpr int TC_ROWS = 144;        // input rows staged: 128 + 14 halo, rounded
 constexpr int TC_NST = 4;           // weight ring depth
 constexpr int TC_HDR = 1024;        // barriers + TMEM slot
 
+// Each CTA owns up to R output tiles (R accumulators side by side in TMEM) that share ONE pass
+// over the weight ring: the L2 -> shared-memory weight traffic per FLOP drops by R, which is what
+// bounds this kernel otherwise (a 128-row tile reuses each weight byte only 128 times).
 __global__ void __launch_bounds__(192, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __nv_bfloat16* __restrict__ wprep,
                const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
-               int Ci, int Co, int L, int kch, uint32_t tmem_cols) {
+               int Ci, int Co, int L, int kch, uint32_t tmem_cols, int R, int total_tiles, int tiles_t) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);            // [TC_NST]
     uint64_t* empty = full + TC_NST;                                // [TC_NST]
@@ -145,14 +149,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __nv_bfloat16* __
     const uint32_t xbytes = (uint32_t)Ci * TC_ROWS * 2;
     const uint32_t xbytes_al = (xbytes + 1023u) & ~1023u;
     uint8_t* xs = smem + TC_HDR;
-    uint8_t* wsm = xs + xbytes_al;
+    uint8_t* wsm = xs + (size_t)R * xbytes_al;
     const uint32_t stage_bytes = (uint32_t)kch * Co * 2;
     const int groups = Ci / kch;
     const int nstage = ECG_KS * groups;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t0 = blockIdx.x * TC_TILE_M;
-    const int b = blockIdx.y;
+    const int tile0 = blockIdx.x * R;
+    const int rcount = min(R, total_tiles - tile0);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < TC_NST; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(empty + i, 1); }
@@ -170,8 +174,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __nv_bfloat16* __
 
     if (warp == 0) {
         if (lane == 0) {
-            tc::mbar_arrive_expect_tx(xfull, xbytes);
-            tc::tma_load_4d(xs, &xmap, xfull, 0, t0 - ECG_PAD, 0, b);
+            tc::mbar_arrive_expect_tx(xfull, xbytes * (uint32_t)rcount);
+            for (int r = 0; r < rcount; ++r) {
+                const int tile = tile0 + r;
+                const int b = tile / tiles_t, t0 = (tile - b * tiles_t) * TC_TILE_M;
+                tc::tma_load_4d(xs + (size_t)r * xbytes_al, &xmap, xfull, 0, t0 - ECG_PAD, 0, b);
+            }
             for (int s = 0; s < nstage; ++s) {
                 const int slot = s % TC_NST;
                 if (s >= TC_NST) tc::mbar_wait(empty + slot, ((s / TC_NST) - 1) & 1);
@@ -194,39 +202,45 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __nv_bfloat16* __
                 tc::mbar_wait(full + slot, (s / TC_NST) & 1);
                 tc::fence_after_sync();
                 const uint32_t wbase = ws_addr + slot * stage_bytes;
-                const uint32_t xbase = xs_addr + (uint32_t)(g * (kch / 8)) * (TC_ROWS * 16) + (uint32_t)k * 16;
-                for (int j = 0; j < kch / 16; ++j) {
-                    const uint64_t ad = tc::make_desc(xbase + (uint32_t)(2 * j) * (TC_ROWS * 16), TC_ROWS * 16, 128);
-                    const uint64_t bd = tc::make_desc(wbase + (uint32_t)(2 * j) * (Co * 16), (uint32_t)Co * 16, 128);
-                    tc::mma_bf16(tmem_base, ad, bd, idesc, (s > 0 || j > 0) ? 1u : 0u);
+                const uint32_t xoff = (uint32_t)(g * (kch / 8)) * (TC_ROWS * 16) + (uint32_t)k * 16;
+                for (int r = 0; r < rcount; ++r) {
+                    const uint32_t xbase = xs_addr + (uint32_t)r * xbytes_al + xoff;
+                    for (int j = 0; j < kch / 16; ++j) {
+                        const uint64_t ad = tc::make_desc(xbase + (uint32_t)(2 * j) * (TC_ROWS * 16), TC_ROWS * 16, 128);
+                        const uint64_t bd = tc::make_desc(wbase + (uint32_t)(2 * j) * (Co * 16), (uint32_t)Co * 16, 128);
+                        tc::mma_bf16(tmem_base + (uint32_t)(r * Co), ad, bd, idesc, (s > 0 || j > 0) ? 1u : 0u);
+                    }
                 }
                 tc::mma_commit(empty + slot);          // frees the weight slot when these MMAs finish
             }
-            tc::mma_commit(accfull);                   // accumulator complete
+            tc::mma_commit(accfull);                   // all accumulators complete
         }
     } else {
         const int q = warp & 3;                        // TMEM lane quarter this warp may access
         const int row = 32 * q + lane;
-        const int t = t0 + row;
         tc::mbar_wait(accfull, 0);
         tc::fence_after_sync();
-        const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16);
         const size_t chunk_stride = (size_t)L * 8;     // elements between channel chunks
-        __nv_bfloat16* yrow = y + ((size_t)b * (Co / 8) * L + t) * 8;
-        for (int c0 = 0; c0 < Co; c0 += 32) {
-            float v[32];
-            tc::tmem_ld32(taddr + (uint32_t)c0, v);
-            tc::tmem_ld_wait();
-            if (t < L) {
+        for (int r = 0; r < rcount; ++r) {
+            const int tile = tile0 + r;
+            const int b = tile / tiles_t, t = (tile - b * tiles_t) * TC_TILE_M + row;
+            const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(r * Co);
+            __nv_bfloat16* yrow = y + ((size_t)b * (Co / 8) * L + t) * 8;
+            for (int c0 = 0; c0 < Co; c0 += 32) {
+                float v[32];
+                tc::tmem_ld32(taddr + (uint32_t)c0, v);
+                tc::tmem_ld_wait();
+                if (t < L) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float o[8];
+                    for (int i = 0; i < 4; ++i) {
+                        float o[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        o[j] = v[8 * i + j] + (bias != nullptr ? __ldg(bias + c0 + 8 * i + j) : 0.f);
-                    const uint4 pk = make_uint4(tc::pack_bf16(o[0], o[1]), tc::pack_bf16(o[2], o[3]),
-                                                tc::pack_bf16(o[4], o[5]), tc::pack_bf16(o[6], o[7]));
-                    *reinterpret_cast<uint4*>(yrow + (size_t)(c0 / 8 + i) * chunk_stride) = pk;
+                        for (int j = 0; j < 8; ++j)
+                            o[j] = v[8 * i + j] + (bias != nullptr ? __ldg(bias + c0 + 8 * i + j) : 0.f);
+                        const uint4 pk = make_uint4(tc::pack_bf16(o[0], o[1]), tc::pack_bf16(o[2], o[3]),
+                                                    tc::pack_bf16(o[4], o[5]), tc::pack_bf16(o[6], o[7]));
+                        *reinterpret_cast<uint4*>(yrow + (size_t)(c0 / 8 + i) * chunk_stride) = pk;
+                    }
                 }
             }
         }
@@ -253,16 +267,26 @@ extern "C" int ecgb200_conv1d_fwd_bf16(const void* xb, const void* wprep, const 
     if (rc) return rc;
     const int kch = Ci < 64 ? Ci : 64;
     const uint32_t xbytes_al = ((uint32_t)Ci * TC_ROWS * 2 + 1023u) & ~1023u;
-    const size_t smem = TC_HDR + xbytes_al + (size_t)TC_NST * kch * Co * 2;
+    const size_t wring = (size_t)TC_NST * kch * Co * 2;
+    const int tiles_t = ecg_cdiv(L, TC_TILE_M);
+    const int total = B * tiles_t;
+    // tiles per CTA: bounded by TMEM (512 fp32 columns), shared memory (~200 KB) and by keeping >= ~1 wave of CTAs
+    int R = 512 / Co;
+    if (R > 2) R = 2;
+    if (const char* e = getenv("ECGB200_CONV_R")) { const int v = atoi(e); if (v >= 1 && v <= 16) R = v; }   // tuning
+    if (R * Co > 512) R = 512 / Co;
+    while (R > 1 && TC_HDR + (size_t)R * xbytes_al + wring > 225 * 1024) --R;
+    while (R > 1 && ecg_cdiv(total, R) < 120) --R;
+    const size_t smem = TC_HDR + (size_t)R * xbytes_al + wring;
     static size_t smem_set = 0;
     if (smem > smem_set) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         smem_set = smem;
     }
-    dim3 grid(ecg_cdiv(L, TC_TILE_M), B);
-    conv_tc_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(xmap, (const __nv_bfloat16*)wprep, bias,
-                                                              (__nv_bfloat16*)yb, Ci, Co, L, kch, tmem_cols_for(Co));
+    conv_tc_kernel<<<ecg_cdiv(total, R), 192, smem, (cudaStream_t)stream>>>(
+        xmap, (const __nv_bfloat16*)wprep, bias, (__nv_bfloat16*)yb, Ci, Co, L, kch, tmem_cols_for(R * Co), R,
+        total, tiles_t);
     return ecg_launch_status();
 }
 
