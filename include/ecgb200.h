@@ -85,6 +85,21 @@ int ecgb200_conv1d_prep_weights_bf16(const float* w, void* wf, void* wd, int Co,
 int ecgb200_conv1d_fwd_bf16(const void* xb, const void* wprep, const float* bias, void* yb,
                             int B, int Ci, int Co, int L, void* stream);
 
+/* Same conv, persistent one-CTA-per-SM kernel, that also emits the train-mode BatchNorm statistics of
+ * its (bf16-rounded) outputs: stat_part float[parts][2][Co] = per-CTA {sum, sum of squares},
+ * parts = ecgb200_conv1d_stat_parts_bf16(B,Ci,Co,L) (<= number of SMs).  stat_part may be NULL.
+ * ecgb200_conv1d_fwd_bf16 is this call with stat_part == NULL. */
+int ecgb200_conv1d_fwd_stats_bf16(const void* xb, const void* wprep, const float* bias, void* yb,
+                                  float* stat_part, int B, int Ci, int Co, int L, void* stream);
+int ecgb200_conv1d_stat_parts_bf16(int B, int Ci, int Co, int L);
+/* Train-mode BatchNorm1d + ReLU + MaxPool1d(2) (+GAP) in ONE pass over yb: finalises the statistics from
+ * the conv partials (mean, biased var -> bn_state {mean,rstd,scale,shift}; running stats with momentum and
+ * the unbiased variance; *num_batches_tracked += 1), then applies them.  ecg_cnn.py:14-16,46,62. */
+int ecgb200_bn_relu_pool_fwd_train_bf16(const void* yb, const float* stat_part, int nparts, const float* gamma,
+                                        const float* beta, float* running_mean, float* running_var,
+                                        int64_t* num_batches_tracked, float* bn_state, void* pb, float* gap,
+                                        int B, int C, int L, float momentum, float eps, void* stream);
+
 /* dW (Co,Ci,15) fp32 and db (Co) fp32 from blocked-bf16 dy [B][Co/8][L][8] and x [B][Cip/8][L][8]
  * (Cip = Ci rounded up to 16) on tcgen05, accumulators resident in TMEM across the whole batch
  * share of a CTA; split-K partials in ws (ecgb200_conv1d_wgrad_bf16_ws_bytes) are reduced in a
@@ -175,6 +190,40 @@ int ecgb200_bce_logits_f32(const float* logits, const float* target, float* loss
 int ecgb200_adamw_f32(int ntensors, float* const* p, const float* const* g, float* const* m,
                       float* const* v, const int64_t* numel, const float* hyper, int* step_ctr,
                       void* stream);
+
+/* ------------------------------------------------ fused per-step kernels (TrainStep engine) --
+ * Step prologue in one launch: pack x (B,Ci0,T) fp32 -> xb blocked bf16 (ecgb200_pack_input_bf16), re-lay the
+ * nlayers <= 4 conv weights (ecgb200_conv1d_prep_weights_bf16), transpose the proj weight wp (F,Cin) ->
+ * wpT (Cin,F) [wp may be NULL], and *step_ctr += 1 [may be NULL].  w/wf/wd/co/ci are HOST arrays. */
+int ecgb200_step_prep_bf16(const float* x, void* xb, int B, int Ci0, int T, int nlayers,
+                           const float* const* w, void* const* wf, void* const* wd, const int* co,
+                           const int* ci, const float* wp, float* wpT, int F, int Cin, int* step_ctr,
+                           void* stream);
+/* ECGCNN head, forward + loss + input gradients in one launch (ecg_cnn.py:63-64, loop.py:32-33):
+ *   z = gap Wp^T + bp; logits = z Wh^T + bh; BCE terms; dlogits = (sigmoid-y)*gscale/(B*NL);
+ *   dz = dlogits Wh; dgap = dz Wp.   loss_part[ecgb200_head_loss_parts(B)] = partial sums of the BCE terms.
+ * Cin, F <= 256, NL <= 8. */
+int ecgb200_head_fwd_bwd_f32(const float* gap, const float* wpT, const float* wp, const float* bp,
+                             const float* wh, const float* bh, const float* target, float* z, float* logits,
+                             float* dlogits, float* dz, float* dgap, float* loss_part, int B, int Cin, int F,
+                             int NL, float gscale, void* stream);
+int ecgb200_head_loss_parts(int B);
+/* ... and its weight gradients + the scalar loss (only the optimizer needs them; runs beside the conv
+ * backward): dWp = dz^T gap, dbp, dWh = dlogits^T z, dbh, loss = mean BCE. */
+int ecgb200_head_wgrad_f32(const float* gap, const float* z, const float* dz, const float* dlogits,
+                           const float* loss_part, float* dwp, float* dbp, float* dwh, float* dbh, float* loss,
+                           int B, int Cin, int F, int NL, void* stream);
+/* AdamW (as ecgb200_adamw_f32) over one flat, 16-byte aligned array; t = *step_now, the 1-based step index
+ * already incremented by ecgb200_step_prep_bf16. */
+int ecgb200_adamw_flat_f32(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper,
+                           const int* step_now, void* stream);
+
+/* Debug only: when buf != NULL, CTA 0 of the bf16 conv kernel writes clock64() stamps of its pipeline
+ * events into buf[0..63] (device memory).  NULL switches tracing off (the default). */
+int ecgb200_debug_set_trace(long long* buf);
+/* Debug only: pinned (device-visible) host buffer of >= 4 words; a barrier wait that exceeds its 2 s deadlock
+ * limit records {0xDEAD, block<<32|thread, smem address<<32|parity} there before the kernel traps. */
+int ecgb200_debug_set_diag(unsigned long long* pinned_host);
 
 /* --------------------------------------------------------------- Grad-CAM --
  * All-class batched Grad-CAM from the raw 4th-conv output A (B,C,L') in eval mode,

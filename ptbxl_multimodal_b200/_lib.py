@@ -50,6 +50,16 @@ _SIGS = {
     "ecgb200_bn_relu_pool_fwd_bf16": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "ecgb200_bn_relu_pool_bwd_bf16": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "ecgb200_bn_nsplit": (_I, [_I, _I]),
+    "ecgb200_conv1d_fwd_stats_bf16": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "ecgb200_conv1d_stat_parts_bf16": (_I, [_I, _I, _I, _I]),
+    "ecgb200_bn_relu_pool_fwd_train_bf16": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _P]),
+    "ecgb200_step_prep_bf16": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
+    "ecgb200_head_fwd_bwd_f32": (_I, [_P] * 13 + [_I, _I, _I, _I, _F, _P]),
+    "ecgb200_head_loss_parts": (_I, [_I]),
+    "ecgb200_head_wgrad_f32": (_I, [_P] * 10 + [_I, _I, _I, _I, _P]),
+    "ecgb200_debug_set_trace": (_I, [_P]),
+    "ecgb200_debug_set_diag": (_I, [_P]),
+    "ecgb200_adamw_flat_f32": (_I, [_P, _P, _P, _P, C.c_int64, _P, _P, _P]),
 }
 
 EXPORTED = tuple(_SIGS)

@@ -364,13 +364,36 @@ __device__ __forceinline__ void block_sum_vec(float* v, float* sh /* [8][NV] */)
 // Work split: grid (C/8, NS); block (cc, s) owns samples [s*tile_b, min(B, (s+1)*tile_b)) of channel
 // chunk cc and walks the flattened (sample, time) index space with 256 threads, so that every
 // block has a few thousand 16-byte vectors to stream and exactly ONE block reduction at the end.
-__host__ __device__ inline int bnb_tile_b(int B, int C) {
-    int ns = (592 + C / 8 - 1) / (C / 8);          // ~4 blocks per SM over the whole grid
+__host__ __device__ inline int bnb_tile_b(int B, int C, int blocks_per_sm = 4) {
+    int ns = (148 * blocks_per_sm) / (C / 8);      // one full wave of resident blocks, never more
     if (ns > B) ns = B;
     if (ns < 1) ns = 1;
     return (B + ns - 1) / ns;
 }
-extern "C" int ecgb200_bn_nsplit(int B, int C) { const int tb = bnb_tile_b(B, C); return (B + tb - 1) / tb; }
+// backward kernels hold ~90 registers: 3 blocks of 256 threads per SM
+extern "C" int ecgb200_bn_nsplit(int B, int C) { const int tb = bnb_tile_b(B, C, 3); return (B + tb - 1) / tb; }
+
+// Merge `nparts` partial pairs laid out part[i][2][C] for the 8 channels of chunk cc with all 256
+// threads (double, fixed order => deterministic): out[0..7] = first moments, out[8..15] = second.
+__device__ __forceinline__ void merge_parts8(const float* __restrict__ part, int nparts, int C, int cc,
+                                             double* shd /* [32*16] */, double* out /* [16] */) {
+    const int ch = threadIdx.x & 7, grp = threadIdx.x >> 3;
+    double a = 0.0, b = 0.0;
+    for (int i = grp; i < nparts; i += 32) {
+        a += (double)__ldg(part + ((size_t)i * 2 + 0) * C + cc * 8 + ch);
+        b += (double)__ldg(part + ((size_t)i * 2 + 1) * C + cc * 8 + ch);
+    }
+    shd[grp * 16 + ch] = a;
+    shd[grp * 16 + 8 + ch] = b;
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        double t = 0.0;
+#pragma unroll 8
+        for (int g = 0; g < 32; ++g) t += shd[g * 16 + threadIdx.x];
+        out[threadIdx.x] = t;
+    }
+    __syncthreads();
+}
 
 // {sum, centred M2} per (channel, split): part[c][s], part[C + c][s]
 __global__ void __launch_bounds__(256)
@@ -521,6 +544,121 @@ extern "C" int ecgb200_bn_relu_pool_fwd_bf16(const void* yb, const float* bn_sta
     return ecg_launch_status();
 }
 
+// Train-mode forward in ONE pass over y: every block first turns the conv epilogue's per-CTA
+// {sum, sum of squares} partials into mean / rstd / scale / shift for its 8 channels (identical in
+// every block; block row 0 publishes bn_state and updates the running statistics), then applies
+// BN + ReLU + MaxPool1d(2) (GAP variant: also the mean over time of the UNROUNDED pooled values).
+template <bool GAP>
+__global__ void __launch_bounds__(256, 4)
+bn_fwd_train_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__ part, int nparts,
+                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                         float* __restrict__ running_mean, float* __restrict__ running_var,
+                         int64_t* __restrict__ nbt, float* __restrict__ bn_state, uint4* __restrict__ p,
+                         float* __restrict__ gap, int B, int C, int L, int Lp, int tile_b, float momentum,
+                         float eps) {
+    __shared__ double shd[32 * 16], mom[16];
+    __shared__ float scs[8], sfs[8];
+    const int cc = blockIdx.x;
+    const int b0 = blockIdx.y * tile_b, nb = min(tile_b, B - b0);
+    merge_parts8(part, nparts, C, cc, shd, mom);
+    if (threadIdx.x < 8) {
+        const int c = cc * 8 + threadIdx.x;
+        const double n = (double)B * (double)L;
+        const double mean = mom[threadIdx.x] / n;
+        double var = mom[8 + threadIdx.x] / n - mean * mean;          // biased
+        if (var < 0.0) var = 0.0;
+        const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+        const float meanf = (float)mean;
+        const float scale = __ldg(gamma + c) * rstd;
+        const float shift = __ldg(beta + c) - meanf * scale;
+        scs[threadIdx.x] = scale;
+        sfs[threadIdx.x] = shift;
+        if (blockIdx.y == 0) {
+            bn_state[c] = meanf;
+            bn_state[C + c] = rstd;
+            bn_state[2 * C + c] = scale;
+            bn_state[3 * C + c] = shift;
+            if (running_mean != nullptr) {
+                const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
+                running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * meanf;
+                running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+            }
+            if (c == 0 && nbt != nullptr) *nbt += 1;
+        }
+    }
+    __syncthreads();
+    float sc[8], sf[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sc[i] = scs[i]; sf[i] = sfs[i]; }
+    if (!GAP) {
+        const int n = nb * Lp;
+        for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+            const int bl = idx / Lp, j = idx - bl * Lp;
+            const size_t row = (size_t)(b0 + bl) * (C / 8) + cc;
+            float a0[8], a1[8], m[8];
+            bf8_unpack(__ldg(y + row * L + 2 * j), a0);
+            bf8_unpack(__ldg(y + row * L + 2 * j + 1), a1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float r0 = fmaxf(fmaf(a0[i], sc[i], sf[i]), 0.f), r1 = fmaxf(fmaf(a1[i], sc[i], sf[i]), 0.f);
+                m[i] = fmaxf(r0, r1);
+            }
+            p[row * Lp + j] = bf8_pack(m);
+        }
+    } else {
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        for (int bl = w; bl < nb; bl += nw) {
+            const size_t row = (size_t)(b0 + bl) * (C / 8) + cc;
+            float acc[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+            for (int j = lane; j < Lp; j += 32) {
+                float a0[8], a1[8], m[8];
+                bf8_unpack(__ldg(y + row * L + 2 * j), a0);
+                bf8_unpack(__ldg(y + row * L + 2 * j + 1), a1);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float r0 = fmaxf(fmaf(a0[i], sc[i], sf[i]), 0.f), r1 = fmaxf(fmaf(a1[i], sc[i], sf[i]), 0.f);
+                    m[i] = fmaxf(r0, r1);
+                    acc[i] += m[i];
+                }
+                if (p != nullptr) p[row * Lp + j] = bf8_pack(m);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = warp_sum(acc[i]);
+            if (lane < 8) {
+                float t = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) if (i == lane) t = acc[i];
+                gap[(size_t)(b0 + bl) * C + cc * 8 + lane] = t / (float)Lp;
+            }
+        }
+    }
+}
+
+// yb blocked bf16; stat_part float[nparts][2][C] from ecgb200_conv1d_fwd_stats_bf16.
+extern "C" int ecgb200_bn_relu_pool_fwd_train_bf16(const void* yb, const float* stat_part, int nparts,
+                                                   const float* gamma, const float* beta, float* running_mean,
+                                                   float* running_var, int64_t* nbt, float* bn_state, void* pb,
+                                                   float* gap, int B, int C, int L, float momentum, float eps,
+                                                   void* stream) {
+    if (!yb || !stat_part || nparts <= 0 || !gamma || !beta || !bn_state || (!pb && !gap) || B <= 0 || C <= 0 ||
+        (C & 7) || L < 2)
+        return ECGB200_EINVAL;
+    const int Lp = L / 2;
+    const int tile_b = bnb_tile_b(B, C, 4), NS = (B + tile_b - 1) / tile_b;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (gap != nullptr)
+        bn_fwd_train_bf16_kernel<true><<<dim3(C / 8, NS), 256, 0, st>>>(
+            (const uint4*)yb, stat_part, nparts, gamma, beta, running_mean, running_var, nbt, bn_state, (uint4*)pb,
+            gap, B, C, L, Lp, tile_b, momentum, eps);
+    else
+        bn_fwd_train_bf16_kernel<false><<<dim3(C / 8, NS), 256, 0, st>>>(
+            (const uint4*)yb, stat_part, nparts, gamma, beta, running_mean, running_var, nbt, bn_state, (uint4*)pb,
+            nullptr, B, C, L, Lp, tile_b, momentum, eps);
+    return ecg_launch_status();
+}
+
 // Routing of one pool pair in terms of the raw conv outputs a0, a1 (first index wins ties, ReLU mask):
 //   sel0 = relu(bn(a0)) >= relu(bn(a1)) && relu(bn(a0)) > 0 ;  sel1 = relu(bn(a1)) > relu(bn(a0))
 __device__ __forceinline__ void pool_sel(float a0, float a1, float sc, float sf, bool& sel0, bool& sel1) {
@@ -583,8 +721,8 @@ bn_bwd_reduce_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__
         float t1 = 0.f, t2 = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) if (i == threadIdx.x) { t1 = s[i]; t2 = s[8 + i]; }
-        part[(size_t)(cc * 8 + threadIdx.x) * NS + blockIdx.y] = t1;
-        part[((size_t)C + cc * 8 + threadIdx.x) * NS + blockIdx.y] = t2;
+        part[((size_t)blockIdx.y * 2 + 0) * C + cc * 8 + threadIdx.x] = t1;
+        part[((size_t)blockIdx.y * 2 + 1) * C + cc * 8 + threadIdx.x] = t2;
     }
 }
 
@@ -600,13 +738,14 @@ bn_bwd_apply_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__ 
                          float inv_n, int train, int tile_b) {
     __shared__ float sh[8 * 8];
     __shared__ float cA[8], cB[8];
+    __shared__ double shd[32 * 16], mom[16];
     const int cc = blockIdx.x, NS = gridDim.y;
     const int b0 = blockIdx.y * tile_b, nb = min(tile_b, B - b0);
     const float inv_lp = 1.0f / (float)Lp;
+    merge_parts8(part, NS, C, cc, shd, mom);
     if (threadIdx.x < 8) {
         const int c = cc * 8 + threadIdx.x;
-        double sg = 0.0, sga = 0.0;
-        for (int i = 0; i < NS; ++i) { sg += (double)part[(size_t)c * NS + i]; sga += (double)part[((size_t)C + c) * NS + i]; }
+        const double sg = mom[threadIdx.x], sga = mom[8 + threadIdx.x];
         const float mean = __ldg(bn_state + c), rstd = __ldg(bn_state + C + c), scl = __ldg(bn_state + 2 * C + c);
         const double sgx = (double)rstd * (sga - (double)mean * sg);       // sum g * xhat
         if (blockIdx.y == 0) {
@@ -678,7 +817,7 @@ extern "C" int ecgb200_bn_relu_pool_bwd_bf16(const void* yb, const float* bn_sta
     if (dgap != nullptr && (((uintptr_t)dgap & 15) != 0)) return ECGB200_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     const int Lp = L / 2;
-    const int tile_b = bnb_tile_b(B, C), NS = (B + tile_b - 1) / tile_b;
+    const int tile_b = bnb_tile_b(B, C, 3), NS = (B + tile_b - 1) / tile_b;
     float* part = (float*)ws;
     bn_bwd_reduce_bf16_kernel<<<dim3(C / 8, NS), 256, 0, st>>>((const uint4*)yb, bn_state, (const uint4*)dpb,
                                                               dgap, part, B, C, L, Lp, tile_b);

@@ -128,126 +128,351 @@ extern "C" int ecgb200_conv1d_prep_weights_bf16(const float* w, void* wf, void* 
 }
 
 // ---------------------------------------------------------------- forward / dgrad implicit GEMM
-constexpr int TC_TILE_M = 128;      // output time steps per CTA (TMEM lanes)
+constexpr int TC_TILE_M = 128;      // output time steps per tile (TMEM lanes)
 constexpr int TC_ROWS = 144;        // input rows staged: 128 + 14 halo, rounded to 8
-constexpr int TC_NST = 4;           // weight ring depth
 constexpr int TC_HDR = 1024;        // barriers + TMEM slot
+constexpr int C2_MAXST = 8;         // weight ring depth (max)
+constexpr int C2_STATB = 8 * 2 * 256 * 4;   // per-epilogue-warp {sum, sumsq} x 256 channels
 
-// Each CTA owns up to R output tiles (R accumulators side by side in TMEM) that share ONE pass
-// over the weight ring: the L2 -> shared-memory weight traffic per FLOP drops by R, which is what
-// bounds this kernel otherwise (a 128-row tile reuses each weight byte only 128 times).
-__global__ void __launch_bounds__(192, 1)
+extern "C" int ecgb200_debug_set_diag(unsigned long long* pinned_host) {
+    cudaError_t e = cudaMemcpyToSymbol(tc::g_mbar_diag, &pinned_host, sizeof(pinned_host));
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+// Debug timeline (clock64 stamps of CTA 0), enabled by ecgb200_debug_set_trace(ptr != NULL).
+__device__ long long* g_conv_trace = nullptr;
+#define CTR(id) do { if (trace != nullptr && blockIdx.x == 0) trace[id] = clock64(); } while (0)
+extern "C" int ecgb200_debug_set_trace(long long* buf) {
+    cudaError_t e = cudaMemcpyToSymbol(g_conv_trace, &buf, sizeof(buf));
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+struct Conv2Cfg {
+    int Ci, Co, L, kch;              // kch = input channels per weight stage
+    int R;                           // tiles per group (accumulators side by side, one weight pass)
+    int AS;                          // accumulator stages (2 = epilogue overlaps the next group's MMAs)
+    int NXB;                         // input-tile buffers (2 = next group's tiles stream in under the MMAs)
+    int NST;                         // weight ring depth; 0 = whole weight tensor resident in shared memory
+    int total_tiles, tiles_t, ngroups;
+    uint32_t tmem_cols, xbytes_al;
+};
+
+// All MMAs of one weight stage: RC tiles x NJ K-steps, fully unrolled so that every descriptor is
+// "uniform base + constant multiple of a uniform stride" (stays in the uniform datapath), issued four per
+// asm statement with compile-time accumulate flags.  FIRST: this stage starts the accumulators (j == 0).
+template <int NJ, int RC, bool FIRST>
+__device__ __forceinline__ void conv_issue_stage(uint32_t acc0, uint32_t alo_k, uint32_t wlo, uint32_t co,
+                                                 uint32_t xal16, uint32_t bstep, uint32_t ahi, uint32_t bhi,
+                                                 uint32_t idesc, bool leader, uint64_t* commit_bar) {
+    constexpr int CNT = NJ * RC;
+    uint32_t dd[CNT], al[CNT], bl[CNT];
+#pragma unroll
+    for (int r = 0; r < RC; ++r)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            dd[r * NJ + j] = acc0 + (uint32_t)r * co;
+            al[r * NJ + j] = alo_k + (uint32_t)r * xal16 + (uint32_t)(j * 2 * TC_ROWS);
+            bl[r * NJ + j] = wlo + (uint32_t)j * bstep;
+        }
+    if (!leader) return;
+    constexpr int MASK = FIRST ? (NJ == 4 ? 0xE : (NJ == 2 ? 0xA : 0x0)) : 0xF;
+#pragma unroll
+    for (int c = 0; c + 4 <= CNT; c += 4) tc::mma_bf16_x4<MASK>(dd + c, al + c, bl + c, ahi, bhi, idesc);
+#pragma unroll
+    for (int c = CNT & ~3; c < CNT; ++c) {
+        if (!FIRST || (c % NJ) != 0) tc::mma_bf16_c<1>(dd[c], al[c], bl[c], ahi, bhi, idesc);
+        else tc::mma_bf16_c<0>(dd[c], al[c], bl[c], ahi, bhi, idesc);
+    }
+    // The commit MUST stay inside this one-lane region: when it sat in its own `if (leader)` after the
+    // warp had reconverged, ptxas turned it into an UNGUARDED warp-level UTCBAR (operand broadcast from the
+    // leader) and the barrier over-arrived -> sporadic producer/consumer deadlock on the weight ring.
+    if (commit_bar != nullptr) tc::mma_commit(commit_bar);
+}
+
+template <int NJ, bool FIRST>
+__device__ __forceinline__ void conv_issue_stage_rc(int rcount, uint32_t acc0, uint32_t alo_k, uint32_t wlo,
+                                                    uint32_t co, uint32_t xal16, uint32_t bstep, uint32_t ahi,
+                                                    uint32_t bhi, uint32_t idesc, bool leader, uint64_t* cb) {
+    switch (rcount) {
+        case 4: conv_issue_stage<NJ, 4, FIRST>(acc0, alo_k, wlo, co, xal16, bstep, ahi, bhi, idesc, leader, cb); break;
+        case 3: conv_issue_stage<NJ, 3, FIRST>(acc0, alo_k, wlo, co, xal16, bstep, ahi, bhi, idesc, leader, cb); break;
+        case 2: conv_issue_stage<NJ, 2, FIRST>(acc0, alo_k, wlo, co, xal16, bstep, ahi, bhi, idesc, leader, cb); break;
+        default: conv_issue_stage<NJ, 1, FIRST>(acc0, alo_k, wlo, co, xal16, bstep, ahi, bhi, idesc, leader, cb); break;
+    }
+}
+
+template <bool FIRST>
+__device__ __forceinline__ void conv_issue_stage_any(int nj, int rcount, uint32_t acc0, uint32_t alo_k,
+                                                     uint32_t wlo, uint32_t co, uint32_t xal16, uint32_t bstep,
+                                                     uint32_t ahi, uint32_t bhi, uint32_t idesc, bool leader,
+                                                     uint64_t* cb) {
+    if (nj == 4) conv_issue_stage_rc<4, FIRST>(rcount, acc0, alo_k, wlo, co, xal16, bstep, ahi, bhi, idesc, leader, cb);
+    else if (nj == 2) conv_issue_stage_rc<2, FIRST>(rcount, acc0, alo_k, wlo, co, xal16, bstep, ahi, bhi, idesc, leader, cb);
+    else conv_issue_stage_rc<1, FIRST>(rcount, acc0, alo_k, wlo, co, xal16, bstep, ahi, bhi, idesc, leader, cb);
+}
+
+// Persistent CTA (one per SM): loops over groups of R consecutive 128-step output tiles.
+//   warp 0   TMA producer: input tiles (double buffered) + weights (resident once, or a ring of slabs)
+//   warp 1   single-thread tcgen05.mma issuer, accumulators in TMEM (double buffered when they fit)
+//   warps 2-9 epilogue: tcgen05.ld -> +bias -> bf16 -> HBM, and the per-channel {sum, sum of squares}
+//            of the ROUNDED outputs for the train-mode BatchNorm that follows (one partial per CTA,
+//            combined in a fixed order by the consumer => deterministic).  Two warps share each TMEM
+//            lane quarter and split the (tile, 32-channel block) items between them: the epilogue is
+//            bound by one warp's instruction latency, not by bandwidth.
+constexpr int C2_THREADS = 320;
+__global__ void __launch_bounds__(C2_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __nv_bfloat16* __restrict__ wprep,
-               const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
-               int Ci, int Co, int L, int kch, uint32_t tmem_cols, int R, int total_tiles, int tiles_t) {
+               const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, float* __restrict__ stat_part,
+               const Conv2Cfg P) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem);            // [TC_NST]
-    uint64_t* empty = full + TC_NST;                                // [TC_NST]
-    uint64_t* xfull = empty + TC_NST;
-    uint64_t* accfull = xfull + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfull + 1);
+    uint64_t* wfull = reinterpret_cast<uint64_t*>(smem);           // [C2_MAXST]
+    uint64_t* wempty = wfull + C2_MAXST;                            // [C2_MAXST]
+    uint64_t* xfull = wempty + C2_MAXST;                            // [2]
+    uint64_t* xempty = xfull + 2;                                   // [2]
+    uint64_t* accfull = xempty + 2;                                 // [2]
+    uint64_t* accempty = accfull + 2;                               // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + 2);
+    float* statsh = reinterpret_cast<float*>(smem + TC_HDR);        // [4][2][256]
+    uint8_t* xs = smem + TC_HDR + C2_STATB;
+    uint8_t* wsm = xs + (size_t)P.NXB * P.R * P.xbytes_al;
+
+    const int Ci = P.Ci, Co = P.Co, L = P.L, kch = P.kch, R = P.R;
     const uint32_t xbytes = (uint32_t)Ci * TC_ROWS * 2;
-    const uint32_t xbytes_al = (xbytes + 1023u) & ~1023u;
-    uint8_t* xs = smem + TC_HDR;
-    uint8_t* wsm = xs + (size_t)R * xbytes_al;
     const uint32_t stage_bytes = (uint32_t)kch * Co * 2;
     const int groups = Ci / kch;
     const int nstage = ECG_KS * groups;
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile0 = blockIdx.x * R;
-    const int rcount = min(R, total_tiles - tile0);
+    const bool resident = P.NST == 0;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);     // provably warp-uniform
+    const int lane = threadIdx.x & 31;
+    const int ngl = ((int)blockIdx.x < P.ngroups) ? (P.ngroups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    long long* const trace = g_conv_trace;
+    if (threadIdx.x == 0) CTR(0);
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < TC_NST; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(empty + i, 1); }
-        tc::mbar_init(xfull, 1);
-        tc::mbar_init(accfull, 1);
+        for (int i = 0; i < C2_MAXST; ++i) { tc::mbar_init(wfull + i, 1); tc::mbar_init(wempty + i, 1); }
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(xfull + i, 1); tc::mbar_init(xempty + i, 1);
+            tc::mbar_init(accfull + i, 1); tc::mbar_init(accempty + i, 8);
+        }
         tc::fence_barrier_init();
         tc::fence_proxy_async();
         tc::prefetch_tmap(&xmap);
     }
-    if (warp == 2) tc::tmem_alloc(tmem_slot, tmem_cols);
+    if (warp == 2) tc::tmem_alloc(tmem_slot, P.tmem_cols);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);        // uniform for the compiler too
+    if (threadIdx.x == 0) CTR(1);
 
     if (warp == 0) {
         if (lane == 0) {
-            tc::mbar_arrive_expect_tx(xfull, xbytes * (uint32_t)rcount);
-            for (int r = 0; r < rcount; ++r) {
-                const int tile = tile0 + r;
-                const int b = tile / tiles_t, t0 = (tile - b * tiles_t) * TC_TILE_M;
-                tc::tma_load_4d(xs + (size_t)r * xbytes_al, &xmap, xfull, 0, t0 - ECG_PAD, 0, b);
-            }
-            for (int s = 0; s < nstage; ++s) {
-                const int slot = s % TC_NST;
-                if (s >= TC_NST) tc::mbar_wait(empty + slot, ((s / TC_NST) - 1) & 1);
-                tc::mbar_arrive_expect_tx(full + slot, stage_bytes);
-                tc::bulk_load(wsm + (size_t)slot * stage_bytes,
-                              reinterpret_cast<const uint8_t*>(wprep) + (size_t)s * stage_bytes, stage_bytes,
-                              full + slot);
+            auto load_x = [&](int gi) {
+                const int xb = gi % P.NXB;
+                if (gi >= P.NXB) tc::mbar_wait(xempty + xb, ((gi / P.NXB) - 1) & 1);
+                const int tile0 = ((int)blockIdx.x + gi * (int)gridDim.x) * R;
+                const int rcount = min(R, P.total_tiles - tile0);
+                tc::mbar_arrive_expect_tx(xfull + xb, xbytes * (uint32_t)rcount);
+                for (int r = 0; r < rcount; ++r) {
+                    const int tile = tile0 + r;
+                    const int b = tile / P.tiles_t, t0 = (tile - b * P.tiles_t) * TC_TILE_M;
+                    tc::tma_load_4d(xs + (size_t)(xb * R + r) * P.xbytes_al, &xmap, xfull + xb, 0, t0 - ECG_PAD, 0, b);
+                }
+                if (gi < 4) CTR(8 + gi);                         // x load of group gi issued
+            };
+            if (ngl > 0) load_x(0);
+            if (resident) {
+                const uint32_t wbytes = (uint32_t)nstage * stage_bytes;
+                tc::mbar_arrive_expect_tx(wfull, wbytes);
+                for (uint32_t off = 0; off < wbytes; off += 16384u) {
+                    const uint32_t n = wbytes - off < 16384u ? wbytes - off : 16384u;
+                    tc::bulk_load(wsm + off, reinterpret_cast<const uint8_t*>(wprep) + off, n, wfull);
+                }
+                for (int gi = 1; gi < ngl; ++gi) load_x(gi);
+            } else {
+                int slot = 0;
+                uint32_t ephase = 1;                             // first pass over the ring: slots start free
+                for (int gi = 0; gi < ngl; ++gi) {
+                    // the next group's input tiles are requested once this group's MMAs are under way
+                    const int xat = nstage - 1 < P.NST ? nstage - 1 : P.NST;
+                    for (int s = 0; s < nstage; ++s) {
+                        if (!(gi == 0 && s < P.NST)) tc::mbar_wait(wempty + slot, ephase);
+                        tc::mbar_arrive_expect_tx(wfull + slot, stage_bytes);
+                        tc::bulk_load(wsm + (size_t)slot * stage_bytes,
+                                      reinterpret_cast<const uint8_t*>(wprep) + (size_t)s * stage_bytes, stage_bytes,
+                                      wfull + slot);
+                        if (s == xat && gi + 1 < ngl) load_x(gi + 1);
+                        if (++slot == P.NST) { slot = 0; ephase ^= 1; }
+                    }
+                }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = tc::make_idesc_bf16(TC_TILE_M, Co, 0, 0);
-            const uint32_t xs_addr = tc::smem_u32(xs);
-            const uint32_t ws_addr = tc::smem_u32(wsm);
-            tc::mbar_wait(xfull, 0);
+        // MMA issuer.  The WHOLE warp runs this loop with warp-uniform values and one elected lane issues:
+        // measured on B200, descriptors that reach tcgen05.mma through per-thread registers (R2UR transfers,
+        // run-time accumulate predicates) cost 130-420 cycles of issue per MMA against 47 (N<=64) / 64
+        // (N=128) / 128 (N=256) cycles of tensor time; descriptors are therefore built once, only their
+        // 14-bit address field (low word, 16-byte units) advances, and MMAs go out four per asm statement.
+        const bool leader = tc::elect_one();
+        const uint32_t idesc = tc::make_idesc_bf16(TC_TILE_M, Co, 0, 0);
+        const uint64_t adesc0 = tc::make_desc(0, TC_ROWS * 16, 128);
+        const uint64_t bdesc0 = tc::make_desc(0, (uint32_t)Co * 16, 128);
+        const uint32_t ahi = (uint32_t)(adesc0 >> 32), bhi = (uint32_t)(bdesc0 >> 32);
+        const uint32_t alo0 = (uint32_t)adesc0 + (tc::smem_u32(xs) >> 4);
+        const uint32_t blo0 = (uint32_t)bdesc0 + (tc::smem_u32(wsm) >> 4);
+        const uint32_t xal16 = P.xbytes_al >> 4, stage16 = stage_bytes >> 4;
+        const uint32_t bstep = (uint32_t)(2 * Co);             // two 8-channel chunks of the weight slab
+        const uint32_t gstep = (uint32_t)(kch / 8) * TC_ROWS;  // one channel group of the input tile
+        const int nj = kch / 16;                               // 1, 2 or 4 K-steps per weight stage
+        if (resident && ngl > 0) {
+            if (leader) tc::mbar_wait(wfull, 0);
+            __syncwarp();
             tc::fence_after_sync();
-            for (int s = 0; s < nstage; ++s) {
-                const int slot = s % TC_NST;
-                const int k = s / groups, g = s - k * groups;
-                tc::mbar_wait(full + slot, (s / TC_NST) & 1);
-                tc::fence_after_sync();
-                const uint32_t wbase = ws_addr + slot * stage_bytes;
-                const uint32_t xoff = (uint32_t)(g * (kch / 8)) * (TC_ROWS * 16) + (uint32_t)k * 16;
-                for (int r = 0; r < rcount; ++r) {
-                    const uint32_t xbase = xs_addr + (uint32_t)r * xbytes_al + xoff;
-                    for (int j = 0; j < kch / 16; ++j) {
-                        const uint64_t ad = tc::make_desc(xbase + (uint32_t)(2 * j) * (TC_ROWS * 16), TC_ROWS * 16, 128);
-                        const uint64_t bd = tc::make_desc(wbase + (uint32_t)(2 * j) * (Co * 16), (uint32_t)Co * 16, 128);
-                        tc::mma_bf16(tmem_base + (uint32_t)(r * Co), ad, bd, idesc, (s > 0 || j > 0) ? 1u : 0u);
+        }
+        if (lane == 0) CTR(3);                                 // resident weights landed
+        int slot = 0;
+        uint32_t wphase = 0;
+        for (int gi = 0; gi < ngl; ++gi) {
+            const int xb = gi % P.NXB, as = gi % P.AS;
+            const int tile0 = ((int)blockIdx.x + gi * (int)gridDim.x) * R;
+            const int rcount = min(R, P.total_tiles - tile0);
+            if (leader) {
+                tc::mbar_wait(xfull + xb, (gi / P.NXB) & 1);
+                if (gi < 4) CTR(16 + gi);                      // x tiles of group gi landed
+                if (gi >= P.AS) tc::mbar_wait(accempty + as, ((gi / P.AS) - 1) & 1);
+                if (gi < 4) CTR(24 + gi);                      // accumulator stage free
+            }
+            __syncwarp();
+            tc::fence_after_sync();
+            const uint32_t acc0 = tmem_base + (uint32_t)(as * R * Co);
+            const uint32_t alo_g = alo0 + (uint32_t)(xb * R) * xal16;
+            uint32_t wlo = blo0;                               // resident: walks the whole weight tensor
+            bool first = true;
+            for (int k = 0; k < ECG_KS; ++k) {
+                uint32_t alo_k = alo_g + (uint32_t)k;          // tap k = the same tile, k rows (16 B each) further
+                for (int g = 0; g < groups; ++g, alo_k += gstep) {
+                    if (!resident) {
+                        if (leader) tc::mbar_wait(wfull + slot, wphase);
+                        __syncwarp();
+                        tc::fence_after_sync();
+                        wlo = blo0 + (uint32_t)slot * stage16;
+                    }
+                    // the (tile r, K-step j) MMAs of this stage
+                    uint64_t* cb = resident ? nullptr : wempty + slot;   // frees the weight slot when these MMAs finish
+                    if (first) conv_issue_stage_any<true>(nj, rcount, acc0, alo_k, wlo, (uint32_t)Co, xal16, bstep, ahi, bhi, idesc, leader, cb);
+                    else conv_issue_stage_any<false>(nj, rcount, acc0, alo_k, wlo, (uint32_t)Co, xal16, bstep, ahi, bhi, idesc, leader, cb);
+                    first = false;
+                    if (!resident) {
+                        if (++slot == P.NST) { slot = 0; wphase ^= 1; }
+                    } else {
+                        wlo += stage16;
                     }
                 }
-                tc::mma_commit(empty + slot);          // frees the weight slot when these MMAs finish
             }
-            tc::mma_commit(accfull);                   // all accumulators complete
+            if (leader) {
+                tc::mma_commit(xempty + xb);           // input tiles of this group are free again
+                tc::mma_commit(accfull + as);          // accumulators of this group are complete
+                if (gi < 4) CTR(32 + gi);              // all MMAs of group gi issued
+            }
+            __syncwarp();
         }
     } else {
         const int q = warp & 3;                        // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;              // which of the two warps of this quarter
+        const int nblk = Co >> 5;
         const int row = 32 * q + lane;
-        tc::mbar_wait(accfull, 0);
-        tc::fence_after_sync();
         const size_t chunk_stride = (size_t)L * 8;     // elements between channel chunks
-        for (int r = 0; r < rcount; ++r) {
-            const int tile = tile0 + r;
-            const int b = tile / tiles_t, t = (tile - b * tiles_t) * TC_TILE_M + row;
-            const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(r * Co);
-            __nv_bfloat16* yrow = y + ((size_t)b * (Co / 8) * L + t) * 8;
-            for (int c0 = 0; c0 < Co; c0 += 32) {
-                float v[32];
-                tc::tmem_ld32(taddr + (uint32_t)c0, v);
-                tc::tmem_ld_wait();
-                if (t < L) {
+        const bool want_stats = stat_part != nullptr;
+        float ssum[8], ssq[8];                         // lane j: channel 32*cb + j, over this warp's rows
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float o[8];
+        for (int i = 0; i < 8; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
+        for (int gi = 0; gi < ngl; ++gi) {
+            const int as = gi % P.AS;
+            const int tile0 = ((int)blockIdx.x + gi * (int)gridDim.x) * R;
+            const int rcount = min(R, P.total_tiles - tile0);
+            tc::mbar_wait(accfull + as, (gi / P.AS) & 1);
+            if (gi < 4 && threadIdx.x == 64) CTR(40 + gi);       // accumulators of group gi complete
+            tc::fence_after_sync();
+            for (int r = 0; r < rcount; ++r) {
+                const int tile = tile0 + r;
+                const int b = tile / P.tiles_t, t = (tile - b * P.tiles_t) * TC_TILE_M + row;
+                const bool live = t < L;
+                const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)((as * R + r) * Co);
+                __nv_bfloat16* yrow = y + ((size_t)b * (Co / 8) * L + t) * 8;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            o[j] = v[8 * i + j] + (bias != nullptr ? __ldg(bias + c0 + 8 * i + j) : 0.f);
-                        const uint4 pk = make_uint4(tc::pack_bf16(o[0], o[1]), tc::pack_bf16(o[2], o[3]),
-                                                    tc::pack_bf16(o[4], o[5]), tc::pack_bf16(o[6], o[7]));
-                        *reinterpret_cast<uint4*>(yrow + (size_t)(c0 / 8 + i) * chunk_stride) = pk;
+                for (int cb = 0; cb < 8; ++cb) {
+                    if (cb < nblk && ((r * nblk + cb) & 1) == half) {
+                        const int c0 = cb * 32;
+                        float v[32];
+                        tc::tmem_ld32(taddr + (uint32_t)c0, v);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            uint32_t pk[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int c = 8 * i + 2 * j;
+                                const float o0 = v[c] + (bias != nullptr ? __ldg(bias + c0 + c) : 0.f);
+                                const float o1 = v[c + 1] + (bias != nullptr ? __ldg(bias + c0 + c + 1) : 0.f);
+                                pk[j] = tc::pack_bf16(o0, o1);
+                                const float2 rr = tc::unpack_bf16(pk[j]);      // the value the next kernels will read
+                                v[c] = live ? rr.x : 0.f;
+                                v[c + 1] = live ? rr.y : 0.f;
+                            }
+                            if (live)
+                                *reinterpret_cast<uint4*>(yrow + (size_t)(c0 / 8 + i) * chunk_stride) =
+                                    make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        }
+                        if (want_stats) {
+                            // transposing butterfly: 31 shuffles leave lane j with the sum of column j over 32 rows
+                            float sq[32];
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) sq[i] = v[i] * v[i];
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) {
+                                const bool up = (lane & o) != 0;
+#pragma unroll
+                                for (int i = 0; i < o; ++i) {
+                                    const float send = up ? v[i] : v[i + o], keep = up ? v[i + o] : v[i];
+                                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                                    const float send2 = up ? sq[i] : sq[i + o], keep2 = up ? sq[i + o] : sq[i];
+                                    sq[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, o);
+                                }
+                            }
+                            ssum[cb] += v[0];
+                            ssq[cb] += sq[0];
+                        }
                     }
                 }
+            }
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(accempty + as);
+            if (gi < 4 && threadIdx.x == 64) CTR(48 + gi);       // epilogue of group gi done
+        }
+        if (want_stats) {
+            float* mine = statsh + (size_t)(half * 4 + q) * 2 * 256;
+#pragma unroll
+            for (int cb = 0; cb < 8; ++cb)
+                if (cb < nblk) {
+                    mine[cb * 32 + lane] = ssum[cb];
+                    mine[256 + cb * 32 + lane] = ssq[cb];
+                }
+            asm volatile("bar.sync 1, 256;" ::: "memory");            // the eight epilogue warps only
+            const int e = threadIdx.x - 64;
+            for (int c = e; c < Co; c += 256) {
+                float s = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) { s += statsh[(w * 2 + 0) * 256 + c]; s2 += statsh[(w * 2 + 1) * 256 + c]; }
+                stat_part[((size_t)blockIdx.x * 2 + 0) * Co + c] = s;
+                stat_part[((size_t)blockIdx.x * 2 + 1) * Co + c] = s2;
             }
         }
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 2) tc::tmem_dealloc(tmem_base, tmem_cols);
+    if (threadIdx.x == 0) CTR(2);
+    if (warp == 2) tc::tmem_dealloc(tmem_base, P.tmem_cols);
 }
 
 static uint32_t tmem_cols_for(int n) {
@@ -256,38 +481,102 @@ static uint32_t tmem_cols_for(int n) {
     return c;
 }
 
+static int ecg_num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
+        else { (void)cudaGetLastError(); return 148; }
+    }
+    return n;
+}
+
+// Shape -> schedule.  Returns the grid size (number of persistent CTAs = number of stat partials).
+static int conv2_cfg(int B, int Ci, int Co, int L, Conv2Cfg* P, size_t* smem_out) {
+    const int nsm = ecg_num_sms();
+    P->Ci = Ci; P->Co = Co; P->L = L;
+    P->kch = Ci < 64 ? Ci : 64;
+    P->tiles_t = ecg_cdiv(L, TC_TILE_M);
+    P->total_tiles = B * P->tiles_t;
+    P->xbytes_al = ((uint32_t)Ci * TC_ROWS * 2 + 1023u) & ~1023u;
+    const size_t wbytes = (size_t)ECG_KS * Ci * Co * 2;
+    const size_t stage = (size_t)P->kch * Co * 2;
+    const bool resident = wbytes <= 64 * 1024;
+    const size_t budget = 225 * 1024 - TC_HDR - C2_STATB;
+    int bestR = 1, bestSpan = 1 << 30;
+    const int rmax = Co >= 256 ? 2 : (512 / (2 * Co) < 4 ? 512 / (2 * Co) : 4);
+    for (int R = rmax; R >= 1; R >>= 1) {
+        const int ng = ecg_cdiv(P->total_tiles, R);
+        const int grid = ng < nsm ? ng : nsm;
+        const int span = ecg_cdiv(ng, grid) * R;                     // tiles on the busiest CTA
+        const int nxb = ecg_cdiv(ng, grid) > 1 ? 2 : 1;
+        const size_t need = (size_t)nxb * R * P->xbytes_al + (resident ? wbytes : 3 * stage);
+        if (need > budget) continue;
+        // streamed weights: fewer, larger groups halve the L2->SM weight traffic, so prefer the larger R
+        if (span < bestSpan || (!resident && span == bestSpan && R > bestR)) { bestSpan = span; bestR = R; }
+        // largest R that fits; small-channel layers also need R * (kch/16) >= 4 MMAs per issue batch
+        if (!resident || R * (P->kch / 16) <= 4) break;
+    }
+    if (const char* e = getenv("ECGB200_CONV_R")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) bestR = v; }
+    if (bestR * Co > 512) bestR = 512 / Co;
+    P->R = bestR;
+    P->AS = 2 * bestR * Co <= 512 ? 2 : 1;
+    P->ngroups = ecg_cdiv(P->total_tiles, bestR);
+    const int grid = P->ngroups < nsm ? P->ngroups : nsm;
+    P->NXB = ecg_cdiv(P->ngroups, grid) > 1 ? 2 : 1;
+    const size_t xall = (size_t)P->NXB * bestR * P->xbytes_al;
+    if (resident) {
+        P->NST = 0;
+        *smem_out = TC_HDR + C2_STATB + xall + wbytes;
+    } else {
+        int nst = (int)((budget - xall) / stage);
+        if (nst > C2_MAXST) nst = C2_MAXST;
+        if (nst < 2) return -1;
+        P->NST = nst;
+        *smem_out = TC_HDR + C2_STATB + xall + (size_t)nst * stage;
+    }
+    P->tmem_cols = tmem_cols_for(P->AS * bestR * Co);
+    return grid;
+}
+
+extern "C" int ecgb200_conv1d_stat_parts_bf16(int B, int Ci, int Co, int L) {
+    Conv2Cfg P;
+    size_t smem;
+    if (B <= 0 || L <= 0 || Ci <= 0 || (Ci & 15) || Ci > 256 || Co <= 0 || (Co & 31) || Co > 256) return 0;
+    const int g = conv2_cfg(B, Ci, Co, L, &P, &smem);
+    return g > 0 ? g : 0;
+}
+
 // xb [B][Ci/8][L][8] bf16 (Ci % 16 == 0), wprep [15][Ci/8][Co][8] bf16, bias fp32 (Co) or NULL,
 // yb [B][Co/8][L][8] bf16.  Co % 32 == 0, Co <= 256, Ci <= 256.
-extern "C" int ecgb200_conv1d_fwd_bf16(const void* xb, const void* wprep, const float* bias, void* yb,
-                                       int B, int Ci, int Co, int L, void* stream) {
+// stat_part: NULL or float[parts][2][Co] (parts = ecgb200_conv1d_stat_parts_bf16) receiving per-CTA
+// {sum, sum of squares} of the bf16-rounded outputs.
+extern "C" int ecgb200_conv1d_fwd_stats_bf16(const void* xb, const void* wprep, const float* bias, void* yb,
+                                             float* stat_part, int B, int Ci, int Co, int L, void* stream) {
     if (!xb || !wprep || !yb || B <= 0 || L <= 0) return ECGB200_EINVAL;
-    if (Ci <= 0 || (Ci & 15) || Ci > 256 || Co <= 0 || (Co & 31) || Co > 256 || B > 65535) return ECGB200_EUNSUPPORTED;
+    if (Ci <= 0 || (Ci & 15) || Ci > 256 || Co <= 0 || (Co & 31) || Co > 256) return ECGB200_EUNSUPPORTED;
     CUtensorMap xmap;
     int rc = ecg_make_act_tmap(&xmap, xb, B, Ci, L, TC_ROWS, Ci / 8);
     if (rc) return rc;
-    const int kch = Ci < 64 ? Ci : 64;
-    const uint32_t xbytes_al = ((uint32_t)Ci * TC_ROWS * 2 + 1023u) & ~1023u;
-    const size_t wring = (size_t)TC_NST * kch * Co * 2;
-    const int tiles_t = ecg_cdiv(L, TC_TILE_M);
-    const int total = B * tiles_t;
-    // tiles per CTA: bounded by TMEM (512 fp32 columns), shared memory (~200 KB) and by keeping >= ~1 wave of CTAs
-    int R = 512 / Co;
-    if (R > 2) R = 2;
-    if (const char* e = getenv("ECGB200_CONV_R")) { const int v = atoi(e); if (v >= 1 && v <= 16) R = v; }   // tuning
-    if (R * Co > 512) R = 512 / Co;
-    while (R > 1 && TC_HDR + (size_t)R * xbytes_al + wring > 225 * 1024) --R;
-    while (R > 1 && ecg_cdiv(total, R) < 120) --R;
-    const size_t smem = TC_HDR + (size_t)R * xbytes_al + wring;
+    Conv2Cfg P;
+    size_t smem;
+    const int grid = conv2_cfg(B, Ci, Co, L, &P, &smem);
+    if (grid <= 0) return ECGB200_EUNSUPPORTED;
     static size_t smem_set = 0;
     if (smem > smem_set) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         smem_set = smem;
     }
-    conv_tc_kernel<<<ecg_cdiv(total, R), 192, smem, (cudaStream_t)stream>>>(
-        xmap, (const __nv_bfloat16*)wprep, bias, (__nv_bfloat16*)yb, Ci, Co, L, kch, tmem_cols_for(R * Co), R,
-        total, tiles_t);
+    conv_tc_kernel<<<grid, C2_THREADS, smem, (cudaStream_t)stream>>>(xmap, (const __nv_bfloat16*)wprep, bias,
+                                                              (__nv_bfloat16*)yb, stat_part, P);
     return ecg_launch_status();
+}
+
+extern "C" int ecgb200_conv1d_fwd_bf16(const void* xb, const void* wprep, const float* bias, void* yb,
+                                       int B, int Ci, int Co, int L, void* stream) {
+    return ecgb200_conv1d_fwd_stats_bf16(xb, wprep, bias, yb, nullptr, B, Ci, Co, L, stream);
 }
 
 // ---------------------------------------------------------------- wgrad implicit GEMM
@@ -341,39 +630,58 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant
 
     if (warp == 0) {
         if (lane == 0) {
+            int slot = 0;
+            uint32_t ephase = 1;                                 // fresh barriers: the first pass does not block
+            int b = z / tiles_t, tt = z - b * tiles_t;           // item -> (sample, time tile), advanced by S per step
+            const int db = S / tiles_t, dt = S - db * tiles_t;
             for (int n = 0; n < nloc; ++n) {
-                const int it = z + n * S;
-                const int b = it / tiles_t, t0 = (it - b * tiles_t) * TC_TILE_M;
-                const int slot = n % WT_NST;
-                if (n >= WT_NST) tc::mbar_wait(empty + slot, ((n / WT_NST) - 1) & 1);
+                tc::mbar_wait(empty + slot, ephase);
                 uint8_t* st = stages + (size_t)slot * WT_STAGE;
                 tc::mbar_arrive_expect_tx(full + slot, dybytes + xbytes);
-                tc::tma_load_4d(st, &dymap, full + slot, 0, t0, ob * 16, b);
-                tc::tma_load_4d(st + WT_DY_BYTES, &xmap, full + slot, 0, t0 - ECG_PAD, cb * ncc, b);
+                tc::tma_load_4d(st, &dymap, full + slot, 0, tt * TC_TILE_M, ob * 16, b);
+                tc::tma_load_4d(st + WT_DY_BYTES, &xmap, full + slot, 0, tt * TC_TILE_M - ECG_PAD, cb * ncc, b);
+                if (++slot == WT_NST) { slot = 0; ephase ^= 1; }
+                b += db; tt += dt;
+                if (tt >= tiles_t) { tt -= tiles_t; ++b; }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
+            // lean issue loop (see conv_tc_kernel): descriptors built once, only the address field advances
             const uint32_t idesc = tc::make_idesc_bf16(128, 128, 1, 1);
-            const uint32_t st_addr = tc::smem_u32(stages);
+            // A = dY^T: M (o) chunks 128*16 B apart, K (t) 8-row groups 128 B apart
+            const uint64_t adesc0 = tc::make_desc(0, 128, 128 * 16);
+            // B = X chunk: N chunk n = tap n = the chunk shifted by n rows (SBO = 16 B)
+            const uint64_t bdesc0 = tc::make_desc(0, 128, 16);
+            const uint32_t ahi = (uint32_t)(adesc0 >> 32), bhi = (uint32_t)(bdesc0 >> 32);
+            const uint32_t alo0 = (uint32_t)adesc0 + (tc::smem_u32(stages) >> 4);
+            const uint32_t blo0 = (uint32_t)bdesc0 + ((tc::smem_u32(stages) + WT_DY_BYTES) >> 4);
+            int slot = 0;
+            uint32_t fphase = 0, accum = 0;
             for (int n = 0; n < nloc; ++n) {
-                const int slot = n % WT_NST;
-                tc::mbar_wait(full + slot, (n / WT_NST) & 1);
+                tc::mbar_wait(full + slot, fphase);
                 tc::fence_after_sync();
-                const uint32_t dy_addr = st_addr + slot * WT_STAGE;
-                const uint32_t x_addr = dy_addr + WT_DY_BYTES;
+                const uint32_t alo = alo0 + (uint32_t)slot * (WT_STAGE >> 4);
+                uint32_t blo = blo0 + (uint32_t)slot * (WT_STAGE >> 4);
 #pragma unroll 1
-                for (int i = 0; i < ncc; ++i) {
+                for (int i = 0; i < ncc; ++i, blo += TC_ROWS) {
+                    const uint32_t d = tmem_base + (uint32_t)(i * 128);
 #pragma unroll
-                    for (int j = 0; j < TC_TILE_M / 16; ++j) {
-                        // A = dY^T: M (o) chunks 128*16 B apart, K (t) 8-row groups 128 B apart
-                        const uint64_t ad = tc::make_desc(dy_addr + (uint32_t)j * 256, 128, 128 * 16);
-                        // B = X chunk i: N chunk n = tap n = the chunk shifted by n rows (SBO = 16 B)
-                        const uint64_t bd = tc::make_desc(x_addr + (uint32_t)i * (TC_ROWS * 16) + (uint32_t)j * 256, 128, 16);
-                        tc::mma_bf16(tmem_base + (uint32_t)(i * 128), ad, bd, idesc, (n > 0 || j > 0) ? 1u : 0u);
+                    for (int jb = 0; jb < TC_TILE_M / 16; jb += 4) {
+                        uint32_t dd[4], al[4], bl[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            dd[e] = d;
+                            al[e] = alo + (uint32_t)(jb + e) * 16;
+                            bl[e] = blo + (uint32_t)(jb + e) * 16;
+                        }
+                        if (accum || jb > 0) tc::mma_bf16_x4<0xF>(dd, al, bl, ahi, bhi, idesc);
+                        else tc::mma_bf16_x4<0xE>(dd, al, bl, ahi, bhi, idesc);
                     }
                 }
+                accum = 1;
                 tc::mma_commit(empty + slot);
+                if (++slot == WT_NST) { slot = 0; fphase ^= 1; }
             }
             tc::mma_commit(accfull);
         }

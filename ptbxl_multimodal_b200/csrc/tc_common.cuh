@@ -27,7 +27,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Bounded wait: a protocol bug must abort the kernel (trap) instead of hanging the GPU.
+// Bounded wait: a protocol bug must abort the kernel (trap) instead of hanging the GPU.  If a diagnostic
+// buffer was registered (ecgb200_debug_set_diag: pinned host memory), the stuck barrier is recorded first.
+static __device__ unsigned long long* g_mbar_diag = nullptr;   // per translation unit
 __device__ __forceinline__ uint64_t globaltimer_ns() {
     uint64_t t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -40,16 +42,33 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     for (uint32_t it = 0;; ++it) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(addr), "r"(parity), "r"(10000u)
+            : "r"(addr), "r"(parity)
             : "memory");
         if (done) return;
         if ((it & 1023u) == 1023u) {
             const uint64_t now = globaltimer_ns();
             if (t0 == 0) t0 = now;
-            else if (now - t0 > 2000000000ull) __trap();          // 2 s: deadlock
+            else if (now - t0 > 2000000000ull) {                  // 2 s: deadlock
+                unsigned long long* d = g_mbar_diag;
+                if (d != nullptr) {
+                    d[1] = ((unsigned long long)blockIdx.x << 32) | threadIdx.x;
+                    d[2] = ((unsigned long long)addr << 32) | parity;
+                    d[0] = 0xDEADull;
+                    __threadfence_system();
+                }
+                __trap();
+            } else if (now - t0 > 1000000000ull) {                // 1 s: every stuck waiter leaves a note
+                unsigned long long* d = g_mbar_diag;
+                if (d != nullptr && (threadIdx.x & 31) == (threadIdx.x >> 5) % 32 * 0 + ((threadIdx.x & 31))) {
+                    const unsigned w = threadIdx.x >> 5;
+                    d[4 + 2 * w] = ((unsigned long long)blockIdx.x << 32) | threadIdx.x;
+                    d[5 + 2 * w] = ((unsigned long long)addr << 32) | parity;
+                    __threadfence_system();
+                }
+            }
         }
     }
 }
@@ -88,6 +107,15 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {    
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// One lane of a converged warp (elect.sync): the lane that issues TMA / tcgen05 instructions while the
+// whole warp executes the surrounding loop, so that every index / descriptor value stays WARP-UNIFORM and
+// lives in the uniform register file the tensor-core instructions read (no per-MMA R2UR transfers).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---------------------------------------------------------------- UMMA descriptors
 // Shared-memory matrix descriptor, SWIZZLE_NONE ("interleave") canonical layouts, 16-byte units:
 //   K-major : ((8,m),(T,2)) : ((1T,SBO),(1,LBO))   LBO = between the two 8-element K halves,
@@ -116,6 +144,60 @@ __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Four MMAs issued back to back from ONE asm statement.  Measured on B200: a tcgen05.mma whose descriptor
+// registers were written just before it stalls the issuing thread for ~100+ cycles (130-420 cycles per MMA
+// in a compute-descriptor / issue / compute / issue loop, against 47 (N<=64), 64 (N=128), 128 (N=256) cycles
+// when the descriptors are ready), so all operands of a batch are formed first and the tensor pipe keeps
+// draining the batch while the next one is being prepared.
+//   alo/blo: low descriptor words (address field already added), ahi/bhi: shared high words,
+//   d: TMEM accumulator addresses.  No per-slot enable predicate: a predicated tcgen05.mma makes ptxas
+//   re-materialise its uniform operands in front of every instruction.
+//   ACCMASK bit e = accumulate flag of slot e, a COMPILE-TIME constant: a run-time predicate (written by a
+//   uniform-datapath instruction just before the batch) is what made the issue ~100 cycles per MMA slower.
+template <int ACCMASK>
+__device__ __forceinline__ void mma_bf16_x4(const uint32_t* d, const uint32_t* alo, const uint32_t* blo,
+                                            uint32_t ahi, uint32_t bhi, uint32_t idesc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pa0, pa1, pa2, pa3;\n\t"
+        ".reg .b64 da0, da1, da2, da3, db0, db1, db2, db3;\n\t"
+        "mov.b64 da0, {%4, %16};\n\t"
+        "mov.b64 da1, {%5, %16};\n\t"
+        "mov.b64 da2, {%6, %16};\n\t"
+        "mov.b64 da3, {%7, %16};\n\t"
+        "mov.b64 db0, {%8, %17};\n\t"
+        "mov.b64 db1, {%9, %17};\n\t"
+        "mov.b64 db2, {%10, %17};\n\t"
+        "mov.b64 db3, {%11, %17};\n\t"
+        "setp.ne.b32 pa0, %12, 0;\n\t"
+        "setp.ne.b32 pa1, %13, 0;\n\t"
+        "setp.ne.b32 pa2, %14, 0;\n\t"
+        "setp.ne.b32 pa3, %15, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da0, db0, %18, pa0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], da1, db1, %18, pa1;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%2], da2, db2, %18, pa2;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%3], da3, db3, %18, pa3;\n\t"
+        "}"
+        ::"r"(d[0]), "r"(d[1]), "r"(d[2]), "r"(d[3]),
+          "r"(alo[0]), "r"(alo[1]), "r"(alo[2]), "r"(alo[3]),
+          "r"(blo[0]), "r"(blo[1]), "r"(blo[2]), "r"(blo[3]),
+          "n"(ACCMASK & 1), "n"((ACCMASK >> 1) & 1), "n"((ACCMASK >> 2) & 1), "n"((ACCMASK >> 3) & 1),
+          "r"(ahi), "r"(bhi), "r"(idesc)
+        : "memory");
+}
+// Single MMA with a compile-time accumulate flag (see mma_bf16_x4).
+template <int ACC>
+__device__ __forceinline__ void mma_bf16_c(uint32_t d, uint32_t alo, uint32_t blo, uint32_t ahi, uint32_t bhi,
+                                           uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(d), "r"(alo), "r"(blo), "r"(ahi), "r"(bhi), "r"(idesc), "n"(ACC)
         : "memory");
 }
 // mbarrier arrives when all previously issued MMAs of this thread have completed

@@ -159,6 +159,13 @@ class TrainStep:
             self.ndb = [lib.ecgb200_bn_nsplit(B, self.chan[l + 1]) for l in range(4)]
             self.dbpart = [e(self.chan[l + 1], self.ndb[l]) for l in range(4)]
             self.stat = [None] * 4
+            # per-CTA {sum, sumsq} partials written by the conv epilogue
+            self.nstat = [lib.ecgb200_conv1d_stat_parts_bf16(B, self.cip[l], self.chan[l + 1], self.L[l]) for l in range(4)]
+            if min(self.nstat) <= 0:
+                raise EcgB200Error("bf16 conv kernel does not support this shape")
+            self.statp = [e(self.nstat[l], 2, self.chan[l + 1]) for l in range(4)]
+            self.wpT = e(self.chan[4], self.bb.proj.out_features)
+            self.loss_part = e(lib.ecgb200_head_loss_parts(B))
         c4 = self.chan[4]
         self.gap = e(B, c4)
         self.dgap = e(B, c4)
@@ -177,6 +184,9 @@ class TrainStep:
         big = B * 32 * T                                          # every conv output has 32*T elems/sample
         act_dt = torch.bfloat16 if self.bf16 else F32
         self.dy = torch.empty(max(B * co * L for co, L in zip(self.chan[1:], self.L)), dtype=act_dt, device=dev)
+        # bf16 engine: wgrad of block l runs on the side stream while block l-1's BN backward writes its
+        # own dy, so dy ping-pongs between two buffers
+        self.dy2 = torch.empty_like(self.dy) if self.bf16 else None
         self.dp = torch.empty(max(B * self.chan[l] * self.L[l] for l in range(1, 4)), dtype=act_dt, device=dev)
         wsfn = lib.ecgb200_conv1d_wgrad_bf16_ws_bytes if self.bf16 else lib.ecgb200_conv1d_wgrad_ws_bytes
         ws = max(wsfn(B, self.chan[l], self.chan[l + 1], self.L[l]) for l in range(4))
@@ -186,7 +196,8 @@ class TrainStep:
         ws = max(ws, max(lib.ecgb200_bn_bwd_ws_bytes(B, c) for c in self.chan[1:]))
         self.ws = torch.empty(ws, dtype=torch.uint8, device=dev)
         del big
-        self.side = torch.cuda.Stream(device=dev) if self.world > 1 else None
+        self.side = torch.cuda.Stream(device=dev) if (self.world > 1 or self.bf16) else None
+        self.comm = torch.cuda.Stream(device=dev) if (self.world > 1 and self.bf16) else None
 
     # ------------------------------------------------------------------ the kernel sequence
     def _k(self, name, fn, *args):
@@ -226,28 +237,78 @@ class TrainStep:
         return n
 
     def _fwd_blocks_bf16(self, st, pre, Pp, blocks):
-        """tcgen05 path: pack the fp32 (B,12,T) input once, then per block
-        weight re-layout -> implicit-GEMM conv -> batch statistics -> BN+ReLU+pool, all on
-        blocked channels-last bf16 activations."""
+        """tcgen05 path: ONE prologue launch (input pack + the four weight re-layouts + proj transpose +
+        step counter), then per block the persistent implicit-GEMM conv with BatchNorm statistics in
+        its epilogue and one BN-finalise + ReLU + pool pass, on blocked channels-last bf16."""
         B = self.B
         n = 0
         self._prof_tag = ""
-        self._k("pack_input", lib.ecgb200_pack_input_bf16, _p(self.x), _p(self.acts[0]), B, self.chan[0], self.T, st)
+        PV, I4 = C.c_void_p * 4, C.c_int * 4
+        wkeys = [f"{pre}backbone.{l}.net.0.weight" for l in range(4)]
+        self._k("prep", lib.ecgb200_step_prep_bf16, _p(self.x), _p(self.acts[0]), B, self.chan[0], self.T, 4,
+                PV(*[Pp(k) for k in wkeys]), PV(*[_p(w) for w in self.wt]), PV(*[_p(w) for w in self.wd]),
+                I4(*self.chan[1:5]), I4(*self.chan[0:4]),
+                None if self.mm else Pp(pre + "proj.weight"), None if self.mm else _p(self.wpT),
+                self.feat, self.chan[4], self.step_dev.data_ptr(), st)
         n += 1
         for l in range(4):
-            ci, cip, co, L = self.chan[l], self.cip[l], self.chan[l + 1], self.L[l]
+            cip, co, L = self.cip[l], self.chan[l + 1], self.L[l]
             k = f"{pre}backbone.{l}.net."
             bn = blocks[l].net[1]
             self._prof_tag = f"_L{l + 1}"
-            self._k("prep", lib.ecgb200_conv1d_prep_weights_bf16, Pp(k + "0.weight"), _p(self.wt[l]), _p(self.wd[l]), co, ci, st)
-            self._k("conv_fwd", lib.ecgb200_conv1d_fwd_bf16, _p(self.acts[l]), _p(self.wt[l]), Pp(k + "0.bias"),
-                    _p(self.ybuf[l]), B, cip, co, L, st)
-            self._k("bn_stats", lib.ecgb200_bn_train_stats_bf16, _p(self.ybuf[l]), Pp(k + "1.weight"), Pp(k + "1.bias"),
-                    bn.running_mean.data_ptr(), bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(),
-                    _p(self.bnst[l]), _p(self.ws2), B, co, L, float(bn.momentum), float(bn.eps), st)
-            self._k("bn_relu_pool", lib.ecgb200_bn_relu_pool_fwd_bf16, _p(self.ybuf[l]), _p(self.bnst[l]),
-                    _p(self.acts[l + 1]) if l < 3 else None, _p(self.gap) if l == 3 else None, B, co, L, st)
-            n += 5
+            self._k("conv_fwd", lib.ecgb200_conv1d_fwd_stats_bf16, _p(self.acts[l]), _p(self.wt[l]), Pp(k + "0.bias"),
+                    _p(self.ybuf[l]), _p(self.statp[l]), B, cip, co, L, st)
+            self._k("bn_relu_pool", lib.ecgb200_bn_relu_pool_fwd_train_bf16, _p(self.ybuf[l]), _p(self.statp[l]),
+                    self.nstat[l], Pp(k + "1.weight"), Pp(k + "1.bias"), bn.running_mean.data_ptr(),
+                    bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(), _p(self.bnst[l]),
+                    _p(self.acts[l + 1]) if l < 3 else None, _p(self.gap) if l == 3 else None, B, co, L,
+                    float(bn.momentum), float(bn.eps), st)
+            n += 2
+        return n
+
+    def _fork_side(self, main):
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.side.wait_event(ev)
+
+    def _bwd_blocks_bf16(self, pre, Gp):
+        """Critical path on the main stream: BN/ReLU/pool backward -> dgrad, block 4 down to 1.  The weight
+        gradients (only AdamW needs them) run on the side stream beside it; dy ping-pongs so block l-1's
+        BN backward never overwrites what block l's wgrad still reads."""
+        B = self.B
+        n = 0
+        main = torch.cuda.current_stream(self.dev)
+        st = main.cuda_stream
+        dys = [self.dy, self.dy2]
+        wg_done = [None, None]
+        for l in (3, 2, 1, 0):
+            ci, co, L = self.chan[l], self.chan[l + 1], self.L[l]
+            k = f"{pre}backbone.{l}.net."
+            self._prof_tag = f"_L{l + 1}"
+            dy = dys[l & 1]
+            if wg_done[l & 1] is not None:
+                main.wait_event(wg_done[l & 1])                # wgrad of block l+2 has finished reading this dy
+            self._k("bn_bwd", lib.ecgb200_bn_relu_pool_bwd_bf16, _p(self.ybuf[l]), _p(self.bnst[l]),
+                    _p(self.dp) if l < 3 else None, _p(self.dgap) if l == 3 else None, _p(dy),
+                    Gp(k + "1.weight"), Gp(k + "1.bias"), _p(self.dbpart[l]), _p(self.ws2), B, co, L, 1, st)
+            n += 2
+            self._fork_side(main)
+            with torch.cuda.stream(self.side):
+                self._k("wgrad", lib.ecgb200_conv1d_wgrad_bf16, _p(dy), _p(self.acts[l]), Gp(k + "0.weight"),
+                        Gp(k + "0.bias"), _p(self.dbpart[l]), self.ndb[l], _p(self.ws), B, ci, co, L,
+                        self.side.cuda_stream)
+                wg_done[l & 1] = torch.cuda.Event()
+                wg_done[l & 1].record(self.side)
+                if l == 3 and self.world > 1:
+                    # bucket A (block 4, the tail of G) is final: all-reduce it while blocks 3..1 run
+                    self.comm.wait_event(wg_done[l & 1])
+                    with torch.cuda.stream(self.comm):
+                        torch.distributed.all_reduce(self.G[self.bucket_a_off:], group=self.pg)
+            n += 2
+            if l > 0:
+                self._k("dgrad", lib.ecgb200_conv1d_fwd_bf16, _p(dy), _p(self.wd[l]), None, _p(self.dp),
+                        B, co, ci, L, st)
+                n += 1
         return n
 
     def _bwd_blocks(self, st, pre, Pp, Gp):
@@ -289,7 +350,8 @@ class TrainStep:
         return n
 
     def _enqueue(self):
-        st = torch.cuda.current_stream(self.dev).cuda_stream
+        main = torch.cuda.current_stream(self.dev)
+        st = main.cuda_stream
         B = self.B
         n = 0
         pre = "ecg_backbone." if self.mm else ""
@@ -302,6 +364,62 @@ class TrainStep:
         else:
             n += self._fwd_blocks_fp32(st, pre, Pp, blocks)
         self._prof_tag = ""
+        c4, F_, NL = self.chan[4], self.feat, self.nl
+        if self.bf16 and not self.mm:
+            # fused head: forward + BCE + input gradients in one launch; weight gradients + loss on the side
+            self._k("head_fwd_bwd", lib.ecgb200_head_fwd_bwd_f32, _p(self.gap), _p(self.wpT), Pp("proj.weight"),
+                    Pp("proj.bias"), Pp("head.weight"), Pp("head.bias"), _p(self.y), _p(self.z), _p(self.logits),
+                    _p(self.dlogits), _p(self.dz), _p(self.dgap), _p(self.loss_part), B, c4, F_, NL, 1.0, st)
+            self._fork_side(main)
+            with torch.cuda.stream(self.side):
+                self._k("head_wgrad", lib.ecgb200_head_wgrad_f32, _p(self.gap), _p(self.z), _p(self.dz),
+                        _p(self.dlogits), _p(self.loss_part), Gp("proj.weight"), Gp("proj.bias"), Gp("head.weight"),
+                        Gp("head.bias"), _p(self.loss), B, c4, F_, NL, self.side.cuda_stream)
+            n += 2
+        else:
+            n += self._head_unfused(st, pre, Pp, Gp)
+        # ---- backward: conv blocks 4..1
+        if self.bf16:
+            n += self._bwd_blocks_bf16(pre, Gp)
+        else:
+            n += self._bwd_blocks(st, pre, Pp, Gp)
+        # ---- gradient exchange + optimizer
+        self._prof_tag = ""
+        if self.world > 1:
+            if self.bf16:
+                ev = torch.cuda.Event()
+                ev.record(self.side)
+                self.comm.wait_event(ev)                        # all weight gradients are final
+                with torch.cuda.stream(self.comm):
+                    torch.distributed.all_reduce(self.G[:self.bucket_a_off], group=self.pg)
+                ev2 = torch.cuda.Event()
+                ev2.record(self.comm)
+                main.wait_event(ev2)
+            else:
+                torch.distributed.all_reduce(self.G[:self.bucket_a_off], group=self.pg)
+                ev2 = torch.cuda.Event()
+                ev2.record(self.side)
+                main.wait_event(ev2)
+        if self.bf16:
+            ev3 = torch.cuda.Event()
+            ev3.record(self.side)
+            main.wait_event(ev3)                                # join the weight-gradient branch
+            self._k("adamw", lib.ecgb200_adamw_flat_f32, self.P.data_ptr(), self.G.data_ptr(), self.M.data_ptr(),
+                    self.V.data_ptr(), self.total, self.hyper.data_ptr(), self.step_dev.data_ptr(), st)
+            n += 1
+        else:
+            one = C.c_void_p * 1
+            num = (C.c_int64 * 1)(self.total)
+            self._k("adamw", lib.ecgb200_adamw_f32, 1, one(self.P.data_ptr()), one(self.G.data_ptr()), one(self.M.data_ptr()),
+                    one(self.V.data_ptr()), num, self.hyper.data_ptr(), self.step_dev.data_ptr(), st)
+            n += 2
+        self.launches_per_step = n
+
+    def _head_unfused(self, st, pre, Pp, Gp):
+        """proj / (demo encoder, FiLM) / head / BCE and their backward as separate launches (fp32 engine and
+        the multimodal model)."""
+        B = self.B
+        n = 0
         c4, F_, NL = self.chan[4], self.feat, self.nl
         self._k("proj", lib.ecgb200_linear_fwd_f32, _p(self.gap), Pp(pre + "proj.weight"), Pp(pre + "proj.bias"), _p(self.z),
                                          B, c4, F_, 0, st)
@@ -341,21 +459,7 @@ class TrainStep:
         self._k("proj_bwd", lib.ecgb200_linear_bwd_f32, _p(self.gap), Pp(pre + "proj.weight"), _p(self.dz), None, _p(self.dgap),
                                          Gp(pre + "proj.weight"), Gp(pre + "proj.bias"), B, c4, F_, st)
         n += 3
-        # ---- backward: conv blocks 4..1
-        n += self._bwd_blocks(st, pre, Pp, Gp)
-        # ---- gradient exchange + optimizer
-        self._prof_tag = ""
-        if self.world > 1:
-            torch.distributed.all_reduce(self.G[:self.bucket_a_off], group=self.pg)
-            ev2 = torch.cuda.Event()
-            ev2.record(self.side)
-            main.wait_event(ev2)
-        one = C.c_void_p * 1
-        num = (C.c_int64 * 1)(self.total)
-        self._k("adamw", lib.ecgb200_adamw_f32, 1, one(self.P.data_ptr()), one(self.G.data_ptr()), one(self.M.data_ptr()),
-                                    one(self.V.data_ptr()), num, self.hyper.data_ptr(), self.step_dev.data_ptr(), st)
-        n += 2
-        self.launches_per_step = n
+        return n
 
     # ------------------------------------------------------------------ public API
     def capture(self):

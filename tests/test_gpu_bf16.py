@@ -149,3 +149,140 @@ def test_bn_relu_pool_bf16(B, C, L, use_gap):
     dy = from_blocked(dyb.cpu(), C)
     assert rel_inf(dy, y.grad) < 6e-3
     assert float((dbp.sum(dim=1).cpu() - dy.sum(dim=(0, 2))).abs().max()) < 1e-2 * float(dy.abs().max()) * (B * L) ** 0.5
+
+
+# --------------------------------------------------------------------------- fused per-step kernels
+@pytest.mark.parametrize("B,Ci,Co,L", [(8, 16, 32, 1000), (5, 32, 64, 500), (300, 32, 64, 250), (7, 64, 128, 250),
+                                       (3, 128, 256, 125), (200, 128, 256, 125), (2, 64, 128, 129)])
+def test_conv_stats_and_fused_bn_forward(B, Ci, Co, L):
+    """conv epilogue statistics + one-pass BN-finalise/ReLU/pool against torch on the bf16-rounded conv
+    output; persistent multi-group schedule (B large) and partial groups / ragged tiles (B, L odd)."""
+    x = gen(B, Ci, L, seed=12)
+    w = gen(Co, Ci, 15, seed=13, scale=0.05)
+    bias = gen(Co, seed=14, scale=0.1)
+    gamma = 1 + 0.2 * gen(Co, seed=15)
+    beta = 0.1 * gen(Co, seed=16)
+    xr, wr = x.to(BF).float(), w.to(BF).float()
+    yref = F.conv1d(xr, wr, bias, padding=7).to(BF).float()            # what the kernels store
+    rm, rv = torch.zeros(Co), torch.ones(Co)
+    h = F.batch_norm(yref, rm, rv, gamma, beta, training=True, momentum=0.1, eps=1e-5)
+    pref = F.max_pool1d(F.relu(h), 2)
+    xb, wg, bg = to_blocked(x).to(DEV), w.to(DEV), bias.to(DEV)
+    wf = torch.empty(15, Ci // 8, Co, 8, dtype=BF, device=DEV)
+    check(lib.ecgb200_conv1d_prep_weights_bf16(ptr(wg), ptr(wf), None, Co, Ci, stream()), "prep")
+    nparts = lib.ecgb200_conv1d_stat_parts_bf16(B, Ci, Co, L)
+    assert 0 < nparts <= torch.cuda.get_device_properties(0).multi_processor_count
+    part = torch.full((nparts, 2, Co), float("nan"), device=DEV)
+    yb = torch.full((B, Co // 8, L, 8), float("nan"), dtype=BF, device=DEV)
+    check(lib.ecgb200_conv1d_fwd_stats_bf16(ptr(xb), ptr(wf), ptr(bg), ptr(yb), ptr(part), B, Ci, Co, L, stream()), "conv")
+    torch.cuda.synchronize()
+    y = from_blocked(yb.cpu(), Co)
+    assert torch.isfinite(y).all() and torch.isfinite(part).all()
+    assert rel_inf(y, yref) < 1e-2
+    s1, s2 = part[:, 0].double().sum(0).cpu(), part[:, 1].double().sum(0).cpu()
+    assert rel_inf(s1, y.double().sum(dim=(0, 2))) < 1e-4 * (B * L) ** 0.5      # stats of the stored values
+    assert rel_inf(s2, (y.double() ** 2).sum(dim=(0, 2))) < 1e-5
+    gg, btg = gamma.to(DEV), beta.to(DEV)
+    rmg, rvg = torch.zeros(Co, device=DEV), torch.ones(Co, device=DEV)
+    nbt = torch.zeros((), dtype=torch.int64, device=DEV)
+    st = torch.empty(4, Co, device=DEV)
+    for use_gap in (False, True):
+        pb = torch.full((B, Co // 8, L // 2, 8), float("nan"), dtype=BF, device=DEV)
+        gap = torch.empty(B, Co, device=DEV) if use_gap else None
+        check(lib.ecgb200_bn_relu_pool_fwd_train_bf16(ptr(yb), ptr(part), nparts, ptr(gg), ptr(btg), ptr(rmg), ptr(rvg),
+                                                      ptr(nbt), ptr(st), ptr(pb), ptr(gap), B, Co, L, 0.1, 1e-5,
+                                                      stream()), "bn_fwd_train")
+        torch.cuda.synchronize()
+        # reference statistics from the values the GPU actually stored (y differs from yref by bf16 ties)
+        rm2, rv2 = torch.zeros(Co), torch.ones(Co)
+        h2 = F.batch_norm(y, rm2, rv2, gamma, beta, training=True, momentum=0.1, eps=1e-5)
+        p2 = F.max_pool1d(F.relu(h2), 2)
+        assert rel_inf(from_blocked(pb.cpu(), Co), p2) < 6e-3
+        if use_gap:
+            assert rel_inf(gap, p2.mean(dim=2)) < 2e-5
+        else:
+            assert rel_inf(rmg, rm2) < 1e-5 and rel_inf(rvg, rv2) < 1e-4 and int(nbt) == 1
+            mean = y.mean(dim=(0, 2)); var = y.var(dim=(0, 2), unbiased=False)
+            assert rel_inf(st[0], mean) < 1e-5 and rel_inf(st[1], 1 / torch.sqrt(var + 1e-5)) < 1e-4
+    assert rel_inf(pref, p2) < 2e-2
+
+
+@pytest.mark.parametrize("B,NL", [(256, 5), (7, 1), (33, 5)])
+def test_fused_head(B, NL):
+    """head_fwd_bwd + head_wgrad == proj -> head -> BCE and its autograd (ecg_cnn.py:63-64, loop.py:32-33)."""
+    Cin = F_ = 256
+    g = torch.Generator().manual_seed(3)
+    gap = torch.rand(B, Cin, generator=g)
+    wp = (torch.rand(F_, Cin, generator=g) - 0.5) / 8
+    bp = (torch.rand(F_, generator=g) - 0.5) / 8
+    wh = (torch.rand(NL, F_, generator=g) - 0.5) / 8
+    bh = (torch.rand(NL, generator=g) - 0.5) / 8
+    y = (torch.rand(B, NL, generator=g) < 0.3).float()
+    leaves = [t.clone().requires_grad_(True) for t in (gap, wp, bp, wh, bh)]
+    z = F.linear(leaves[0], leaves[1], leaves[2])
+    z.retain_grad()
+    logits = F.linear(z, leaves[3], leaves[4])
+    loss = F.binary_cross_entropy_with_logits(logits, y)
+    loss.backward()
+    d = lambda t: t.to(DEV).contiguous()          # noqa: E731
+    gap_g, wp_g, bp_g, wh_g, bh_g, y_g = map(d, (gap, wp, bp, wh, bh, y))
+    wpT = wp_g.t().contiguous()
+    e = lambda *s: torch.full(s, float("nan"), device=DEV)       # noqa: E731
+    zz, lg, dl, dz, dgap = e(B, F_), e(B, NL), e(B, NL), e(B, F_), e(B, Cin)
+    lp = e(lib.ecgb200_head_loss_parts(B))
+    check(lib.ecgb200_head_fwd_bwd_f32(ptr(gap_g), ptr(wpT), ptr(wp_g), ptr(bp_g), ptr(wh_g), ptr(bh_g), ptr(y_g),
+                                       ptr(zz), ptr(lg), ptr(dl), ptr(dz), ptr(dgap), ptr(lp), B, Cin, F_, NL, 1.0,
+                                       stream()), "head_fwd_bwd")
+    dwp, dbp, dwh, dbh, ls = e(F_, Cin), e(F_), e(NL, F_), e(NL), e(1)
+    check(lib.ecgb200_head_wgrad_f32(ptr(gap_g), ptr(zz), ptr(dz), ptr(dl), ptr(lp), ptr(dwp), ptr(dbp), ptr(dwh),
+                                     ptr(dbh), ptr(ls), B, Cin, F_, NL, stream()), "head_wgrad")
+    torch.cuda.synchronize()
+    tol = 1e-5
+    assert rel_inf(lg, logits) < tol and rel_inf(zz, z) < tol
+    assert abs(float(ls) - float(loss)) < 1e-6 * max(1.0, abs(float(loss)))
+    assert rel_inf(dz, z.grad) < tol and rel_inf(dgap, leaves[0].grad) < tol
+    assert rel_inf(dwp, leaves[1].grad) < tol and rel_inf(dbp, leaves[2].grad) < tol
+    assert rel_inf(dwh, leaves[3].grad) < tol and rel_inf(dbh, leaves[4].grad) < tol
+
+
+def test_step_prep_and_flat_adamw():
+    import ctypes as C
+    B, T = 3, 250
+    chan = [12, 32, 64, 128, 256]
+    x = gen(B, 12, T, seed=21).to(DEV)
+    ws = [gen(chan[l + 1], chan[l], 15, seed=30 + l, scale=0.1).to(DEV) for l in range(4)]
+    cip = [16, 32, 64, 128]
+    wf = [torch.empty(15, cip[l] // 8, chan[l + 1], 8, dtype=BF, device=DEV) for l in range(4)]
+    wd = [None] + [torch.empty(15, chan[l + 1] // 8, cip[l], 8, dtype=BF, device=DEV) for l in range(1, 4)]
+    wp = gen(256, 256, seed=40).to(DEV)
+    wpT = torch.empty(256, 256, device=DEV)
+    ctr = torch.tensor([4], dtype=torch.int32, device=DEV)
+    xb = torch.empty(B, 2, T, 8, dtype=BF, device=DEV)
+    PV, I4 = C.c_void_p * 4, C.c_int * 4
+    check(lib.ecgb200_step_prep_bf16(ptr(x), ptr(xb), B, 12, T, 4, PV(*[ptr(w) for w in ws]), PV(*[ptr(w) for w in wf]),
+                                     PV(*[ptr(w) for w in wd]), I4(*chan[1:]), I4(*chan[:4]), ptr(wp), ptr(wpT), 256, 256,
+                                     ptr(ctr), stream()), "step_prep")
+    xb2 = torch.empty_like(xb)
+    check(lib.ecgb200_pack_input_bf16(ptr(x), ptr(xb2), B, 12, T, stream()), "pack")
+    assert torch.equal(xb, xb2) and int(ctr) == 5 and torch.equal(wpT, wp.t())
+    for l in range(4):
+        f2 = torch.empty_like(wf[l])
+        d2 = torch.empty_like(wd[l]) if wd[l] is not None else None
+        check(lib.ecgb200_conv1d_prep_weights_bf16(ptr(ws[l]), ptr(f2), ptr(d2), chan[l + 1], chan[l], stream()), "prep")
+        assert torch.equal(wf[l], f2) and (d2 is None or torch.equal(wd[l], d2))
+    # flat AdamW == multi-tensor AdamW at the same step index
+    n = 10007 * 4
+    p0, g0 = gen(n, seed=50).to(DEV), gen(n, seed=51).to(DEV)
+    hyper = torch.tensor([1.5e-3, 0.9, 0.999, 1e-8, 1e-4, 0.5], device=DEV)
+    pa, ma, va = p0.clone(), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    pb_, mb, vb = p0.clone(), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    ca = torch.tensor([0], dtype=torch.int32, device=DEV)
+    cb = torch.tensor([1], dtype=torch.int32, device=DEV)
+    one = C.c_void_p * 1
+    for it in range(3):
+        check(lib.ecgb200_adamw_f32(1, one(ptr(pa)), one(ptr(g0)), one(ptr(ma)), one(ptr(va)), (C.c_int64 * 1)(n),
+                                    ptr(hyper), ptr(ca), stream()), "adamw")
+        check(lib.ecgb200_adamw_flat_f32(ptr(pb_), ptr(g0), ptr(mb), ptr(vb), n, ptr(hyper), ptr(cb), stream()), "adamw_flat")
+        cb += 1
+    torch.cuda.synchronize()
+    assert torch.equal(pa, pb_) and torch.equal(ma, mb) and torch.equal(va, vb)
