@@ -161,54 +161,67 @@ struct Conv2Cfg {
 // "uniform base + constant multiple of a uniform stride" (stays in the uniform datapath), issued four per
 // asm statement with compile-time accumulate flags.  FIRST: this stage starts the accumulators (j == 0).
 template <int NJ, int RC, bool FIRST>
-__device__ __forceinline__ void conv_issue_stage(uint32_t acc0, uint32_t alo_k, uint32_t wlo, uint32_t co,
-                                                 uint32_t xal16, uint32_t bstep, uint32_t ahi, uint32_t bhi,
-                                                 uint32_t idesc, bool leader, uint64_t* commit_bar) {
+__device__ __forceinline__ void conv_issue_stage(uint32_t acc0, uint64_t ad_k, uint64_t bd_w, uint32_t co,
+                                                 uint32_t xal16, uint32_t bstep, uint32_t idesc, bool leader,
+                                                 uint64_t* commit_bar) {
     constexpr int CNT = NJ * RC;
-    uint32_t dd[CNT], al[CNT], bl[CNT];
+    uint32_t dd[CNT];
+    uint64_t ad[CNT], bd[CNT];
 #pragma unroll
     for (int r = 0; r < RC; ++r)
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
             dd[r * NJ + j] = acc0 + (uint32_t)r * co;
-            al[r * NJ + j] = alo_k + (uint32_t)r * xal16 + (uint32_t)(j * 2 * TC_ROWS);
-            bl[r * NJ + j] = wlo + (uint32_t)j * bstep;
+            ad[r * NJ + j] = ad_k + (uint64_t)((uint32_t)r * xal16 + (uint32_t)(j * 2 * TC_ROWS));
+            bd[r * NJ + j] = bd_w + (uint64_t)((uint32_t)j * bstep);
         }
-    if (!leader) return;
+    (void)leader;
     constexpr int MASK = FIRST ? (NJ == 4 ? 0xE : (NJ == 2 ? 0xA : 0x0)) : 0xF;
 #pragma unroll
-    for (int c = 0; c + 4 <= CNT; c += 4) tc::mma_bf16_x4<MASK>(dd + c, al + c, bl + c, ahi, bhi, idesc);
+    for (int c = 0; c + 4 <= CNT; c += 4) tc::mma_bf16_x4<MASK>(dd + c, ad + c, bd + c, idesc);
 #pragma unroll
     for (int c = CNT & ~3; c < CNT; ++c) {
-        if (!FIRST || (c % NJ) != 0) tc::mma_bf16_c<1>(dd[c], al[c], bl[c], ahi, bhi, idesc);
-        else tc::mma_bf16_c<0>(dd[c], al[c], bl[c], ahi, bhi, idesc);
+        if (!FIRST || (c % NJ) != 0) tc::mma_bf16_c<1>(dd[c], ad[c], bd[c], idesc);
+        else tc::mma_bf16_c<0>(dd[c], ad[c], bd[c], idesc);
     }
-    // The commit MUST stay inside this one-lane region: when it sat in its own `if (leader)` after the
-    // warp had reconverged, ptxas turned it into an UNGUARDED warp-level UTCBAR (operand broadcast from the
-    // leader) and the barrier over-arrived -> sporadic producer/consumer deadlock on the weight ring.
     if (commit_bar != nullptr) tc::mma_commit(commit_bar);
 }
 
-template <int NJ, bool FIRST>
-__device__ __forceinline__ void conv_issue_stage_rc(int rcount, uint32_t acc0, uint32_t alo_k, uint32_t wlo,
-                                                    uint32_t co, uint32_t xal16, uint32_t bstep, uint32_t ahi,
-                                                    uint32_t bhi, uint32_t idesc, bool leader, uint64_t* cb) {
-    switch (rcount) {
-        case 4: conv_issue_stage<NJ, 4, FIRST>(acc0, alo_k, wlo, co, xal16, bstep, ahi, bhi, idesc, leader, cb); break;
-        case 3: conv_issue_stage<NJ, 3, FIRST>(acc0, alo_k, wlo, co, xal16, bstep, ahi, bhi, idesc, leader, cb); break;
-        case 2: conv_issue_stage<NJ, 2, FIRST>(acc0, alo_k, wlo, co, xal16, bstep, ahi, bhi, idesc, leader, cb); break;
-        default: conv_issue_stage<NJ, 1, FIRST>(acc0, alo_k, wlo, co, xal16, bstep, ahi, bhi, idesc, leader, cb); break;
-    }
+// One whole group with the weight tensor resident in shared memory (small-channel layers: one channel
+// group, no barrier inside): 15 taps fully unrolled, every descriptor = group base + compile-time multiple
+// of a uniform stride.  The (NJ, RC) dispatch happens once per group, not per stage.
+template <int NJ, int RC>
+__device__ __forceinline__ void conv_issue_group_resident(uint32_t acc0, uint64_t ad_g, uint64_t bd_w, uint32_t co,
+                                                          uint32_t xal16, uint32_t bstep, uint32_t stage16,
+                                                          uint32_t idesc, bool leader) {
+    conv_issue_stage<NJ, RC, true>(acc0, ad_g, bd_w, co, xal16, bstep, idesc, leader, nullptr);
+#pragma unroll
+    for (int k = 1; k < ECG_KS; ++k)
+        conv_issue_stage<NJ, RC, false>(acc0, ad_g + (uint64_t)k, bd_w + (uint64_t)((uint32_t)k * stage16), co, xal16,
+                                        bstep, idesc, leader, nullptr);
 }
 
-template <bool FIRST>
-__device__ __forceinline__ void conv_issue_stage_any(int nj, int rcount, uint32_t acc0, uint32_t alo_k,
-                                                     uint32_t wlo, uint32_t co, uint32_t xal16, uint32_t bstep,
-                                                     uint32_t ahi, uint32_t bhi, uint32_t idesc, bool leader,
-                                                     uint64_t* cb) {
-    if (nj == 4) conv_issue_stage_rc<4, FIRST>(rcount, acc0, alo_k, wlo, co, xal16, bstep, ahi, bhi, idesc, leader, cb);
-    else if (nj == 2) conv_issue_stage_rc<2, FIRST>(rcount, acc0, alo_k, wlo, co, xal16, bstep, ahi, bhi, idesc, leader, cb);
-    else conv_issue_stage_rc<1, FIRST>(rcount, acc0, alo_k, wlo, co, xal16, bstep, ahi, bhi, idesc, leader, cb);
+// One whole group with streamed weights: per stage, wait for the slab, issue RC x NJ MMAs, commit the slot.
+// slot / phase are carried across groups.
+template <int NJ, int RC>
+__device__ __forceinline__ void conv_issue_group_stream(uint32_t acc0, uint64_t ad_g, uint64_t bd0, uint32_t co,
+                                                        uint32_t xal16, uint32_t bstep, uint32_t stage16,
+                                                        uint32_t gstep, int groups, uint32_t idesc, bool leader,
+                                                        uint64_t* wfull, uint64_t* wempty, int nst, int& slot,
+                                                        uint32_t& wphase) {
+    bool first = true;
+    for (int k = 0; k < ECG_KS; ++k) {
+        uint64_t ad_k = ad_g + (uint64_t)k;                    // tap k = the same tile, k rows (16 B each) further
+        for (int g = 0; g < groups; ++g, ad_k += gstep) {
+            tc::mbar_wait(wfull + slot, wphase);
+            tc::fence_after_sync();
+            const uint64_t bd_w = bd0 + (uint64_t)((uint32_t)slot * stage16);
+            if (first) conv_issue_stage<NJ, RC, true>(acc0, ad_k, bd_w, co, xal16, bstep, idesc, leader, wempty + slot);
+            else conv_issue_stage<NJ, RC, false>(acc0, ad_k, bd_w, co, xal16, bstep, idesc, leader, wempty + slot);
+            first = false;
+            if (++slot == nst) { slot = 0; wphase ^= 1; }
+        }
+    }
 }
 
 // Persistent CTA (one per SM): loops over groups of R consecutive 128-step output tiles.
@@ -308,74 +321,64 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __nv_bfloat16* __
             }
         }
     } else if (warp == 1) {
-        // MMA issuer.  The WHOLE warp runs this loop with warp-uniform values and one elected lane issues:
-        // measured on B200, descriptors that reach tcgen05.mma through per-thread registers (R2UR transfers,
-        // run-time accumulate predicates) cost 130-420 cycles of issue per MMA against 47 (N<=64) / 64
-        // (N=128) / 128 (N=256) cycles of tensor time; descriptors are therefore built once, only their
-        // 14-bit address field (low word, 16-byte units) advances, and MMAs go out four per asm statement.
+        // MMA issuer: ONE elected thread runs everything (waits, tcgen05.mma, tcgen05.commit) inside a single
+        // divergent region.  Two measured facts shape this code:
+        //  * the issue loop is bound by the issuing thread's own instruction latency, not by the tensor pipe:
+        //    130-420 cycles per MMA when descriptors / accumulate predicates are recomputed per instruction,
+        //    against 47 (N<=64) / 64 (N=128) / 128 (N=256) cycles of tensor time.  So the (NJ, RC) structure
+        //    is dispatched once per group into fully unrolled code whose descriptors are "base + constant",
+        //    accumulate flags are compile-time, and MMAs leave four per asm statement;
+        //  * tcgen05.commit must NOT sit in a small `if (leader)` of warp-converged code: ptxas 12.9 turns it
+        //    into an unguarded warp-level UTCBAR fed by R2UR.BROADCAST, and the ring then deadlocked
+        //    sporadically.  Hence no warp-uniform tricks here: everything below is single-thread code.
         const bool leader = tc::elect_one();
+        if (leader) {
         const uint32_t idesc = tc::make_idesc_bf16(TC_TILE_M, Co, 0, 0);
         const uint64_t adesc0 = tc::make_desc(0, TC_ROWS * 16, 128);
         const uint64_t bdesc0 = tc::make_desc(0, (uint32_t)Co * 16, 128);
-        const uint32_t ahi = (uint32_t)(adesc0 >> 32), bhi = (uint32_t)(bdesc0 >> 32);
-        const uint32_t alo0 = (uint32_t)adesc0 + (tc::smem_u32(xs) >> 4);
-        const uint32_t blo0 = (uint32_t)bdesc0 + (tc::smem_u32(wsm) >> 4);
+        const uint64_t alo0 = adesc0 + (uint64_t)(tc::smem_u32(xs) >> 4);        // address field: low 14 bits
+        const uint64_t blo0 = bdesc0 + (uint64_t)(tc::smem_u32(wsm) >> 4);
         const uint32_t xal16 = P.xbytes_al >> 4, stage16 = stage_bytes >> 4;
         const uint32_t bstep = (uint32_t)(2 * Co);             // two 8-channel chunks of the weight slab
         const uint32_t gstep = (uint32_t)(kch / 8) * TC_ROWS;  // one channel group of the input tile
         const int nj = kch / 16;                               // 1, 2 or 4 K-steps per weight stage
         if (resident && ngl > 0) {
-            if (leader) tc::mbar_wait(wfull, 0);
-            __syncwarp();
+            tc::mbar_wait(wfull, 0);
             tc::fence_after_sync();
         }
-        if (lane == 0) CTR(3);                                 // resident weights landed
+        CTR(3);                                                // resident weights landed
         int slot = 0;
         uint32_t wphase = 0;
         for (int gi = 0; gi < ngl; ++gi) {
             const int xb = gi % P.NXB, as = gi % P.AS;
             const int tile0 = ((int)blockIdx.x + gi * (int)gridDim.x) * R;
             const int rcount = min(R, P.total_tiles - tile0);
-            if (leader) {
-                tc::mbar_wait(xfull + xb, (gi / P.NXB) & 1);
-                if (gi < 4) CTR(16 + gi);                      // x tiles of group gi landed
-                if (gi >= P.AS) tc::mbar_wait(accempty + as, ((gi / P.AS) - 1) & 1);
-                if (gi < 4) CTR(24 + gi);                      // accumulator stage free
-            }
-            __syncwarp();
+            tc::mbar_wait(xfull + xb, (gi / P.NXB) & 1);
+            if (gi < 4) CTR(16 + gi);                          // x tiles of group gi landed
+            if (gi >= P.AS) tc::mbar_wait(accempty + as, ((gi / P.AS) - 1) & 1);
+            if (gi < 4) CTR(24 + gi);                          // accumulator stage free
             tc::fence_after_sync();
             const uint32_t acc0 = tmem_base + (uint32_t)(as * R * Co);
-            const uint32_t alo_g = alo0 + (uint32_t)(xb * R) * xal16;
-            uint32_t wlo = blo0;                               // resident: walks the whole weight tensor
-            bool first = true;
-            for (int k = 0; k < ECG_KS; ++k) {
-                uint32_t alo_k = alo_g + (uint32_t)k;          // tap k = the same tile, k rows (16 B each) further
-                for (int g = 0; g < groups; ++g, alo_k += gstep) {
-                    if (!resident) {
-                        if (leader) tc::mbar_wait(wfull + slot, wphase);
-                        __syncwarp();
-                        tc::fence_after_sync();
-                        wlo = blo0 + (uint32_t)slot * stage16;
-                    }
-                    // the (tile r, K-step j) MMAs of this stage
-                    uint64_t* cb = resident ? nullptr : wempty + slot;   // frees the weight slot when these MMAs finish
-                    if (first) conv_issue_stage_any<true>(nj, rcount, acc0, alo_k, wlo, (uint32_t)Co, xal16, bstep, ahi, bhi, idesc, leader, cb);
-                    else conv_issue_stage_any<false>(nj, rcount, acc0, alo_k, wlo, (uint32_t)Co, xal16, bstep, ahi, bhi, idesc, leader, cb);
-                    first = false;
-                    if (!resident) {
-                        if (++slot == P.NST) { slot = 0; wphase ^= 1; }
-                    } else {
-                        wlo += stage16;
-                    }
-                }
+            const uint64_t alo_g = alo0 + (uint64_t)((uint32_t)(xb * R) * xal16);
+            if (resident) {
+#define ECG_RES(NJ_, RC_) conv_issue_group_resident<NJ_, RC_>(acc0, alo_g, blo0, (uint32_t)Co, xal16, bstep, stage16, idesc, leader)
+                if (nj == 1) { if (rcount == 4) ECG_RES(1, 4); else if (rcount == 3) ECG_RES(1, 3); else if (rcount == 2) ECG_RES(1, 2); else ECG_RES(1, 1); }
+                else if (nj == 2) { if (rcount == 4) ECG_RES(2, 4); else if (rcount == 3) ECG_RES(2, 3); else if (rcount == 2) ECG_RES(2, 2); else ECG_RES(2, 1); }
+                else { if (rcount == 4) ECG_RES(4, 4); else if (rcount == 3) ECG_RES(4, 3); else if (rcount == 2) ECG_RES(4, 2); else ECG_RES(4, 1); }
+#undef ECG_RES
+            } else {
+#define ECG_STR(NJ_, RC_) conv_issue_group_stream<NJ_, RC_>(acc0, alo_g, blo0, (uint32_t)Co, xal16, bstep, stage16, gstep, groups, idesc, leader, wfull, wempty, P.NST, slot, wphase)
+                if (nj == 4) { if (rcount == 4) ECG_STR(4, 4); else if (rcount == 3) ECG_STR(4, 3); else if (rcount == 2) ECG_STR(4, 2); else ECG_STR(4, 1); }
+                else if (nj == 2) { if (rcount == 2) ECG_STR(2, 2); else ECG_STR(2, 1); }
+                else { if (rcount == 2) ECG_STR(1, 2); else ECG_STR(1, 1); }
+#undef ECG_STR
             }
-            if (leader) {
-                tc::mma_commit(xempty + xb);           // input tiles of this group are free again
-                tc::mma_commit(accfull + as);          // accumulators of this group are complete
-                if (gi < 4) CTR(32 + gi);              // all MMAs of group gi issued
-            }
-            __syncwarp();
+            tc::mma_commit(xempty + xb);               // input tiles of this group are free again
+            tc::mma_commit(accfull + as);              // accumulators of this group are complete
+            if (gi < 4) CTR(32 + gi);                  // all MMAs of group gi issued
         }
+        }
+        __syncwarp();
     } else {
         const int q = warp & 3;                        // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;              // which of the two warps of this quarter
@@ -653,30 +656,30 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant
             const uint64_t adesc0 = tc::make_desc(0, 128, 128 * 16);
             // B = X chunk: N chunk n = tap n = the chunk shifted by n rows (SBO = 16 B)
             const uint64_t bdesc0 = tc::make_desc(0, 128, 16);
-            const uint32_t ahi = (uint32_t)(adesc0 >> 32), bhi = (uint32_t)(bdesc0 >> 32);
-            const uint32_t alo0 = (uint32_t)adesc0 + (tc::smem_u32(stages) >> 4);
-            const uint32_t blo0 = (uint32_t)bdesc0 + ((tc::smem_u32(stages) + WT_DY_BYTES) >> 4);
+            const uint64_t alo0 = adesc0 + (uint64_t)(tc::smem_u32(stages) >> 4);
+            const uint64_t blo0 = bdesc0 + (uint64_t)((tc::smem_u32(stages) + WT_DY_BYTES) >> 4);
             int slot = 0;
             uint32_t fphase = 0, accum = 0;
             for (int n = 0; n < nloc; ++n) {
                 tc::mbar_wait(full + slot, fphase);
                 tc::fence_after_sync();
-                const uint32_t alo = alo0 + (uint32_t)slot * (WT_STAGE >> 4);
-                uint32_t blo = blo0 + (uint32_t)slot * (WT_STAGE >> 4);
+                const uint64_t alo = alo0 + (uint64_t)((uint32_t)slot * (WT_STAGE >> 4));
+                uint64_t blo = blo0 + (uint64_t)((uint32_t)slot * (WT_STAGE >> 4));
 #pragma unroll 1
                 for (int i = 0; i < ncc; ++i, blo += TC_ROWS) {
                     const uint32_t d = tmem_base + (uint32_t)(i * 128);
 #pragma unroll
                     for (int jb = 0; jb < TC_TILE_M / 16; jb += 4) {
-                        uint32_t dd[4], al[4], bl[4];
+                        uint32_t dd[4];
+                        uint64_t al[4], bl[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             dd[e] = d;
-                            al[e] = alo + (uint32_t)(jb + e) * 16;
-                            bl[e] = blo + (uint32_t)(jb + e) * 16;
+                            al[e] = alo + (uint64_t)((jb + e) * 16);
+                            bl[e] = blo + (uint64_t)((jb + e) * 16);
                         }
-                        if (accum || jb > 0) tc::mma_bf16_x4<0xF>(dd, al, bl, ahi, bhi, idesc);
-                        else tc::mma_bf16_x4<0xE>(dd, al, bl, ahi, bhi, idesc);
+                        if (accum || jb > 0) tc::mma_bf16_x4<0xF>(dd, al, bl, idesc);
+                        else tc::mma_bf16_x4<0xE>(dd, al, bl, idesc);
                     }
                 }
                 accum = 1;

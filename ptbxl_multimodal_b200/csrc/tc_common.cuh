@@ -157,50 +157,49 @@ __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64
 //   ACCMASK bit e = accumulate flag of slot e, a COMPILE-TIME constant: a run-time predicate (written by a
 //   uniform-datapath instruction just before the batch) is what made the issue ~100 cycles per MMA slower.
 template <int ACCMASK>
-__device__ __forceinline__ void mma_bf16_x4(const uint32_t* d, const uint32_t* alo, const uint32_t* blo,
-                                            uint32_t ahi, uint32_t bhi, uint32_t idesc) {
+__device__ __forceinline__ void mma_bf16_x4(const uint32_t* d, const uint64_t* ad, const uint64_t* bd, uint32_t idesc) {
+    // 64-bit descriptor operands formed in C++ (not packed inside the asm): ptxas then keeps the whole
+    // descriptor arithmetic in the uniform datapath (UIADD3.64) instead of per-thread registers + R2UR.
     asm volatile(
         "{\n\t"
         ".reg .pred pa0, pa1, pa2, pa3;\n\t"
-        ".reg .b64 da0, da1, da2, da3, db0, db1, db2, db3;\n\t"
-        "mov.b64 da0, {%4, %16};\n\t"
-        "mov.b64 da1, {%5, %16};\n\t"
-        "mov.b64 da2, {%6, %16};\n\t"
-        "mov.b64 da3, {%7, %16};\n\t"
-        "mov.b64 db0, {%8, %17};\n\t"
-        "mov.b64 db1, {%9, %17};\n\t"
-        "mov.b64 db2, {%10, %17};\n\t"
-        "mov.b64 db3, {%11, %17};\n\t"
-        "setp.ne.b32 pa0, %12, 0;\n\t"
-        "setp.ne.b32 pa1, %13, 0;\n\t"
-        "setp.ne.b32 pa2, %14, 0;\n\t"
-        "setp.ne.b32 pa3, %15, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da0, db0, %18, pa0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%1], da1, db1, %18, pa1;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%2], da2, db2, %18, pa2;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%3], da3, db3, %18, pa3;\n\t"
+        "setp.ne.b32 pa0, %13, 0;\n\t"
+        "setp.ne.b32 pa1, %14, 0;\n\t"
+        "setp.ne.b32 pa2, %15, 0;\n\t"
+        "setp.ne.b32 pa3, %16, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %4, %8, %12, pa0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], %5, %9, %12, pa1;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%2], %6, %10, %12, pa2;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%3], %7, %11, %12, pa3;\n\t"
         "}"
         ::"r"(d[0]), "r"(d[1]), "r"(d[2]), "r"(d[3]),
-          "r"(alo[0]), "r"(alo[1]), "r"(alo[2]), "r"(alo[3]),
-          "r"(blo[0]), "r"(blo[1]), "r"(blo[2]), "r"(blo[3]),
-          "n"(ACCMASK & 1), "n"((ACCMASK >> 1) & 1), "n"((ACCMASK >> 2) & 1), "n"((ACCMASK >> 3) & 1),
-          "r"(ahi), "r"(bhi), "r"(idesc)
+          "l"(ad[0]), "l"(ad[1]), "l"(ad[2]), "l"(ad[3]),
+          "l"(bd[0]), "l"(bd[1]), "l"(bd[2]), "l"(bd[3]),
+          "r"(idesc),
+          "n"(ACCMASK & 1), "n"((ACCMASK >> 1) & 1), "n"((ACCMASK >> 2) & 1), "n"((ACCMASK >> 3) & 1)
         : "memory");
 }
 // Single MMA with a compile-time accumulate flag (see mma_bf16_x4).
 template <int ACC>
-__device__ __forceinline__ void mma_bf16_c(uint32_t d, uint32_t alo, uint32_t blo, uint32_t ahi, uint32_t bhi,
-                                           uint32_t idesc) {
+__device__ __forceinline__ void mma_bf16_c(uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-        "mov.b64 da, {%1, %3};\n\t"
-        "mov.b64 db, {%2, %4};\n\t"
-        "setp.ne.b32 p, %6, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
-        ::"r"(d), "r"(alo), "r"(blo), "r"(ahi), "r"(bhi), "r"(idesc), "n"(ACC)
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), "n"(ACC)
         : "memory");
 }
 // mbarrier arrives when all previously issued MMAs of this thread have completed
+// Same, predicated INSIDE the asm on a per-thread flag.  Use this in warp-uniform code: a bare
+// `if (leader) mma_commit(bar)` after the warp has reconverged was compiled by ptxas 12.9 into an unguarded
+// warp-level UTCBAR with the operand broadcast from the leader, and the barrier over-arrived (sporadic
+// deadlock); with the predicate as an asm operand the instruction stays per-thread.
+__device__ __forceinline__ void mma_commit_if(uint64_t* bar, bool pred) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %1, 0;\n\t"
+        "@p tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(smem_u32(bar)), "r"((uint32_t)pred) : "memory");
+}
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                  ::"r"(smem_u32(bar)) : "memory");
