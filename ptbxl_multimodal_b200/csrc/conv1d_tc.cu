@@ -389,6 +389,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __nv_bfloat16* __
         float ssum[8], ssq[8];                         // lane j: channel 32*cb + j, over this warp's rows
 #pragma unroll
         for (int i = 0; i < 8; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
+        // Column sums are first accumulated per thread (same row index of the R tiles of a group, 32 channels),
+        // and only then reduced across the 32 rows by a transposing butterfly (31 shuffles leave lane j with
+        // column j): one butterfly pair per (group, channel block) instead of per tile -- and for layers with
+        // <= 64 channels, where a warp always owns the same block, ONE pair for the whole kernel.
+        const bool small = nblk <= 2;
+        float vs[32], qs[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { vs[i] = 0.f; qs[i] = 0.f; }
+        auto butterfly = [&](int cb) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const bool up = (lane & o) != 0;
+#pragma unroll
+                for (int i = 0; i < o; ++i) {
+                    const float send = up ? vs[i] : vs[i + o], keep = up ? vs[i + o] : vs[i];
+                    vs[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                    const float send2 = up ? qs[i] : qs[i + o], keep2 = up ? qs[i + o] : qs[i];
+                    qs[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, o);
+                }
+            }
+            ssum[cb] += vs[0];
+            ssq[cb] += qs[0];
+        };
         for (int gi = 0; gi < ngl; ++gi) {
             const int as = gi % P.AS;
             const int tile0 = ((int)blockIdx.x + gi * (int)gridDim.x) * R;
@@ -396,18 +419,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __nv_bfloat16* __
             tc::mbar_wait(accfull + as, (gi / P.AS) & 1);
             if (gi < 4 && threadIdx.x == 64) CTR(40 + gi);       // accumulators of group gi complete
             tc::fence_after_sync();
-            for (int r = 0; r < rcount; ++r) {
-                const int tile = tile0 + r;
-                const int b = tile / P.tiles_t, t = (tile - b * P.tiles_t) * TC_TILE_M + row;
-                const bool live = t < L;
-                const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)((as * R + r) * Co);
-                __nv_bfloat16* yrow = y + ((size_t)b * (Co / 8) * L + t) * 8;
 #pragma unroll
-                for (int cb = 0; cb < 8; ++cb) {
-                    if (cb < nblk && ((r * nblk + cb) & 1) == half) {
-                        const int c0 = cb * 32;
+            for (int cb = 0; cb < 8; ++cb) {
+                // work split between the two warps of a lane quarter: by channel block, or by tile when there is one block
+                if (cb < nblk && (nblk == 1 || (cb & 1) == half)) {
+                    const int c0 = cb * 32;
+                    if (!small) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) { vs[i] = 0.f; qs[i] = 0.f; }
+                    }
+                    float bv[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) bv[i] = bias != nullptr ? __ldg(bias + c0 + i) : 0.f;
+                    for (int r = 0; r < rcount; ++r) {
+                        if (nblk == 1 && (r & 1) != half) continue;
+                        const int tile = tile0 + r;
+                        const int b = tile / P.tiles_t, t = (tile - b * P.tiles_t) * TC_TILE_M + row;
+                        const bool live = t < L;
+                        const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)((as * R + r) * Co + c0);
+                        __nv_bfloat16* yrow = y + ((size_t)b * (Co / 8) * L + t) * 8;
                         float v[32];
-                        tc::tmem_ld32(taddr + (uint32_t)c0, v);
+                        tc::tmem_ld32(taddr, v);
                         tc::tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
@@ -415,43 +447,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __nv_bfloat16* __
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const int c = 8 * i + 2 * j;
-                                const float o0 = v[c] + (bias != nullptr ? __ldg(bias + c0 + c) : 0.f);
-                                const float o1 = v[c + 1] + (bias != nullptr ? __ldg(bias + c0 + c + 1) : 0.f);
-                                pk[j] = tc::pack_bf16(o0, o1);
+                                pk[j] = tc::pack_bf16(v[c] + bv[c], v[c + 1] + bv[c + 1]);
                                 const float2 rr = tc::unpack_bf16(pk[j]);      // the value the next kernels will read
-                                v[c] = live ? rr.x : 0.f;
-                                v[c + 1] = live ? rr.y : 0.f;
+                                if (live) {
+                                    vs[c] += rr.x; qs[c] = fmaf(rr.x, rr.x, qs[c]);
+                                    vs[c + 1] += rr.y; qs[c + 1] = fmaf(rr.y, rr.y, qs[c + 1]);
+                                }
                             }
                             if (live)
                                 *reinterpret_cast<uint4*>(yrow + (size_t)(c0 / 8 + i) * chunk_stride) =
                                     make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         }
-                        if (want_stats) {
-                            // transposing butterfly: 31 shuffles leave lane j with the sum of column j over 32 rows
-                            float sq[32];
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) sq[i] = v[i] * v[i];
-#pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) {
-                                const bool up = (lane & o) != 0;
-#pragma unroll
-                                for (int i = 0; i < o; ++i) {
-                                    const float send = up ? v[i] : v[i + o], keep = up ? v[i + o] : v[i];
-                                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-                                    const float send2 = up ? sq[i] : sq[i + o], keep2 = up ? sq[i + o] : sq[i];
-                                    sq[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, o);
-                                }
-                            }
-                            ssum[cb] += v[0];
-                            ssq[cb] += sq[0];
-                        }
                     }
+                    if (want_stats && !small) butterfly(cb);
                 }
             }
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(accempty + as);
             if (gi < 4 && threadIdx.x == 64) CTR(48 + gi);       // epilogue of group gi done
+        }
+        if (want_stats && small) {
+            // this warp's only channel block: `half` when there are two blocks, block 0 otherwise
+            if (nblk == 2 && half == 1) butterfly(1); else butterfly(0);
         }
         if (want_stats) {
             float* mine = statsh + (size_t)(half * 4 + q) * 2 * 256;
@@ -599,6 +617,29 @@ constexpr int WT_DY_BYTES = 16 * 128 * 16;       // [<=16 chunks][128 rows][8] b
 constexpr int WT_X_BYTES = 4 * TC_ROWS * 16;     // [<=4 chunks][144 rows][8] bf16
 constexpr int WT_STAGE = WT_DY_BYTES + WT_X_BYTES;
 
+// All MMAs of one (sample, 128-step tile) work item: NCC channel chunks x 8 K-steps, fully unrolled so every
+// descriptor is "item base + compile-time constant" (see conv_issue_stage for why).
+template <int NCC>
+__device__ __forceinline__ void wgrad_issue_item(uint32_t tmem_base, uint64_t alo, uint64_t blo, uint32_t idesc,
+                                                 bool accum) {
+#pragma unroll
+    for (int i = 0; i < NCC; ++i) {
+#pragma unroll
+        for (int jb = 0; jb < TC_TILE_M / 16; jb += 4) {
+            uint32_t dd[4];
+            uint64_t al[4], bl[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                dd[e] = tmem_base + (uint32_t)(i * 128);
+                al[e] = alo + (uint64_t)((jb + e) * 16);
+                bl[e] = blo + (uint64_t)(i * TC_ROWS + (jb + e) * 16);
+            }
+            if (jb > 0 || accum) tc::mma_bf16_x4<0xF>(dd, al, bl, idesc);
+            else tc::mma_bf16_x4<0xE>(dd, al, bl, idesc);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(192, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant__ CUtensorMap xmap,
                 float* __restrict__ part, int Co, int Cip, int L, int B, int ncc, int ochunks) {
@@ -664,24 +705,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant
                 tc::mbar_wait(full + slot, fphase);
                 tc::fence_after_sync();
                 const uint64_t alo = alo0 + (uint64_t)((uint32_t)slot * (WT_STAGE >> 4));
-                uint64_t blo = blo0 + (uint64_t)((uint32_t)slot * (WT_STAGE >> 4));
-#pragma unroll 1
-                for (int i = 0; i < ncc; ++i, blo += TC_ROWS) {
-                    const uint32_t d = tmem_base + (uint32_t)(i * 128);
-#pragma unroll
-                    for (int jb = 0; jb < TC_TILE_M / 16; jb += 4) {
-                        uint32_t dd[4];
-                        uint64_t al[4], bl[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            dd[e] = d;
-                            al[e] = alo + (uint64_t)((jb + e) * 16);
-                            bl[e] = blo + (uint64_t)((jb + e) * 16);
-                        }
-                        if (accum || jb > 0) tc::mma_bf16_x4<0xF>(dd, al, bl, idesc);
-                        else tc::mma_bf16_x4<0xE>(dd, al, bl, idesc);
-                    }
-                }
+                const uint64_t blo = blo0 + (uint64_t)((uint32_t)slot * (WT_STAGE >> 4));
+                if (ncc == 4) wgrad_issue_item<4>(tmem_base, alo, blo, idesc, accum != 0);
+                else if (ncc == 2) wgrad_issue_item<2>(tmem_base, alo, blo, idesc, accum != 0);
+                else wgrad_issue_item<1>(tmem_base, alo, blo, idesc, accum != 0);
                 accum = 1;
                 tc::mma_commit(empty + slot);
                 if (++slot == WT_NST) { slot = 0; fphase ^= 1; }

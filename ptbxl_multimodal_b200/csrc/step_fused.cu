@@ -52,17 +52,19 @@ step_prep_kernel(const __grid_constant__ PrepArgs A) {
     for (int l = 0; l < 4; ++l) {
         const PrepLayer& P = A.layer[l];
         if (P.w == nullptr) continue;
-        for (long long i = tid; i < P.n; i += nthreads) {
-            const int ii = (int)i;                               // wf index: [k][c/8][o][c%8]
-            const int j = ii & 7;
-            const int o = (ii >> 3) % P.Co;
-            const int cc = (ii / (8 * P.Co)) % (P.Cip / 8);
-            const int k = ii / (8 * P.Co * (P.Cip / 8));
-            const int c = cc * 8 + j;
-            const float v = c < P.Ci ? __ldg(P.w + ((size_t)o * P.Ci + c) * ECG_KS + k) : 0.f;
-            P.wf[ii] = __float2bfloat16(v);
-            if (P.wd != nullptr)
-                P.wd[(((size_t)(ECG_KS - 1 - k) * (P.Co / 8) + (o >> 3)) * P.Cip + c) * 8 + (o & 7)] = __float2bfloat16(v);
+        // one thread per (o, c): its 15 taps are 60 contiguous bytes of the fp32 master; 8 neighbouring threads
+        // (c % 8) fill one 16-byte unit of wf per tap
+        const long long npair = (long long)P.Co * P.Cip;
+        for (long long i = tid; i < npair; i += nthreads) {
+            const int c = (int)(i % P.Cip), o = (int)(i / P.Cip);
+            const float* src = P.w + ((size_t)o * P.Ci + c) * ECG_KS;
+#pragma unroll
+            for (int k = 0; k < ECG_KS; ++k) {
+                const __nv_bfloat16 v = __float2bfloat16(c < P.Ci ? __ldg(src + k) : 0.f);
+                P.wf[(((size_t)k * (P.Cip / 8) + (c >> 3)) * P.Co + o) * 8 + (c & 7)] = v;
+                if (P.wd != nullptr)
+                    P.wd[(((size_t)(ECG_KS - 1 - k) * (P.Co / 8) + (o >> 3)) * P.Cip + c) * 8 + (o & 7)] = v;
+            }
         }
     }
     if (A.wp != nullptr) {
@@ -114,7 +116,8 @@ constexpr int HMAXL = 8;
 constexpr int HT = 1024;        // threads: 4 K-quarters x 256 output features, every weight load in flight at once
 
 // out[s][o] (+)= sum_{k in this thread's quarter} in[s][k] * W[k*ldw + o]; partials combined through shared memory
-__device__ __forceinline__ void head_gemv4(const float (*in)[HMAXF], const float* __restrict__ W, int K, int N,
+// `in` is stored window-minor ([k][HB]) so that the HB operands of one k are ONE 16-byte broadcast load.
+__device__ __forceinline__ void head_gemv4(const float4* in, const float* __restrict__ W, int K, int N,
                                            float (*red)[HB][HMAXF], float* acc) {
     const int o = threadIdx.x & 255, kq = threadIdx.x >> 8;
     const int kper = (K + 3) >> 2, k0 = kq * kper, k1 = min(K, k0 + kper);
@@ -124,8 +127,9 @@ __device__ __forceinline__ void head_gemv4(const float (*in)[HMAXF], const float
 #pragma unroll 16
         for (int k = k0; k < k1; ++k) {
             const float w = __ldg(W + (size_t)k * N + o);
-#pragma unroll
-            for (int s = 0; s < HB; ++s) acc[s] = fmaf(in[s][k], w, acc[s]);
+            const float4 x = in[k];
+            acc[0] = fmaf(x.x, w, acc[0]); acc[1] = fmaf(x.y, w, acc[1]);
+            acc[2] = fmaf(x.z, w, acc[2]); acc[3] = fmaf(x.w, w, acc[3]);
         }
     }
 #pragma unroll
@@ -143,7 +147,9 @@ head_fwd_bwd_kernel(const float* __restrict__ gap, const float* __restrict__ wpT
                     const float* __restrict__ target, float* __restrict__ z, float* __restrict__ logits,
                     float* __restrict__ dlogits, float* __restrict__ dz, float* __restrict__ dgap,
                     float* __restrict__ loss_part, int B, int Cin, int F, int NL, float gscale) {
-    __shared__ float gs[HB][HMAXF], zs[HB][HMAXF], dzs[HB][HMAXF];
+    static_assert(HB == 4, "head kernels keep the HB windows of one feature in a float4");
+    __shared__ float4 gs4[HMAXF], dzs4[HMAXF];       // [feature][window]
+    __shared__ float zs[HB][HMAXF];
     __shared__ float red[4][HB][HMAXF];
     __shared__ float dls[HB][HMAXL];
     __shared__ float lsum[HB * HMAXL];
@@ -152,12 +158,12 @@ head_fwd_bwd_kernel(const float* __restrict__ gap, const float* __restrict__ wpT
     const int o = tid & 255;
     for (int i = tid; i < HB * Cin; i += HT) {
         const int s = i / Cin, c = i - s * Cin;
-        gs[s][c] = s < nb ? __ldg(gap + (size_t)(b0 + s) * Cin + c) : 0.f;
+        reinterpret_cast<float*>(gs4)[c * HB + s] = s < nb ? __ldg(gap + (size_t)(b0 + s) * Cin + c) : 0.f;
     }
     __syncthreads();
     float acc[HB];
     // z[s][o] = bp[o] + sum_c gap[s][c] * Wp[o][c]          (transposed copy: coalesced over o)
-    head_gemv4(gs, wpT, Cin, F, red, acc);
+    head_gemv4(gs4, wpT, Cin, F, red, acc);
     if (tid < 256 && o < F) {
         const float bo = __ldg(bp + o);
 #pragma unroll
@@ -204,15 +210,14 @@ head_fwd_bwd_kernel(const float* __restrict__ gap, const float* __restrict__ wpT
 #pragma unroll
             for (int s = 0; s < HB; ++s) acc[s] = fmaf(dls[s][c], w, acc[s]);
         }
+        dzs4[o] = make_float4(acc[0], acc[1], acc[2], acc[3]);
 #pragma unroll
-        for (int s = 0; s < HB; ++s) {
-            dzs[s][o] = acc[s];
+        for (int s = 0; s < HB; ++s)
             if (s < nb) dz[(size_t)(b0 + s) * F + o] = acc[s];
-        }
     }
     __syncthreads();
     // dgap[s][c] = sum_o dz[s][o] * Wp[o][c]                (coalesced over c)
-    head_gemv4(dzs, wp, F, Cin, red, acc);
+    head_gemv4(dzs4, wp, F, Cin, red, acc);
     if (tid < 256 && o < Cin) {
 #pragma unroll
         for (int s = 0; s < HB; ++s)
