@@ -218,6 +218,18 @@ int ecgb200_head_wgrad_f32(const float* gap, const float* z, const float* dz, co
 int ecgb200_adamw_flat_f32(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper,
                            const int* step_now, void* stream);
 
+/* ------------------------------------------------ data parallel: gradient exchange fused with AdamW --
+ * One launch per rank over NVLink peer memory: barrier -> this rank's 1/world shard of the flat parameter space
+ * gets g = sum_r G_r (peer loads, fixed order) * hyper[5] -> AdamW (as ecgb200_adamw_flat_f32, moments sharded) ->
+ * the new parameters are stored into EVERY rank's buffer (peer stores) -> barrier.  Replaces NCCL all-reduce +
+ * a replicated optimizer step.  p / g / flags are HOST arrays of `world` (<= 8) peer-mapped device pointers;
+ * flags: ecgb200_dp_flag_words(world) zero-initialised uint32 per rank; n % (4*world) == 0; *step_now = 1-based
+ * optimizer step (bias correction), identical on all ranks; all ranks must make the same sequence of calls. */
+int ecgb200_dp_adamw_fused_f32(float* const* p, const float* const* g, unsigned int* const* flags, float* m,
+                               float* v, int64_t n, int rank, int world, const float* hyper, const int* step_now,
+                               void* stream);
+int ecgb200_dp_flag_words(int world);
+
 /* Debug only: when buf != NULL, CTA 0 of the bf16 conv kernel writes clock64() stamps of its pipeline
  * events into buf[0..63] (device memory).  NULL switches tracing off (the default). */
 int ecgb200_debug_set_trace(long long* buf);

@@ -652,6 +652,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cb = blockIdx.x, ob = blockIdx.y, z = blockIdx.z, S = gridDim.z;
+    long long* const trace = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? g_conv_trace : nullptr;
+    if (threadIdx.x == 0) CTR(0);
     const int tiles_t = (L + TC_TILE_M - 1) / TC_TILE_M;
     const int items = B * tiles_t;
     const int nloc = (items - z + S - 1) / S;            // items z, z+S, ...   (host guarantees >= 1)
@@ -684,6 +686,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant
                 tc::mbar_arrive_expect_tx(full + slot, dybytes + xbytes);
                 tc::tma_load_4d(st, &dymap, full + slot, 0, tt * TC_TILE_M, ob * 16, b);
                 tc::tma_load_4d(st + WT_DY_BYTES, &xmap, full + slot, 0, tt * TC_TILE_M - ECG_PAD, cb * ncc, b);
+                if (n < 8) CTR(8 + n);                           // loads of item n issued
                 if (++slot == WT_NST) { slot = 0; ephase ^= 1; }
                 b += db; tt += dt;
                 if (tt >= tiles_t) { tt -= tiles_t; ++b; }
@@ -703,6 +706,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant
             uint32_t fphase = 0, accum = 0;
             for (int n = 0; n < nloc; ++n) {
                 tc::mbar_wait(full + slot, fphase);
+                if (n < 8) CTR(16 + n);                          // item n landed
                 tc::fence_after_sync();
                 const uint64_t alo = alo0 + (uint64_t)((uint32_t)slot * (WT_STAGE >> 4));
                 const uint64_t blo = blo0 + (uint64_t)((uint32_t)slot * (WT_STAGE >> 4));
@@ -711,14 +715,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant
                 else wgrad_issue_item<1>(tmem_base, alo, blo, idesc, accum != 0);
                 accum = 1;
                 tc::mma_commit(empty + slot);
+                if (n < 8) CTR(24 + n);                          // MMAs of item n issued
                 if (++slot == WT_NST) { slot = 0; fphase ^= 1; }
             }
             tc::mma_commit(accfull);
+            CTR(32);
         }
     } else {
         const int q = warp & 3;
         const int o = ob * 128 + 32 * q + lane;
         tc::mbar_wait(accfull, 0);
+        if (threadIdx.x == 64) CTR(33);
         tc::fence_after_sync();
         const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16);
         for (int i = 0; i < ncc; ++i) {
@@ -736,6 +743,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant
             }
         }
     }
+    if (threadIdx.x == 64) CTR(34);
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 2) tc::tmem_dealloc(tmem_base, 512);

@@ -42,7 +42,7 @@ class _Seg:
 
 class TrainStep:
     def __init__(self, model, optimizer: FusedAdamW, batch_size: int, seq_len: int,
-                 process_group=None, use_graph: bool = True, precision: str = "fp32"):
+                 process_group=None, use_graph: bool = True, precision: str = "fp32", dp_mode: str = "auto"):
         if not isinstance(model, (ECGCNN, ECGMultimodal)):
             raise EcgB200Error("TrainStep drives ecgb200 ECGCNN / ECGMultimodal models")
         if not isinstance(optimizer, FusedAdamW) or len(optimizer.param_groups) != 1:
@@ -64,6 +64,13 @@ class TrainStep:
         self.dev = next(model.parameters()).device
         if self.dev.type != "cuda":
             raise EcgB200Error("TrainStep needs the model on a CUDA device (no CPU fallback)")
+        if dp_mode not in ("auto", "fused", "nccl"):
+            raise EcgB200Error("dp_mode must be 'auto', 'fused' (peer-memory reduce-scatter + AdamW + all-gather "
+                               "kernel) or 'nccl' (all-reduce, then a replicated AdamW)")
+        # gradient exchange: the fused NVLink kernel needs the flat-buffer optimizer of the bf16 engine
+        self.dp_fused = self.world > 1 and (dp_mode == "fused" or (dp_mode == "auto" and self.bf16))
+        if self.dp_fused and not self.bf16:
+            raise EcgB200Error("dp_mode='fused' is implemented for precision='bf16'")
         self.use_graph = use_graph
         self.graph = None
         self.launches_per_step = 0
@@ -83,10 +90,15 @@ class TrainStep:
                 [(n, p) for n, p in named if n.startswith(last)]
         total = sum(p.numel() for _, p in order)
         dev = self.dev
-        self.P = torch.empty(total, dtype=F32, device=dev)
-        self.G = torch.zeros(total, dtype=F32, device=dev)
-        self.M = torch.zeros(total, dtype=F32, device=dev)
-        self.V = torch.zeros(total, dtype=F32, device=dev)
+        # padded so that the space splits into 16-byte aligned shards for any world size <= 8
+        self.total_pad = (total + 31) // 32 * 32
+        if self.dp_fused:
+            self._alloc_symmetric(self.total_pad)
+        else:
+            self.P = torch.zeros(self.total_pad, dtype=F32, device=dev)
+            self.G = torch.zeros(self.total_pad, dtype=F32, device=dev)
+        self.M = torch.zeros(self.total_pad, dtype=F32, device=dev)
+        self.V = torch.zeros(self.total_pad, dtype=F32, device=dev)
         self.seg = {}
         off = 0
         with torch.no_grad():
@@ -106,11 +118,46 @@ class TrainStep:
                 self.seg[n] = s
                 off += s.n
         self.total = total
+        if self.world > 1:
+            # replicas must start identical (DDP broadcasts too); cheap, once
+            torch.distributed.broadcast(self.P, src=torch.distributed.get_global_rank(self.pg, 0) if self.pg is not None else 0,
+                                        group=self.pg)
         self.bucket_a_off = self.seg[last + "net.0.weight"].off     # block 4 = tail of the buffers
         self.hyper, self.step_dev = self.opt.device_state(group, dev)
         if self.world > 1:
             self.opt.grad_scale = 1.0 / self.world
             self.hyper, self.step_dev = self.opt.device_state(group, dev)
+
+    def _alloc_symmetric(self, n):
+        """Parameter / gradient / flag buffers in NVLink peer-mapped (symmetric) memory: every rank gets the
+        device pointers of every other rank's buffers for the fused exchange kernel."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        group = self.pg if self.pg is not None else dist.group.WORLD
+        self.rank = dist.get_rank(group)
+        nflag = lib.ecgb200_dp_flag_words(self.world)
+        self.P = symm.empty(n, dtype=F32, device=self.dev)
+        self.G = symm.empty(n, dtype=F32, device=self.dev)
+        self.flags = symm.empty(max(nflag, 64), dtype=torch.int32, device=self.dev)
+        self.P.zero_(); self.G.zero_(); self.flags.zero_()
+        torch.cuda.synchronize(self.dev)
+        hp, hg, hf = (symm.rendezvous(t, group) for t in (self.P, self.G, self.flags))
+        self._symm_handles = (hp, hg, hf)                    # keep the mappings alive
+        ptrs = lambda h: [int(h.buffer_ptrs[r]) for r in range(self.world)]      # noqa: E731
+        self.peer_p, self.peer_g, self.peer_f = ptrs(hp), ptrs(hg), ptrs(hf)
+        if self.peer_p[self.rank] != self.P.data_ptr() or self.peer_g[self.rank] != self.G.data_ptr():
+            raise EcgB200Error("symmetric-memory rendezvous returned unexpected local pointers")
+        dist.barrier(group)
+
+    def gather_optimizer_state(self):
+        """dp_mode='fused' shards the Adam moments (each rank updates 1/world of them).  Before saving an
+        optimizer checkpoint, call this on every rank: all-gathers the shards so that opt.state is complete."""
+        if not self.dp_fused:
+            return
+        per = self.total_pad // self.world
+        for buf in (self.M, self.V):
+            shard = buf[self.rank * per:(self.rank + 1) * per].clone()
+            torch.distributed.all_gather_into_tensor(buf, shard, group=self.pg)
 
     def _refresh_views(self):
         """Re-point parameters at the flat buffers if something (e.g. load_state_dict keeps
@@ -197,7 +244,7 @@ class TrainStep:
         self.ws = torch.empty(ws, dtype=torch.uint8, device=dev)
         del big
         self.side = torch.cuda.Stream(device=dev) if (self.world > 1 or self.bf16) else None
-        self.comm = torch.cuda.Stream(device=dev) if (self.world > 1 and self.bf16) else None
+        self.comm = torch.cuda.Stream(device=dev) if (self.world > 1 and self.bf16 and not self.dp_fused) else None
 
     # ------------------------------------------------------------------ the kernel sequence
     def _k(self, name, fn, *args):
@@ -299,7 +346,7 @@ class TrainStep:
                         self.side.cuda_stream)
                 wg_done[l & 1] = torch.cuda.Event()
                 wg_done[l & 1].record(self.side)
-                if l == 3 and self.world > 1:
+                if l == 3 and self.world > 1 and not self.dp_fused:
                     # bucket A (block 4, the tail of G) is final: all-reduce it while blocks 3..1 run
                     self.comm.wait_event(wg_done[l & 1])
                     with torch.cuda.stream(self.comm):
@@ -385,7 +432,7 @@ class TrainStep:
             n += self._bwd_blocks(st, pre, Pp, Gp)
         # ---- gradient exchange + optimizer
         self._prof_tag = ""
-        if self.world > 1:
+        if self.world > 1 and not self.dp_fused:
             if self.bf16:
                 ev = torch.cuda.Event()
                 ev.record(self.side)
@@ -404,8 +451,15 @@ class TrainStep:
             ev3 = torch.cuda.Event()
             ev3.record(self.side)
             main.wait_event(ev3)                                # join the weight-gradient branch
-            self._k("adamw", lib.ecgb200_adamw_flat_f32, self.P.data_ptr(), self.G.data_ptr(), self.M.data_ptr(),
-                    self.V.data_ptr(), self.total, self.hyper.data_ptr(), self.step_dev.data_ptr(), st)
+            if self.dp_fused:
+                # reduce-scatter + AdamW on the owned shard + all-gather, one kernel over NVLink peer memory
+                W = C.c_void_p * self.world
+                self._k("dp_adamw_fused", lib.ecgb200_dp_adamw_fused_f32, W(*self.peer_p), W(*self.peer_g),
+                        W(*self.peer_f), self.M.data_ptr(), self.V.data_ptr(), self.total_pad, self.rank, self.world,
+                        self.hyper.data_ptr(), self.step_dev.data_ptr(), st)
+            else:
+                self._k("adamw", lib.ecgb200_adamw_flat_f32, self.P.data_ptr(), self.G.data_ptr(), self.M.data_ptr(),
+                        self.V.data_ptr(), self.total_pad, self.hyper.data_ptr(), self.step_dev.data_ptr(), st)
             n += 1
         else:
             one = C.c_void_p * 1
