@@ -24,6 +24,7 @@ from ._lib import lib, check, EcgB200Error
 from .ecg_cnn import ECGCNN
 from .ecg_multimodal import ECGMultimodal
 from .optim import FusedAdamW
+from .parallel import padded_size, shard_bounds
 
 F32 = torch.float32
 
@@ -91,7 +92,7 @@ class TrainStep:
         total = sum(p.numel() for _, p in order)
         dev = self.dev
         # padded so that the space splits into 16-byte aligned shards for any world size <= 8
-        self.total_pad = (total + 31) // 32 * 32
+        self.total_pad = padded_size(total)
         if self.dp_fused:
             self._alloc_symmetric(self.total_pad)
         else:
@@ -154,9 +155,9 @@ class TrainStep:
         optimizer checkpoint, call this on every rank: all-gathers the shards so that opt.state is complete."""
         if not self.dp_fused:
             return
-        per = self.total_pad // self.world
+        lo, hi = shard_bounds(self.total_pad, self.world)[self.rank]
         for buf in (self.M, self.V):
-            shard = buf[self.rank * per:(self.rank + 1) * per].clone()
+            shard = buf[lo:hi].clone()
             torch.distributed.all_gather_into_tensor(buf, shard, group=self.pg)
 
     def _refresh_views(self):
@@ -547,6 +548,46 @@ class TrainStep:
             self._prof = None
             self.opt.param_groups[0]["step"] = self.opt.param_groups[0].get("step", 0) + 1
         return [(n, acc[n] / iters) for n in order]
+
+    def time_kernels(self, iters: int = 10):
+        """Device time of every C-ABI call of the step, free of host launch overhead: each call is captured
+        `iters` times back to back in its own CUDA graph, replayed, and timed with CUDA events on the replay
+        stream (warm caches: in the real step a kernel's inputs were just produced by its predecessor).
+        Returns [(name, ms per launch)].  Advances nothing that matters: buffers are reused, the optimizer
+        kernels run on the live state (call it after the measurement you care about)."""
+        if self.world > 1:
+            raise EcgB200Error("time_kernels() is a single-GPU diagnostic")
+        self._refresh_views()
+        calls = []
+        saved = self._k
+        self._k = lambda name, fn, *args: calls.append((name + self._prof_tag, fn, args))
+        try:
+            self._enqueue()
+        finally:
+            self._k = saved
+        torch.cuda.synchronize(self.dev)
+        out = []
+        s = torch.cuda.Stream(device=self.dev)
+        for name, fn, args in calls:
+            args = list(args)
+            args[-1] = s.cuda_stream
+            with torch.cuda.stream(s):
+                check(fn(*args), name)
+                torch.cuda.synchronize(self.dev)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=s):
+                    for _ in range(iters):
+                        check(fn(*args), name)
+                g.replay()
+                torch.cuda.synchronize(self.dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(s)
+                g.replay()
+                g.replay()
+                e1.record(s)
+                torch.cuda.synchronize(self.dev)
+            out.append((name, e0.elapsed_time(e1) / (2 * iters)))
+        return out
 
     def load_batch(self, x, y, demo=None):
         """Copy a batch (host pinned or device) into the static input buffers (async)."""
