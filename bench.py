@@ -304,6 +304,13 @@ def main():
                 ach = by / (t_ms * 1e-3) / 1e9
                 roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                         "frac": ach / pk["hbm_gbs"], "traffic": None}
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of the same kernels
+            # at this workload (profiles/r01_ncu_full_v3.md); cold-cache, i.e. compulsory traffic
+            ncu_traffic = {"wgrad_L4": 24.9e6, "wgrad_L3": 25.0e6, "wgrad_L2": 24.6e6, "wgrad_L1": 24.6e6, "conv_fwd_L4": 9.3e6,
+                           "conv_fwd_L3": 8.5e6, "conv_fwd_L2": 8.4e6, "conv_fwd_L1": 8.3e6, "dgrad_L4": 17.5e6,
+                           "dgrad_L3": 16.7e6, "dgrad_L2": 16.5e6}
+            if B == 256 and T == 1000 and precision == "bf16":
+                roof["traffic"] = ncu_traffic.get(name)
             roof.update({"peak_source": pk["src"] + " (burst: kernel timed alone, CUDA events around a graph of 10 launches)",
                          "kernel_ms": t_ms, "share_of_step": t_ms / tot,
                          "algorithmic_flops": km["flops"] if km else None,
@@ -321,7 +328,7 @@ def main():
 
     # ---- CPU baseline beside the GPU number (rank 0, N == 1 only; bounded sample)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, b, done, dt = cpu_train_steps(B, T, steps=4, warmup=1, budget_s=25.0)
+        v, b, done, dt = cpu_train_steps(B, T, steps=80, warmup=2, budget_s=15.0)
         line_extra["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                       "sample": f"{done} steps of batch {b} x 12 x {T}, oracle port of the reference "
                                                 f"modules on the host CPU, fp32, {dt:.1f} s"}
