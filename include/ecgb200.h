@@ -194,7 +194,9 @@ int ecgb200_adamw_f32(int ntensors, float* const* p, const float* const* g, floa
 /* ------------------------------------------------ fused per-step kernels (TrainStep engine) --
  * Step prologue in one launch: pack x (B,Ci0,T) fp32 -> xb blocked bf16 (ecgb200_pack_input_bf16), re-lay the
  * nlayers <= 4 conv weights (ecgb200_conv1d_prep_weights_bf16), transpose the proj weight wp (F,Cin) ->
- * wpT (Cin,F) [wp may be NULL], and *step_ctr += 1 [may be NULL].  w/wf/wd/co/ci are HOST arrays. */
+ * wpT (Cin,F) [wp may be NULL], and *step_ctr += 1 [may be NULL].  w/wf/wd/co/ci are HOST arrays.
+ * x may be NULL (weights only): the engine packs the input + block-1 weights on the critical path and
+ * re-lays the other weights beside the first conv. */
 int ecgb200_step_prep_bf16(const float* x, void* xb, int B, int Ci0, int T, int nlayers,
                            const float* const* w, void* const* wf, void* const* wd, const int* co,
                            const int* ci, const float* wp, float* wpT, int F, int Cin, int* step_ctr,

@@ -696,13 +696,20 @@ bn_bwd_reduce_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__
         sf[i] = __ldg(bn_state + 3 * C + cc * 8 + i);
         s[i] = 0.f; s[8 + i] = 0.f;
     }
-    int bl = 0, j = threadIdx.x;
-    while (j >= Lp) { j -= Lp; ++bl; }
-    while (bl < nb) {
-        const size_t row = (size_t)(b0 + bl) * (C / 8) + cc;
-        float a0[8], a1[8], d[8];
+    // flattened (sample, pool pair) walk, two pairs per iteration so that six 16-byte loads are in flight
+    const int n = nb * Lp;
+    for (int idx = threadIdx.x; idx < n; idx += 2 * blockDim.x) {
+        const int idx2 = idx + blockDim.x;
+        const bool has2 = idx2 < n;
+        const int bl = idx / Lp, j = idx - bl * Lp;
+        const int bl2 = has2 ? idx2 / Lp : bl, j2 = has2 ? idx2 - bl2 * Lp : j;
+        const size_t row = (size_t)(b0 + bl) * (C / 8) + cc, row2 = (size_t)(b0 + bl2) * (C / 8) + cc;
         const uint4 u0 = __ldg(y + row * L + 2 * j), u1 = __ldg(y + row * L + 2 * j + 1);
+        const uint4 w0 = __ldg(y + row2 * L + 2 * j2), w1 = __ldg(y + row2 * L + 2 * j2 + 1);
+        float d[8], e[8];
         load_dgrad8(dp, dgap, row, Lp, j, b0 + bl, C, cc, inv_lp, d);
+        load_dgrad8(dp, dgap, row2, Lp, j2, b0 + bl2, C, cc, inv_lp, e);
+        float a0[8], a1[8];
         bf8_unpack(u0, a0);
         bf8_unpack(u1, a1);
 #pragma unroll
@@ -713,8 +720,18 @@ bn_bwd_reduce_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__
             s[i] += g;
             s[8 + i] = fmaf(g, s0 ? a0[i] : a1[i], s[8 + i]);
         }
-        j += blockDim.x;
-        while (j >= Lp) { j -= Lp; ++bl; }
+        if (has2) {
+            bf8_unpack(w0, a0);
+            bf8_unpack(w1, a1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                bool s0, s1;
+                pool_sel(a0[i], a1[i], sc[i], sf[i], s0, s1);
+                const float g = (s0 || s1) ? e[i] : 0.f;
+                s[i] += g;
+                s[8 + i] = fmaf(g, s0 ? a0[i] : a1[i], s[8 + i]);
+            }
+        }
     }
     block_sum_vec<16>(s, sh);
     if (threadIdx.x < 8) {

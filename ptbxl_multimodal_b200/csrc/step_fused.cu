@@ -82,24 +82,26 @@ extern "C" int ecgb200_step_prep_bf16(const float* x, void* xb, int B, int Ci0, 
                                       const float* const* w, void* const* wf, void* const* wd, const int* co,
                                       const int* ci, const float* wp, float* wpT, int F, int Cin,
                                       int* step_ctr, void* stream) {
-    if (!x || !xb || B <= 0 || Ci0 <= 0 || T <= 0 || nlayers < 0 || nlayers > 4) return ECGB200_EINVAL;
+    if (nlayers < 0 || nlayers > 4) return ECGB200_EINVAL;
+    if (x != nullptr && (!xb || B <= 0 || Ci0 <= 0 || T <= 0)) return ECGB200_EINVAL;
     PrepArgs A;
     A.x = x; A.xb = (uint4*)xb; A.B = B; A.Ci0 = Ci0; A.Cp0 = (Ci0 + 15) / 16 * 16; A.T = T;
-    A.n_pack = (long long)B * (A.Cp0 / 8) * T;
-    long long work = A.n_pack;
+    A.n_pack = x != nullptr ? (long long)B * (A.Cp0 / 8) * T : 0;            // x == NULL: weights only
+    long long work = A.n_pack > 0 ? A.n_pack : 1;
     for (int l = 0; l < 4; ++l) {
         PrepLayer& P = A.layer[l];
         if (l < nlayers) {
             if (!w || !wf || !wd || !co || !ci || !w[l] || !wf[l] || co[l] <= 0 || (co[l] & 7) || ci[l] <= 0) return ECGB200_EINVAL;
             P.w = w[l]; P.wf = (__nv_bfloat16*)wf[l]; P.wd = (__nv_bfloat16*)wd[l];
             P.Co = co[l]; P.Ci = ci[l]; P.Cip = (ci[l] + 15) / 16 * 16; P.n = ECG_KS * P.Cip * P.Co;
-            if (P.n > work) work = P.n;
+            if ((long long)P.Co * P.Cip > work) work = (long long)P.Co * P.Cip;
         } else {
             P.w = nullptr; P.wf = nullptr; P.wd = nullptr; P.Co = P.Ci = P.Cip = P.n = 0;
         }
     }
     A.wp = wp; A.wpT = wpT; A.F = F; A.Cin = Cin; A.step_ctr = step_ctr;
     if (wp != nullptr && (!wpT || F <= 0 || Cin <= 0)) return ECGB200_EINVAL;
+    if (wp != nullptr && (long long)F * Cin > work) work = (long long)F * Cin;
     long long blocks = (work + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     step_prep_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(A);

@@ -245,6 +245,7 @@ class TrainStep:
         self.ws = torch.empty(ws, dtype=torch.uint8, device=dev)
         del big
         self.side = torch.cuda.Stream(device=dev) if (self.world > 1 or self.bf16) else None
+        self.linear = False
         self.comm = torch.cuda.Stream(device=dev) if (self.world > 1 and self.bf16 and not self.dp_fused) else None
 
     # ------------------------------------------------------------------ the kernel sequence
@@ -293,17 +294,29 @@ class TrainStep:
         self._prof_tag = ""
         PV, I4 = C.c_void_p * 4, C.c_int * 4
         wkeys = [f"{pre}backbone.{l}.net.0.weight" for l in range(4)]
-        self._k("prep", lib.ecgb200_step_prep_bf16, _p(self.x), _p(self.acts[0]), B, self.chan[0], self.T, 4,
-                PV(*[Pp(k) for k in wkeys]), PV(*[_p(w) for w in self.wt]), PV(*[_p(w) for w in self.wd]),
-                I4(*self.chan[1:5]), I4(*self.chan[0:4]),
-                None if self.mm else Pp(pre + "proj.weight"), None if self.mm else _p(self.wpT),
-                self.feat, self.chan[4], self.step_dev.data_ptr(), st)
-        n += 1
+        main = torch.cuda.current_stream(self.dev)
+        # critical path: pack the input + block-1 weights (+ step counter); blocks 2-4 and the proj transpose
+        # are re-laid beside the first conv on the side stream
+        self._k("prep", lib.ecgb200_step_prep_bf16, _p(self.x), _p(self.acts[0]), B, self.chan[0], self.T, 1,
+                PV(Pp(wkeys[0]), None, None, None), PV(_p(self.wt[0]), None, None, None), PV(None, None, None, None),
+                I4(self.chan[1], 0, 0, 0), I4(self.chan[0], 0, 0, 0), None, None, 0, 0, self.step_dev.data_ptr(), st)
+        self._fork_side(main)
+        with torch.cuda.stream(self.side):
+            self._k("prep_w", lib.ecgb200_step_prep_bf16, None, None, 0, 0, 0, 3,
+                    PV(*[Pp(k) for k in wkeys[1:]], None), PV(*[_p(w) for w in self.wt[1:]], None),
+                    PV(*[_p(w) for w in self.wd[1:]], None), I4(*self.chan[2:5], 0), I4(*self.chan[1:4], 0),
+                    None if self.mm else Pp(pre + "proj.weight"), None if self.mm else _p(self.wpT),
+                    self.feat, self.chan[4], None, self.side.cuda_stream)
+            prep_done = torch.cuda.Event()
+            prep_done.record(self.side)
+        n += 2
         for l in range(4):
             cip, co, L = self.cip[l], self.chan[l + 1], self.L[l]
             k = f"{pre}backbone.{l}.net."
             bn = blocks[l].net[1]
             self._prof_tag = f"_L{l + 1}"
+            if l == 1:
+                main.wait_event(prep_done)
             self._k("conv_fwd", lib.ecgb200_conv1d_fwd_stats_bf16, _p(self.acts[l]), _p(self.wt[l]), Pp(k + "0.bias"),
                     _p(self.ybuf[l]), _p(self.statp[l]), B, cip, co, L, st)
             self._k("bn_relu_pool", lib.ecgb200_bn_relu_pool_fwd_train_bf16, _p(self.ybuf[l]), _p(self.statp[l]),
@@ -315,6 +328,9 @@ class TrainStep:
         return n
 
     def _fork_side(self, main):
+        if self.linear:                      # single-stream schedule: "side" work is enqueued in line
+            self.side = main
+            return
         ev = torch.cuda.Event()
         ev.record(main)
         self.side.wait_event(ev)

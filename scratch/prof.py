@@ -11,13 +11,10 @@ torch.manual_seed(42)
 m = (P.ECGCNN(12,256,5) if kind=='cnn' else P.ECGMultimodal()).cuda().train()
 o = P.FusedAdamW(m.parameters(), lr=1.5e-3, weight_decay=1e-4)
 e = TrainStep(m, o, B, T, precision=prec)
+if os.environ.get('LINEAR'): e.linear = True; e.side = torch.cuda.current_stream()
 e.x.normal_(); e.y.bernoulli_(0.3)
 if kind!='cnn': e.demo.uniform_()
 for _ in range(3): e.run()
-prof = e.profile_kernels(10)
-tot = sum(t for _, t in prof)
-for n, t in prof: print(f'{n:18s} {t*1000:8.1f} us  {100*t/tot:5.1f}%')
-print('total', tot*1000, 'us; launches', e.launches_per_step)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
