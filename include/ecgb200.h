@@ -118,6 +118,13 @@ int ecgb200_bn_relu_pool_fwd_bf16(const void* yb, const float* bn_state, void* p
 int ecgb200_bn_relu_pool_bwd_bf16(const void* yb, const float* bn_state, const void* dpb, const float* dgap,
                                   void* dyb, float* dgamma, float* dbeta, float* db_part, void* ws,
                                   int B, int C, int L, int train, void* stream);
+/* The same backward as ONE cooperative launch (reduce -> grid barrier -> apply from a shared-memory copy of the
+ * block's slice).  ecgb200_bn_bwd_fused_nsplit returns the second dim of db_part for it, or 0 when the slice does
+ * not fit shared memory for this shape (then use the two-kernel call above). */
+int ecgb200_bn_relu_pool_bwd_fused_bf16(const void* yb, const float* bn_state, const void* dpb, const float* dgap,
+                                        void* dyb, float* dgamma, float* dbeta, float* db_part, void* ws,
+                                        int B, int C, int L, int train, void* stream);
+int ecgb200_bn_bwd_fused_nsplit(int B, int C, int L, int has_dp);
 /* number of per-channel partials the bf16 BN kernels produce (second dim of db_part) */
 int ecgb200_bn_nsplit(int B, int C);
 

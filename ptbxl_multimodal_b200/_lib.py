@@ -50,6 +50,8 @@ _SIGS = {
     "ecgb200_bn_relu_pool_fwd_bf16": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "ecgb200_bn_relu_pool_bwd_bf16": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "ecgb200_bn_nsplit": (_I, [_I, _I]),
+    "ecgb200_bn_relu_pool_bwd_fused_bf16": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "ecgb200_bn_bwd_fused_nsplit": (_I, [_I, _I, _I, _I]),
     "ecgb200_conv1d_fwd_stats_bf16": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "ecgb200_conv1d_stat_parts_bf16": (_I, [_I, _I, _I, _I]),
     "ecgb200_bn_relu_pool_fwd_train_bf16": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _P]),

@@ -204,7 +204,15 @@ class TrainStep:
             self.ybuf = [eb(B, self.chan[l + 1] // 8, self.L[l], 8) for l in range(4)]
             self.wt = [eb(15, self.cip[l] // 8, self.chan[l + 1], 8) for l in range(4)]
             self.wd = [None] + [eb(15, self.chan[l + 1] // 8, self.cip[l], 8) for l in range(1, 4)]
-            self.ndb = [lib.ecgb200_bn_nsplit(B, self.chan[l + 1]) for l in range(4)]
+            # BN backward: reduce + apply as two launches.  The single cooperative launch
+            # (ecgb200_bn_relu_pool_bwd_fused_bf16) measured SLOWER inside the step (466 vs 447 us at B=256): its
+            # 2-blocks-per-SM shared-memory slices lower occupancy and, needing the whole GPU at once, it stops
+            # overlapping with the weight-gradient branch.  Kept behind ECGB200_BN_FUSED=1 for experiments.
+            import os
+            use = os.environ.get("ECGB200_BN_FUSED") == "1"
+            self.bn_fused = [lib.ecgb200_bn_bwd_fused_nsplit(B, self.chan[l + 1], self.L[l], 1 if l < 3 else 0) if use else 0
+                             for l in range(4)]
+            self.ndb = [self.bn_fused[l] or lib.ecgb200_bn_nsplit(B, self.chan[l + 1]) for l in range(4)]
             self.dbpart = [e(self.chan[l + 1], self.ndb[l]) for l in range(4)]
             self.stat = [None] * 4
             # per-CTA {sum, sumsq} partials written by the conv epilogue
@@ -352,10 +360,11 @@ class TrainStep:
             dy = dys[l & 1]
             if wg_done[l & 1] is not None:
                 main.wait_event(wg_done[l & 1])                # wgrad of block l+2 has finished reading this dy
-            self._k("bn_bwd", lib.ecgb200_bn_relu_pool_bwd_bf16, _p(self.ybuf[l]), _p(self.bnst[l]),
+            self._k("bn_bwd", lib.ecgb200_bn_relu_pool_bwd_fused_bf16 if self.bn_fused[l] else lib.ecgb200_bn_relu_pool_bwd_bf16,
+                    _p(self.ybuf[l]), _p(self.bnst[l]),
                     _p(self.dp) if l < 3 else None, _p(self.dgap) if l == 3 else None, _p(dy),
                     Gp(k + "1.weight"), Gp(k + "1.bias"), _p(self.dbpart[l]), _p(self.ws2), B, co, L, 1, st)
-            n += 2
+            n += 1 if self.bn_fused[l] else 2
             self._fork_side(main)
             with torch.cuda.stream(self.side):
                 self._k("wgrad", lib.ecgb200_conv1d_wgrad_bf16, _p(dy), _p(self.acts[l]), Gp(k + "0.weight"),

@@ -286,3 +286,40 @@ def test_step_prep_and_flat_adamw():
         cb += 1
     torch.cuda.synchronize()
     assert torch.equal(pa, pb_) and torch.equal(ma, mb) and torch.equal(va, vb)
+
+
+@pytest.mark.parametrize("B,C,L", [(4, 32, 1000), (3, 64, 250), (5, 256, 125), (2, 128, 31), (256, 64, 500), (64, 256, 125)])
+@pytest.mark.parametrize("use_gap", [False, True])
+def test_bn_backward_fused_equals_two_kernel_path(B, C, L, use_gap):
+    """One cooperative launch (reduce -> grid barrier -> apply from shared memory) == the reduce + apply pair."""
+    ns = lib.ecgb200_bn_bwd_fused_nsplit(B, C, L, 0 if use_gap else 1)
+    assert ns > 0
+    y = (gen(B, C, L, seed=5) * 1.7 + 0.3)
+    gamma, beta = (1 + 0.2 * gen(C, seed=6)).to(DEV), (0.1 * gen(C, seed=7)).to(DEV)
+    yb = to_blocked(y).to(DEV)
+    rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    nbt = torch.zeros((), dtype=torch.int64, device=DEV)
+    st = torch.empty(4, C, device=DEV)
+    ws = torch.empty(lib.ecgb200_bn_bwd_ws_bytes(B, C), dtype=torch.uint8, device=DEV)
+    check(lib.ecgb200_bn_train_stats_bf16(ptr(yb), ptr(gamma), ptr(beta), ptr(rm), ptr(rv), ptr(nbt), ptr(st), ptr(ws),
+                                          B, C, L, 0.1, 1e-5, stream()), "stats")
+    Lp = L // 2
+    dout = gen(B, C, seed=11) if use_gap else gen(B, C, Lp, seed=11)
+    dpb = None if use_gap else to_blocked(dout).to(DEV)
+    dgap = dout.to(DEV) if use_gap else None
+    res = []
+    for fused in (False, True):
+        dyb = torch.full((B, C // 8, L, 8), float("nan"), dtype=BF, device=DEV)
+        dgm, dbt = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+        nsp = ns if fused else lib.ecgb200_bn_nsplit(B, C)
+        dbp = torch.empty(C, nsp, device=DEV)
+        fn = lib.ecgb200_bn_relu_pool_bwd_fused_bf16 if fused else lib.ecgb200_bn_relu_pool_bwd_bf16
+        check(fn(ptr(yb), ptr(st), ptr(dpb), ptr(dgap), ptr(dyb), ptr(dgm), ptr(dbt), ptr(dbp), ptr(ws), B, C, L, 1,
+                 stream()), "bn_bwd")
+        torch.cuda.synchronize()
+        res.append((dyb.float().cpu(), dgm.cpu(), dbt.cpu(), dbp.sum(dim=1).cpu()))
+    (dy0, g0, b0, s0), (dy1, g1, b1, s1) = res
+    assert torch.isfinite(dy1).all()
+    assert rel_inf(g1, g0) < 1e-5 and rel_inf(b1, b0) < 1e-5
+    assert rel_inf(dy1, dy0) < 8e-3                      # same math, different partial-sum grouping: bf16 ties
+    assert float((s1 - s0).abs().max()) <= 1e-3 * float(s0.abs().max()) + 1e-2
