@@ -239,6 +239,12 @@ int ecgb200_dp_adamw_fused_f32(float* const* p, const float* const* g, unsigned 
                                void* stream);
 int ecgb200_dp_flag_words(int world);
 
+/* Programmatic dependent launch for the kernels of the bf16 step's critical path (conv, BatchNorm forward): when on,
+ * they are launched with cudaLaunchAttributeProgrammaticStreamSerialization and overlap their prologue with the
+ * previous kernel's tail (each waits for the previous kernel's completion before touching global memory).
+ * Returns the previous setting.  Off by default. */
+int ecgb200_set_pdl(int on);
+
 /* Debug only: when buf != NULL, CTA 0 of the bf16 conv kernel writes clock64() stamps of its pipeline
  * events into buf[0..63] (device memory).  NULL switches tracing off (the default). */
 int ecgb200_debug_set_trace(long long* buf);

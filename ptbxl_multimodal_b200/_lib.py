@@ -61,6 +61,7 @@ _SIGS = {
     "ecgb200_head_wgrad_f32": (_I, [_P] * 10 + [_I, _I, _I, _I, _P]),
     "ecgb200_dp_adamw_fused_f32": (_I, [_P, _P, _P, _P, _P, C.c_int64, _I, _I, _P, _P, _P]),
     "ecgb200_dp_flag_words": (_I, [_I]),
+    "ecgb200_set_pdl": (_I, [_I]),
     "ecgb200_debug_set_trace": (_I, [_P]),
     "ecgb200_debug_set_diag": (_I, [_P]),
     "ecgb200_adamw_flat_f32": (_I, [_P, _P, _P, _P, C.c_int64, _P, _P, _P]),

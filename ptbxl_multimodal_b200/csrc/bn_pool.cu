@@ -560,6 +560,8 @@ bn_fwd_train_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__ 
     __shared__ float scs[8], sfs[8];
     const int cc = blockIdx.x;
     const int b0 = blockIdx.y * tile_b, nb = min(tile_b, B - b0);
+    ecg_pdl_launch_dependents();
+    ecg_pdl_wait();
     merge_parts8(part, nparts, C, cc, shd, mom);
     if (threadIdx.x < 8) {
         const int c = cc * 8 + threadIdx.x;
@@ -649,14 +651,12 @@ extern "C" int ecgb200_bn_relu_pool_fwd_train_bf16(const void* yb, const float* 
     const int tile_b = bnb_tile_b(B, C, 4), NS = (B + tile_b - 1) / tile_b;
     cudaStream_t st = (cudaStream_t)stream;
     if (gap != nullptr)
-        bn_fwd_train_bf16_kernel<true><<<dim3(C / 8, NS), 256, 0, st>>>(
-            (const uint4*)yb, stat_part, nparts, gamma, beta, running_mean, running_var, nbt, bn_state, (uint4*)pb,
-            gap, B, C, L, Lp, tile_b, momentum, eps);
-    else
-        bn_fwd_train_bf16_kernel<false><<<dim3(C / 8, NS), 256, 0, st>>>(
-            (const uint4*)yb, stat_part, nparts, gamma, beta, running_mean, running_var, nbt, bn_state, (uint4*)pb,
-            nullptr, B, C, L, Lp, tile_b, momentum, eps);
-    return ecg_launch_status();
+        return ecg_launch_pdl(bn_fwd_train_bf16_kernel<true>, dim3(C / 8, NS), dim3(256), 0, st, (const uint4*)yb,
+                              stat_part, nparts, gamma, beta, running_mean, running_var, nbt, bn_state, (uint4*)pb, gap,
+                              B, C, L, Lp, tile_b, momentum, eps);
+    return ecg_launch_pdl(bn_fwd_train_bf16_kernel<false>, dim3(C / 8, NS), dim3(256), 0, st, (const uint4*)yb,
+                          stat_part, nparts, gamma, beta, running_mean, running_var, nbt, bn_state, (uint4*)pb,
+                          (float*)nullptr, B, C, L, Lp, tile_b, momentum, eps);
 }
 
 // Routing of one pool pair in terms of the raw conv outputs a0, a1 (first index wins ties, ReLU mask):

@@ -18,6 +18,28 @@ static inline int ecg_launch_status() {
 
 static inline int ecg_cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// Programmatic dependent launch (PDL): when enabled (ecgb200_set_pdl), the kernels of the step's critical path are
+// launched with the programmatic-stream-serialization attribute, so a kernel's CTAs are scheduled -- and run their
+// prologue (barrier init, TMEM allocation, index math) -- while the previous kernel drains.  Every such kernel
+// calls ecg_pdl_wait() before it touches global memory, which blocks until the previous kernel has COMPLETED and
+// flushed (full dependency semantics), and ecg_pdl_launch_dependents() at its top.
+extern int g_ecg_pdl;
+__device__ __forceinline__ void ecg_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void ecg_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KP, typename... KA>
+static inline int ecg_launch_pdl(void (*kernel)(KP...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, KA... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_ecg_pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
+    return e == cudaSuccess ? ecg_launch_status() : (int)e;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

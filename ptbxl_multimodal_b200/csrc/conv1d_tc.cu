@@ -258,6 +258,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __nv_bfloat16* __
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);     // provably warp-uniform
     const int lane = threadIdx.x & 31;
     const int ngl = ((int)blockIdx.x < P.ngroups) ? (P.ngroups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    ecg_pdl_launch_dependents();
     long long* const trace = g_conv_trace;
     if (threadIdx.x == 0) CTR(0);
 
@@ -276,6 +277,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __nv_bfloat16* __
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);        // uniform for the compiler too
+    ecg_pdl_wait();                                    // everything above overlapped the previous kernel's tail
     if (threadIdx.x == 0) CTR(1);
 
     if (warp == 0) {
@@ -590,9 +592,8 @@ extern "C" int ecgb200_conv1d_fwd_stats_bf16(const void* xb, const void* wprep, 
         if (e != cudaSuccess) return (int)e;
         smem_set = smem;
     }
-    conv_tc_kernel<<<grid, C2_THREADS, smem, (cudaStream_t)stream>>>(xmap, (const __nv_bfloat16*)wprep, bias,
-                                                              (__nv_bfloat16*)yb, stat_part, P);
-    return ecg_launch_status();
+    return ecg_launch_pdl(conv_tc_kernel, dim3(grid), dim3(C2_THREADS), smem, (cudaStream_t)stream, xmap,
+                          (const __nv_bfloat16*)wprep, bias, (__nv_bfloat16*)yb, stat_part, P);
 }
 
 extern "C" int ecgb200_conv1d_fwd_bf16(const void* xb, const void* wprep, const float* bias, void* yb,

@@ -223,5 +223,7 @@ extern "C" int ecgb200_row_mean_f32(const float* x, float* out, int rows, int L,
     return ecg_launch_status();
 }
 
+int g_ecg_pdl = 0;
+extern "C" int ecgb200_set_pdl(int on) { const int old = g_ecg_pdl; g_ecg_pdl = on ? 1 : 0; return old; }
 extern "C" int ecgb200_version(void) { return 100; }
 extern "C" int ecgb200_arch(void) { return 1000; }
