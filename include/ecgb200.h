@@ -80,7 +80,7 @@ int ecgb200_unpack_act_bf16(const void* xb, float* x, int B, int C, int L, void*
  * wd bf16 [15][Co/8][Cip][8] (tap-flipped transpose: dgrad operand); Cip = Ci rounded up to 16. */
 int ecgb200_conv1d_prep_weights_bf16(const float* w, void* wf, void* wd, int Co, int Ci, void* stream);
 /* Conv1d(k=15,pad=7) as implicit GEMM on tcgen05: yb = conv(xb, wprep) + bias.
- * Same call computes dgrad with (dy, wd, NULL).  Ci % 16 == 0, Co % 32 == 0, both <= 256.
+ * Same call computes dgrad with (dy, wd, NULL).  Ci % 16 == 0 (Ci % 64 == 0 above 64), Co % 32 == 0, both <= 256.
  * replaces aten::convolution (ecg_cnn.py:13) in bf16 mode. */
 int ecgb200_conv1d_fwd_bf16(const void* xb, const void* wprep, const float* bias, void* yb,
                             int B, int Ci, int Co, int L, void* stream);

@@ -566,7 +566,7 @@ static int conv2_cfg(int B, int Ci, int Co, int L, Conv2Cfg* P, size_t* smem_out
 extern "C" int ecgb200_conv1d_stat_parts_bf16(int B, int Ci, int Co, int L) {
     Conv2Cfg P;
     size_t smem;
-    if (B <= 0 || L <= 0 || Ci <= 0 || (Ci & 15) || Ci > 256 || Co <= 0 || (Co & 31) || Co > 256) return 0;
+    if (B <= 0 || L <= 0 || Ci <= 0 || (Ci & 15) || Ci > 256 || (Ci > 64 && (Ci & 63)) || Co <= 0 || (Co & 31) || Co > 256) return 0;
     const int g = conv2_cfg(B, Ci, Co, L, &P, &smem);
     return g > 0 ? g : 0;
 }
@@ -578,7 +578,7 @@ extern "C" int ecgb200_conv1d_stat_parts_bf16(int B, int Ci, int Co, int L) {
 extern "C" int ecgb200_conv1d_fwd_stats_bf16(const void* xb, const void* wprep, const float* bias, void* yb,
                                              float* stat_part, int B, int Ci, int Co, int L, void* stream) {
     if (!xb || !wprep || !yb || B <= 0 || L <= 0) return ECGB200_EINVAL;
-    if (Ci <= 0 || (Ci & 15) || Ci > 256 || Co <= 0 || (Co & 31) || Co > 256) return ECGB200_EUNSUPPORTED;
+    if (Ci <= 0 || (Ci & 15) || Ci > 256 || (Ci > 64 && (Ci & 63)) || Co <= 0 || (Co & 31) || Co > 256) return ECGB200_EUNSUPPORTED;
     CUtensorMap xmap;
     int rc = ecg_make_act_tmap(&xmap, xb, B, Ci, L, TC_ROWS, Ci / 8);
     if (rc) return rc;
