@@ -555,8 +555,14 @@ class TrainStep:
         # programmatic dependent launch of the conv / BN-forward chain measured slower in the step (460 vs 449 us:
         # early-scheduled dependents take SM slots from the weight-gradient branch), so it is opt-in
         old = lib.ecgb200_set_pdl(1 if (self.bf16 and os.environ.get("ECGB200_PDL", "0") == "1") else 0)
+        # Capturing the critical path on a higher-priority stream than the weight-gradient branch (so that dgrad
+        # wins the SMs over wgrad when both become ready) measured slightly SLOWER (460 vs 451 us): the step is
+        # bound by the sum of the tensor kernels, which cannot share an SM (TMEM / shared memory), not by their
+        # order.  Equal priorities by default.
+        prio = os.environ.get("ECGB200_MAIN_PRIORITY", "0")
+        self.capture_stream = torch.cuda.Stream(device=self.dev, priority=int(prio)) if self.bf16 else None
         try:
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=self.capture_stream):
                 self._enqueue()
         finally:
             lib.ecgb200_set_pdl(old)
