@@ -109,6 +109,7 @@ def cpu_train_steps(batch: int, seq_len: int, steps: int, warmup: int, budget_s:
     st = O.AdamWState(sd, 1.5e-3, 1e-4)
     b = batch
     x, y = O.synth_batch(b, seq_len, 5, seed=0)
+    O.train_step(sd, x, y, st)                     # cold (thread pool, allocator): not representative
     t0 = time.perf_counter()
     O.train_step(sd, x, y, st)
     one = time.perf_counter() - t0
@@ -117,7 +118,7 @@ def cpu_train_steps(batch: int, seq_len: int, steps: int, warmup: int, budget_s:
         b //= 2
     if b != batch:
         x, y = x[:b].contiguous(), y[:b].contiguous()
-    for _ in range(max(0, warmup - 1)):
+    for _ in range(max(0, warmup - 2)):
         O.train_step(sd, x, y, st)
     t0 = time.perf_counter()
     done = 0
@@ -226,10 +227,14 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
-    # ---- device-resident arm (value)
+    # ---- device-resident arm (value): the batches live in the engine's two input slots (HBM); a step = one graph
+    # replay on the slot's graph.  The 12 MB input is evicted from L2 between steps by the step's own ~0.27 GB of
+    # activation traffic.
+    eng.load_batch(dx[0], dy[0], slot=0)
+    eng.load_batch(dx[1], dy[1], slot=1)
+
     def step_dev(i):
-        eng.load_batch(dx[i % NB], dy[i % NB])
-        eng.run()
+        eng.run(slot=i & 1)
 
     for i in range(W):
         step_dev(i)
@@ -240,31 +245,29 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * K / (ms / 1000.0)
 
-    # ---- end-to-end arm: pinned host batches in, loss out, every step; H2D overlapped on a copy stream
+    # ---- end-to-end arm: every step its own pinned-host batch in (H2D on a copy stream, straight into the idle
+    # input slot while the other slot's graph runs) and the loss out (D2H)
     copy_stream = torch.cuda.Stream(device=dev)
-    stage = [(torch.empty_like(dx[0]), torch.empty_like(dy[0])) for _ in range(2)]
     staged = [torch.cuda.Event() for _ in range(2)]
     freed = [torch.cuda.Event() for _ in range(2)]
     host_loss = torch.zeros(64, dtype=torch.float32).pin_memory()
     main_stream = torch.cuda.current_stream(dev)
 
     def prefetch(i):
-        s = i % 2
-        copy_stream.wait_event(freed[s])
+        s = i & 1
+        copy_stream.wait_event(freed[s])                  # the graph that read slot s has finished
         with torch.cuda.stream(copy_stream):
-            stage[s][0].copy_(hx[i % NB], non_blocking=True)
-            stage[s][1].copy_(hy[i % NB], non_blocking=True)
+            eng.load_batch(hx[i % NB], hy[i % NB], slot=s)
             staged[s].record(copy_stream)
 
     def step_e2e(i):
-        s = i % 2
+        s = i & 1
         if i == 0:
             prefetch(0)
         prefetch(i + 1)                                   # next batch streams in under this step's compute
         main_stream.wait_event(staged[s])
-        eng.load_batch(stage[s][0], stage[s][1])
+        loss = eng.run(slot=s)
         freed[s].record(main_stream)
-        loss = eng.run()
         host_loss[i % 64].copy_(loss, non_blocking=True)  # D2H read of the step's result
 
     for s in range(2):
@@ -341,7 +344,7 @@ def main():
             "config": {"workload": "configs[1]: ECGCNN(12,256,5) train step, synthetic 12x1000, 5-label BCE, "
                                    "AdamW(1.5e-3,1e-4)", "batch_per_gpu": B, "global_batch": B * world,
                        "seq_len": T, "parallelism": f"dp{world}", "precision": precision,
-                       "l2": "step working set ~0.27 GB > 126 MB L2; inputs rotate over 8 resident batches"},
+                       "l2": "step working set ~0.27 GB > 126 MB L2; inputs alternate between the engine's two resident input slots"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / K, "last_loss": last_loss},

@@ -179,8 +179,12 @@ class TrainStep:
         self.L = [T, T // 2, T // 4, T // 8]                      # conv lengths; pooled = L // 2
         self.nl = self.model.head.out_features
         self.feat = self.bb.proj.out_features
-        self.x = e(B, self.chan[0], T)
-        self.y = e(B, self.nl)
+        # two input slots: the next batch can be copied in (H2D) while the graph of the other slot runs
+        self.xs = [e(B, self.chan[0], T), e(B, self.chan[0], T)]
+        self.ys = [e(B, self.nl), e(B, self.nl)]
+        self.demos = [None, None]
+        self.cur = 0
+        self.x, self.y, self.demo = self.xs[0], self.ys[0], None
         self.acts = [self.x]                                       # input of conv l
         self.ybuf, self.stat, self.bnst, self.wt, self.wd = [], [], [], [], []
         for l in range(4):
@@ -232,7 +236,8 @@ class TrainStep:
         self.loss = torch.zeros((), dtype=F32, device=dev)
         if self.mm:
             dm = self.model.demo_encoder.mlp
-            self.demo = e(B, dm[0].in_features)
+            self.demos = [e(B, dm[0].in_features), e(B, dm[0].in_features)]
+            self.demo = self.demos[0]
             self.h1, self.dh1 = e(B, dm[0].out_features), e(B, dm[0].out_features)
             self.h2, self.dh2 = e(B, dm[2].out_features), e(B, dm[2].out_features)
             self.film, self.dfilm = e(B, 2 * self.feat), e(B, 2 * self.feat)
@@ -422,6 +427,13 @@ class TrainStep:
                 n += 1
         return n
 
+    def _select(self, slot: int):
+        """Make input slot `slot` the one the next _enqueue() / run() reads."""
+        self.cur = slot
+        self.x, self.y, self.demo = self.xs[slot], self.ys[slot], self.demos[slot]
+        if not self.bf16:
+            self.acts[0] = self.x                      # fp32 mode convolves the input buffer directly
+
     def _enqueue(self):
         main = torch.cuda.current_stream(self.dev)
         st = main.cuda_stream
@@ -550,7 +562,6 @@ class TrainStep:
             return
         # warm-up outside capture would advance the optimizer; capture directly instead
         torch.cuda.synchronize(self.dev)
-        g = torch.cuda.CUDAGraph()
         import os
         # programmatic dependent launch of the conv / BN-forward chain measured slower in the step (460 vs 449 us:
         # early-scheduled dependents take SM slots from the weight-gradient branch), so it is opt-in
@@ -561,12 +572,20 @@ class TrainStep:
         # order.  Equal priorities by default.
         prio = os.environ.get("ECGB200_MAIN_PRIORITY", "0")
         self.capture_stream = torch.cuda.Stream(device=self.dev, priority=int(prio)) if self.bf16 else None
+        keep = self.cur
+        graphs = []
         try:
-            with torch.cuda.graph(g, stream=self.capture_stream):
-                self._enqueue()
+            for slot in (0, 1):                      # one graph per input slot (same kernels, other input pointers)
+                self._select(slot)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self.capture_stream):
+                    self._enqueue()
+                graphs.append(g)
         finally:
             lib.ecgb200_set_pdl(old)
-        self.graph = g
+            self._select(keep)
+        self.graphs = graphs
+        self.graph = graphs[0]
 
     def profile_kernels(self, iters: int = 5):
         """Per-C-ABI-call device time (ms, mean over `iters` un-graphed passes, CUDA events on the
@@ -627,21 +646,28 @@ class TrainStep:
             out.append((name, e0.elapsed_time(e1) / (2 * iters)))
         return out
 
-    def load_batch(self, x, y, demo=None):
-        """Copy a batch (host pinned or device) into the static input buffers (async)."""
+    def load_batch(self, x, y, demo=None, slot=None):
+        """Copy a batch (pinned host or device tensors) into an input slot (async on the current stream).
+        slot=None: the idle slot, which then becomes the one run() uses; an explicit slot (0/1) is only filled
+        (pipelined use: fill slot s on a copy stream while the graph of slot 1-s runs, then run(slot=s))."""
         if tuple(x.shape) != tuple(self.x.shape) or tuple(y.shape) != tuple(self.y.shape):
             raise EcgB200Error(f"TrainStep was built for x{tuple(self.x.shape)} y{tuple(self.y.shape)}, "
                                f"got x{tuple(x.shape)} y{tuple(y.shape)}")
-        self.x.copy_(x, non_blocking=True)
-        self.y.copy_(y, non_blocking=True)
+        s = (self.cur ^ 1) if slot is None else int(slot)
+        self.xs[s].copy_(x, non_blocking=True)
+        self.ys[s].copy_(y, non_blocking=True)
         if self.mm:
             if demo is None:
                 raise EcgB200Error("ECGMultimodal step needs x_demo")
-            self.demo.copy_(demo, non_blocking=True)
+            self.demos[s].copy_(demo, non_blocking=True)
+        if slot is None:
+            self._select(s)
 
-    def run(self):
-        """One optimizer step on whatever the static input buffers hold.  Returns the loss
+    def run(self, slot=None):
+        """One optimizer step on whatever input slot `slot` (default: the current one) holds.  Returns the loss
         buffer (device scalar, overwritten by the next step)."""
+        if slot is not None and int(slot) != self.cur:
+            self._select(int(slot))
         group = self.opt.param_groups[0]
         hyper, _ = self.opt.device_state(group, self.dev)
         if hyper.data_ptr() != self.hyper.data_ptr():          # lr / betas changed on the host
@@ -650,7 +676,7 @@ class TrainStep:
         if self.use_graph:
             if self.graph is None:
                 self.capture()
-            self.graph.replay()
+            self.graphs[self.cur].replay()
         else:
             self._refresh_views()
             self._enqueue()
