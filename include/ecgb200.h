@@ -185,6 +185,13 @@ int ecgb200_film_bwd_f32(const float* z, const float* film, const float* dzc, fl
 int ecgb200_bce_logits_f32(const float* logits, const float* target, float* loss,
                            float* dlogits, float* prob, int n, float gscale, void* stream);
 
+/* Evaluation epilogue on the device (src/training/loop.py:63, scripts/06_ecg_baseline_test.py:127,
+ * src/training/metrics.py:37): prob = sigmoid(logits), pred = prob >= threshold (on the fp32 probability, as the
+ * reference does), counts[c] += {tp, fp, fn, tn} (int32[C][4], caller zeroes it at the start of an epoch).
+ * target / prob / pred / counts may each be NULL.  logits, target, prob: (rows, C) fp32; pred: (rows, C) uint8. */
+int ecgb200_eval_counts_f32(const float* logits, const float* target, float* prob, unsigned char* pred, int* counts,
+                            int rows, int C, float threshold, void* stream);
+
 /* ------------------------------------------------------------------ AdamW --
  * torch.optim.AdamW.step (scripts/03_train_ecg_baseline.py:133, loop.py:34):
  *   p *= 1-lr*wd; m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
@@ -275,6 +282,13 @@ int ecgb200_row_mean_f32(const float* x, float* out, int rows, int L, void* stre
  * per-lead z-score (x-mean)/(std+1e-6), population std, over time
  * (src/datasets/ptbxl.py:122-127).  x, out (B, C, T). */
 int ecgb200_zscore_f32(const float* x, float* out, int rows, int T, void* stream);
+
+/* WFDB format-16 decode + transpose + per-lead z-score from the raw .dat frames (N2):
+ * out[b,l,t] = z-score over t of (dat[b,t,l] - baseline[l]) / gain[l]   (digital -32768 = NaN, as wfdb.rdsamp);
+ * replaces wfdb.rdsamp + np.asarray(float32) + .T + _normalize (src/datasets/ptbxl.py:25-29,36-50,122-127).
+ * dat (B,T,n_leads) int16 little-endian frames; normalize = 0 returns the physical signal.  n_leads <= 16. */
+int ecgb200_wfdb16_zscore_f32(const void* dat, const float* gain, const int* baseline, float* out, int B,
+                              int n_leads, int T, int normalize, void* stream);
 
 #ifdef __cplusplus
 }

@@ -36,9 +36,11 @@ _SIGS = {
     "ecgb200_film_fwd_f32": (_I, [_P, _P, _P, _I, _I, _P]),
     "ecgb200_film_bwd_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _P]),
     "ecgb200_bce_logits_f32": (_I, [_P, _P, _P, _P, _P, _I, _F, _P]),
+    "ecgb200_eval_counts_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _F, _P]),
     "ecgb200_adamw_f32": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ecgb200_gradcam_f32": (_I, [_P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P]),
     "ecgb200_zscore_f32": (_I, [_P, _P, _I, _I, _P]),
+    "ecgb200_wfdb16_zscore_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "ecgb200_row_mean_f32": (_I, [_P, _P, _I, _I, _P]),
     "ecgb200_pack_input_bf16": (_I, [_P, _P, _I, _I, _I, _P]),
     "ecgb200_unpack_act_bf16": (_I, [_P, _P, _I, _I, _I, _P]),

@@ -227,3 +227,51 @@ int g_ecg_pdl = 0;
 extern "C" int ecgb200_set_pdl(int on) { const int old = g_ecg_pdl; g_ecg_pdl = on ? 1 : 0; return old; }
 extern "C" int ecgb200_version(void) { return 100; }
 extern "C" int ecgb200_arch(void) { return 1000; }
+
+// ---------------------------------------------------------------- WFDB format-16 decode + per-lead z-score (N2)
+// PTB-XL records are WFDB format 16: little-endian int16, sample-interleaved (one 2*n_leads-byte frame per time
+// step).  The reference reads them with wfdb.rdsamp (float64 physical = (digital - baseline) / gain, -32768 = NaN),
+// casts to float32, transposes to [leads, T] and z-scores each lead (src/datasets/ptbxl.py:25-29,122-127).  This
+// kernel does all of it on the device from the raw bytes: one block per record, thread t walks frames t, t+256, ...
+constexpr int WF_MAXL = 16;
+__global__ void __launch_bounds__(256)
+wfdb16_zscore_kernel(const short* __restrict__ dat, const float* __restrict__ gain, const int* __restrict__ baseline,
+                     float* __restrict__ out, int n_leads, int T, int normalize) {
+    __shared__ double sh[33];
+    __shared__ float mean_s[WF_MAXL], inv_s[WF_MAXL];
+    const short* rec = dat + (size_t)blockIdx.x * T * n_leads;
+    float* orec = out + (size_t)blockIdx.x * n_leads * T;
+    double g[WF_MAXL];
+    int bl[WF_MAXL];
+    for (int l = 0; l < n_leads; ++l) { g[l] = (double)gain[l]; bl[l] = baseline[l]; }
+    auto phys = [&](int t, int l) -> float {
+        const int d = (int)rec[(size_t)t * n_leads + l];
+        return d == -32768 ? __int_as_float(0x7fc00000) : (float)((double)(d - bl[l]) / g[l]);
+    };
+    if (normalize) {
+        for (int l = 0; l < n_leads; ++l) {
+            double s = 0.0;
+            for (int t = threadIdx.x; t < T; t += blockDim.x) s += (double)phys(t, l);
+            const double mean = block_sum_d(s, sh) / (double)T;
+            double m2 = 0.0;
+            for (int t = threadIdx.x; t < T; t += blockDim.x) { const double d = (double)phys(t, l) - mean; m2 += d * d; }
+            const double var = block_sum_d(m2, sh) / (double)T;
+            if (threadIdx.x == 0) { mean_s[l] = (float)mean; inv_s[l] = 1.0f / ((float)sqrt(var) + 1e-6f); }
+        }
+        __syncthreads();
+    }
+    for (int l = 0; l < n_leads; ++l) {
+        const float m = normalize ? mean_s[l] : 0.f, inv = normalize ? inv_s[l] : 1.f;
+        for (int t = threadIdx.x; t < T; t += blockDim.x) orec[(size_t)l * T + t] = (phys(t, l) - m) * inv;
+    }
+}
+
+// dat: (B, T, n_leads) int16 frames as stored in the .dat file; gain (ADC units per physical unit) and baseline per
+// lead from the .hea header; out: (B, n_leads, T) fp32 = the tensor the reference's Dataset returns.
+extern "C" int ecgb200_wfdb16_zscore_f32(const void* dat, const float* gain, const int* baseline, float* out, int B,
+                                         int n_leads, int T, int normalize, void* stream) {
+    if (!dat || !gain || !baseline || !out || B <= 0 || T <= 0) return ECGB200_EINVAL;
+    if (n_leads <= 0 || n_leads > WF_MAXL) return ECGB200_EUNSUPPORTED;
+    wfdb16_zscore_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const short*)dat, gain, baseline, out, n_leads, T, normalize);
+    return ecg_launch_status();
+}

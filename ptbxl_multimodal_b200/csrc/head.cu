@@ -221,6 +221,53 @@ extern "C" int ecgb200_bce_logits_f32(const float* logits, const float* target, 
     return ecg_launch_status();
 }
 
+// ------------------------------------------------------------------ evaluation epilogue
+// prob = sigmoid(logit) (loop.py:63), pred = prob >= threshold computed on the fp32 probability exactly as the
+// reference does in numpy (scripts/06:127, metrics.py:37), and per-label confusion counts accumulated on the
+// device: counts[c] = {tp, fp, fn, tn} (int32, integer atomics => deterministic), so that an evaluation epoch
+// needs no per-batch host synchronisation for its thresholded metrics.
+__global__ void __launch_bounds__(256)
+eval_counts_kernel(const float* __restrict__ logits, const float* __restrict__ target, float* __restrict__ prob,
+                   unsigned char* __restrict__ pred, int* __restrict__ counts, int rows, int C, float threshold) {
+    __shared__ int sh[8][4];
+    const int c = blockIdx.y;
+    int tp = 0, fp = 0, fn = 0, tn = 0;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
+        const float x = logits[(size_t)r * C + c];
+        const float p = 1.0f / (1.0f + expf(-x));
+        const bool yp = p >= threshold;
+        if (prob != nullptr) prob[(size_t)r * C + c] = p;
+        if (pred != nullptr) pred[(size_t)r * C + c] = yp ? 1 : 0;
+        if (target != nullptr && counts != nullptr) {
+            const bool yt = target[(size_t)r * C + c] > 0.5f;
+            tp += (yp && yt); fp += (yp && !yt); fn += (!yp && yt); tn += (!yp && !yt);
+        }
+    }
+    if (counts == nullptr || target == nullptr) return;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        tp += __shfl_xor_sync(0xffffffffu, tp, o); fp += __shfl_xor_sync(0xffffffffu, fp, o);
+        fn += __shfl_xor_sync(0xffffffffu, fn, o); tn += __shfl_xor_sync(0xffffffffu, tn, o);
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { sh[w][0] = tp; sh[w][1] = fp; sh[w][2] = fn; sh[w][3] = tn; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        int t = 0;
+        for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
+        if (t) atomicAdd(counts + c * 4 + threadIdx.x, t);
+    }
+}
+
+extern "C" int ecgb200_eval_counts_f32(const float* logits, const float* target, float* prob, unsigned char* pred,
+                                       int* counts, int rows, int C, float threshold, void* stream) {
+    if (!logits || rows <= 0 || C <= 0 || C > 65535) return ECGB200_EINVAL;
+    int bx = ecg_cdiv(rows, 256);
+    if (bx > 64) bx = 64;
+    eval_counts_kernel<<<dim3(bx, C), 256, 0, (cudaStream_t)stream>>>(logits, target, prob, pred, counts, rows, C, threshold);
+    return ecg_launch_status();
+}
+
 // ------------------------------------------------------------------ AdamW (multi-tensor, one launch)
 constexpr int ADAM_MAXT = 64;
 struct AdamTensors {

@@ -252,6 +252,22 @@ def sigmoid(logits: torch.Tensor) -> torch.Tensor:
     return prob
 
 
+def eval_counts(logits: torch.Tensor, target: Optional[torch.Tensor] = None, counts: Optional[torch.Tensor] = None,
+                threshold: float = 0.5):
+    """Device-side evaluation epilogue: returns (prob fp32, pred uint8) and, when `target` and `counts`
+    (int32 [C,4] = tp, fp, fn, tn) are given, accumulates the confusion counts with no host synchronisation."""
+    lg = _need_f32_cuda(logits, "logits")
+    rows, c = lg.shape
+    prob = torch.empty_like(lg)
+    pred = torch.empty(rows, c, dtype=torch.uint8, device=lg.device)
+    tg = _need_f32_cuda(target, "target") if target is not None else None
+    if counts is not None and (counts.dtype != torch.int32 or tuple(counts.shape) != (c, 4) or not counts.is_cuda):
+        raise EcgB200Error("counts must be a CUDA int32 tensor of shape (C, 4)")
+    check(lib.ecgb200_eval_counts_f32(ptr(lg), ptr(tg), ptr(prob), ptr(pred), ptr(counts), rows, c, float(threshold),
+                                      stream()), "eval_counts")
+    return prob, pred
+
+
 def linear(x, w, b=None, act: int = 0):
     return LinearFn.apply(x, w, b, act)
 

@@ -8,7 +8,7 @@ import numpy as np
 import torch
 
 from . import functional as Fn
-from .metrics import compute_metrics
+from .metrics import compute_metrics, f1_macro_from_counts
 
 
 def _logits(out):
@@ -34,6 +34,7 @@ def eval_one_epoch(model, loader, device) -> Dict[str, float]:
     model.eval()
     all_targets, all_probs = [], []
     total = torch.zeros((), dtype=torch.float64, device=device)
+    counts = None
     with torch.no_grad():
         for x, y in loader:
             x = x.to(device, non_blocking=True)
@@ -41,10 +42,15 @@ def eval_one_epoch(model, loader, device) -> Dict[str, float]:
             logits = _logits(model(x))
             loss = Fn.binary_cross_entropy_with_logits(logits, y)
             total += loss.double() * x.size(0)
+            if counts is None:
+                counts = torch.zeros(logits.shape[1], 4, dtype=torch.int32, device=logits.device)
+            prob, _ = Fn.eval_counts(logits, y, counts, threshold=0.5)      # sigmoid + threshold + confusion counts
             all_targets.append(y)
-            all_probs.append(Fn.sigmoid(logits))
+            all_probs.append(prob)
     y_true = torch.cat(all_targets).cpu().numpy()
     y_prob = torch.cat(all_probs).cpu().numpy()
     metrics = compute_metrics(y_true, y_prob, threshold=0.5)
+    # thresholded metric from the device-side counts (no per-batch sync); identical to sklearn's value above
+    metrics["f1_macro"] = f1_macro_from_counts(counts.cpu().numpy())
     metrics["bce_loss"] = float(total.item()) / len(loader.dataset)
     return metrics

@@ -469,3 +469,27 @@ def test_train_and_eval_loops_match_reference_loop_semantics():
     losses = [float(O.train_step(sd, a, c, st, demo=b_)["loss"]) for a, b_, c in loader]
     assert abs(got - sum(losses) / 2) < 1e-4 * abs(sum(losses) / 2)      # mean of batch means, loop_demo.py:38-43
     assert "bce_loss" in P.eval_one_epoch_demo(model, loader, DEV)
+
+
+def test_eval_counts_match_sklearn():
+    """Device-side evaluation epilogue (N3): sigmoid + threshold + confusion counts == numpy/sklearn on the same
+    logits, including exact-threshold ties (prob >= 0.5 at logit 0) and an all-negative label."""
+    from sklearn.metrics import f1_score
+    from ptbxl_multimodal_b200.metrics import f1_macro_from_counts
+    g = torch.Generator().manual_seed(9)
+    logits = torch.randn(1000, 5, generator=g) * 2
+    logits[::7, 2] = 0.0                                   # sigmoid(0) = 0.5 exactly -> predicted positive
+    y = (torch.rand(1000, 5, generator=g) < torch.tensor([0.25, 0.24, 0.12, 0.23, 0.0])).float()
+    counts = torch.zeros(5, 4, dtype=torch.int32, device=DEV)
+    prob, pred = Fn.eval_counts(logits[:600].to(DEV), y[:600].to(DEV), counts)
+    prob2, pred2 = Fn.eval_counts(logits[600:].to(DEV), y[600:].to(DEV), counts)      # accumulates across batches
+    p = torch.cat([prob, prob2]).cpu()
+    ref_p = torch.sigmoid(logits)
+    assert float((p - ref_p).abs().max()) < 2e-7
+    y_pred = (p.numpy() >= 0.5).astype(int)
+    assert (torch.cat([pred, pred2]).cpu().numpy() == y_pred).all()
+    yt = y.numpy().astype(int)
+    c = counts.cpu().numpy()
+    assert (c[:, 0] == (y_pred & yt).sum(0)).all() and (c[:, 1] == (y_pred & (1 - yt)).sum(0)).all()
+    assert (c[:, 2] == ((1 - y_pred) & yt).sum(0)).all() and (c.sum(1) == 1000).all()
+    assert abs(f1_macro_from_counts(c) - f1_score(yt, y_pred, average="macro", zero_division=0)) < 1e-12
