@@ -538,8 +538,10 @@ static int conv2_cfg(int B, int Ci, int Co, int L, Conv2Cfg* P, size_t* smem_out
         if (need > budget) continue;
         // streamed weights: fewer, larger groups halve the L2->SM weight traffic, so prefer the larger R
         if (span < bestSpan || (!resident && span == bestSpan && R > bestR)) { bestSpan = span; bestR = R; }
-        // largest R that fits; small-channel layers also need R * (kch/16) >= 4 MMAs per issue batch
-        if (!resident || R * (P->kch / 16) <= 4) break;
+        // streamed weights: keep the largest R unless a smaller one shortens the busiest CTA (small batches: with
+        // fewer groups than SMs, one tile per CTA halves the serial chain); small-channel layers also need
+        // R * (kch/16) >= 4 MMAs per issue batch
+        if (resident ? R * (P->kch / 16) <= 4 : ng >= nsm) break;
     }
     if (const char* e = getenv("ECGB200_CONV_R")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) bestR = v; }
     if (bestR * Co > 512) bestR = 512 / Co;
