@@ -229,6 +229,22 @@ int ecgb200_head_loss_parts(int B);
 int ecgb200_head_wgrad_f32(const float* gap, const float* z, const float* dz, const float* dlogits,
                            const float* loss_part, float* dwp, float* dbp, float* dwh, float* dbh, float* loss,
                            int B, int Cin, int F, int NL, void* stream);
+/* ECGMultimodal head (FiLM, ecg_multimodal.py:88-99), forward + loss + input gradients in one launch:
+ *   h1 = relu(W0 d + b0); h2 = relu(W2 h1 + b2); film = Wf h2 + bf; z = Wp gap + bp;
+ *   zc = (1 + tanh film[:F]) z + film[F:]; logits = Wh zc + bh; BCE; and the chain rule back to dgap, dh1.
+ * Saves for the weight gradients: z, h1, h2, film, zc, dlogits, dz, dfilm, dh2, dh1.  D <= 8, H <= 64, F, Cin <= 256. */
+int ecgb200_mm_head_fwd_bwd_f32(const float* gap, const float* demo, const float* wpT, const float* wp,
+                                const float* bp, const float* w0, const float* b0, const float* w2, const float* b2,
+                                const float* wf, const float* bf, const float* wh, const float* bh,
+                                const float* target, float* z, float* h1, float* h2, float* film, float* zc,
+                                float* logits, float* dlogits, float* dz, float* dfilm, float* dh2, float* dh1,
+                                float* dgap, float* loss_part, int B, int Cin, int F, int D, int H, int NL,
+                                float gscale, void* stream);
+/* Weight / bias gradients of up to 6 small Linear layers in one launch: dW_p = A_p^T X_p (N_p x K_p), db_p = colsum
+ * (A_p) [db[p] may be NULL]; a/x/dw/db/n/k are HOST arrays.  Also loss = sum(loss_part)/(B*NL) unless NULL. */
+int ecgb200_head_wgrad_multi_f32(int nprob, const float* const* a, const float* const* x, float* const* dw,
+                                 float* const* db, const int* n, const int* k, const float* loss_part, float* loss,
+                                 int B, int NL, void* stream);
 /* AdamW (as ecgb200_adamw_f32) over one flat, 16-byte aligned array; t = *step_now, the 1-based step index
  * already incremented by ecgb200_step_prep_bf16. */
 int ecgb200_adamw_flat_f32(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper,

@@ -60,6 +60,8 @@ _SIGS = {
     "ecgb200_step_prep_bf16": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
     "ecgb200_head_fwd_bwd_f32": (_I, [_P] * 13 + [_I, _I, _I, _I, _F, _P]),
     "ecgb200_head_loss_parts": (_I, [_I]),
+    "ecgb200_mm_head_fwd_bwd_f32": (_I, [_P] * 27 + [_I, _I, _I, _I, _I, _I, _F, _P]),
+    "ecgb200_head_wgrad_multi_f32": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "ecgb200_head_wgrad_f32": (_I, [_P] * 10 + [_I, _I, _I, _I, _P]),
     "ecgb200_dp_adamw_fused_f32": (_I, [_P, _P, _P, _P, _P, C.c_int64, _I, _I, _P, _P, _P]),
     "ecgb200_dp_flag_words": (_I, [_I]),

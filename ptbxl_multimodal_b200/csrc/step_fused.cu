@@ -395,3 +395,325 @@ extern "C" int ecgb200_adamw_flat_f32(float* p, const float* g, float* m, float*
     adamw_flat_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, hyper, step_now);
     return ecg_launch_status();
 }
+
+// ------------------------------------------------------------------ fused head of the multimodal (FiLM) model
+// Per-window chain of ECGMultimodal.forward (src/models/ecg_multimodal.py:88-99) + BCE + all input gradients:
+//   h1 = relu(W0 d + b0); h2 = relu(W2 h1 + b2); film = Wf h2 + bf = [gamma_raw, beta];
+//   z = Wp gap + bp; zc = (1 + tanh gamma_raw) * z + beta; logits = Wh zc + bh; BCE
+//   dzc = Wh^T dl; dz = dzc (1 + tanh g); dfilm = [dzc z (1 - tanh^2 g), dzc];
+//   dh2 = (Wf^T dfilm) [h2 > 0]; dh1 = (W2^T dh2) [h1 > 0]; dgap = Wp^T dz
+// One CTA = HB windows; weight gradients are left to ecgb200_head_wgrad_multi_f32.
+constexpr int MMH = 64;         // demo-encoder hidden width (<=)
+constexpr int MMD = 8;          // demographic features (<=)
+
+__global__ void __launch_bounds__(HT)
+mm_head_fwd_bwd_kernel(const float* __restrict__ gap, const float* __restrict__ demo, const float* __restrict__ wpT,
+                       const float* __restrict__ wp, const float* __restrict__ bp, const float* __restrict__ w0,
+                       const float* __restrict__ b0v, const float* __restrict__ w2, const float* __restrict__ b2v,
+                       const float* __restrict__ wf, const float* __restrict__ bfv, const float* __restrict__ wh,
+                       const float* __restrict__ bh, const float* __restrict__ target, float* __restrict__ z,
+                       float* __restrict__ h1g, float* __restrict__ h2g, float* __restrict__ filmg,
+                       float* __restrict__ zcg, float* __restrict__ logits, float* __restrict__ dlogits,
+                       float* __restrict__ dz, float* __restrict__ dfilmg, float* __restrict__ dh2g,
+                       float* __restrict__ dh1g, float* __restrict__ dgap, float* __restrict__ loss_part, int B,
+                       int Cin, int F, int D, int H, int NL, float gscale) {
+    __shared__ float4 gs4[HMAXF], dzs4[HMAXF];
+    __shared__ float zs[HB][HMAXF], zcs[HB][HMAXF];
+    __shared__ float films[HB][2 * HMAXF];            // film, overwritten in place by dfilm in the backward half
+    __shared__ float red[4][HB][HMAXF];
+    __shared__ float ds[HB][MMD], h1s[HB][MMH], h2s[HB][MMH], dh2s[HB][MMH];
+    __shared__ float dls[HB][HMAXL];
+    __shared__ float lsum[HB * HMAXL];
+    const int b0 = blockIdx.x * HB, nb = min(HB, B - b0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int o = tid & 255;
+    for (int i = tid; i < HB * Cin; i += HT) {
+        const int s = i / Cin, c = i - s * Cin;
+        reinterpret_cast<float*>(gs4)[c * HB + s] = s < nb ? __ldg(gap + (size_t)(b0 + s) * Cin + c) : 0.f;
+    }
+    if (tid < HB * D) {
+        const int s = tid / D, i = tid - s * D;
+        ds[s][i] = s < nb ? __ldg(demo + (size_t)(b0 + s) * D + i) : 0.f;
+    }
+    __syncthreads();
+    // ---- demo encoder
+    if (tid < HB * H) {
+        const int s = tid / H, j = tid - s * H;
+        float a = __ldg(b0v + j);
+        for (int i = 0; i < D; ++i) a = fmaf(__ldg(w0 + (size_t)j * D + i), ds[s][i], a);
+        a = fmaxf(a, 0.f);
+        h1s[s][j] = a;
+        if (s < nb) h1g[(size_t)(b0 + s) * H + j] = a;
+    }
+    __syncthreads();
+    // h2 and film: one WARP per output row, lanes across the 64-wide reduction (a thread-per-row walk of the
+    // (out, in) weight matrix touches 32 different lines per load instruction: measured 104 us for this kernel)
+    for (int j = warp; j < H; j += HT / 32) {
+        float a[HB] = {0.f, 0.f, 0.f, 0.f};
+        for (int i = lane; i < H; i += 32) {
+            const float w = __ldg(w2 + (size_t)j * H + i);
+#pragma unroll
+            for (int s = 0; s < HB; ++s) a[s] = fmaf(w, h1s[s][i], a[s]);
+        }
+#pragma unroll
+        for (int s = 0; s < HB; ++s) a[s] = warp_sum(a[s]);
+        if (lane < HB) {
+            float v = 0.f;
+#pragma unroll
+            for (int s = 0; s < HB; ++s) if (s == lane) v = a[s];
+            v = fmaxf(v + __ldg(b2v + j), 0.f);
+            h2s[lane][j] = v;
+            if (lane < nb) h2g[(size_t)(b0 + lane) * H + j] = v;
+        }
+    }
+    __syncthreads();
+    // ---- film = Wf h2 + bf   (four output rows per warp iteration: their weight loads are in flight together)
+    for (int n0 = warp * 4; n0 < 2 * F; n0 += (HT / 32) * 4) {
+        float a[4][HB];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int s = 0; s < HB; ++s) a[u][s] = 0.f;
+        for (int k = lane; k < H; k += 32) {
+            float w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) w[u] = (n0 + u < 2 * F) ? __ldg(wf + (size_t)(n0 + u) * H + k) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int s = 0; s < HB; ++s) a[u][s] = fmaf(w[u], h2s[s][k], a[u][s]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int s = 0; s < HB; ++s) a[u][s] = warp_sum(a[u][s]);
+        if (lane < 4 * HB) {
+            const int u = lane >> 2, sl = lane & 3;
+            float v = 0.f;
+#pragma unroll
+            for (int uu = 0; uu < 4; ++uu)
+#pragma unroll
+                for (int s = 0; s < HB; ++s) if (uu == u && s == sl) v = a[uu][s];
+            const int n = n0 + u;
+            if (n < 2 * F) {
+                v += __ldg(bfv + n);
+                films[sl][n] = v;
+                if (sl < nb) filmg[(size_t)(b0 + sl) * 2 * F + n] = v;
+            }
+        }
+    }
+    // ---- z = Wp gap + bp
+    float acc[HB];
+    head_gemv4(gs4, wpT, Cin, F, red, acc);          // (contains a __syncthreads: films is complete after it)
+    if (tid < 256 && o < F) {
+        const float bo = __ldg(bp + o);
+#pragma unroll
+        for (int s = 0; s < HB; ++s) {
+            const float zv = acc[s] + bo;
+            const float th = tanhf(films[s][o]);
+            const float zc = fmaf(1.0f + th, zv, films[s][F + o]);
+            zs[s][o] = zv;
+            zcs[s][o] = zc;
+            if (s < nb) { z[(size_t)(b0 + s) * F + o] = zv; zcg[(size_t)(b0 + s) * F + o] = zc; }
+        }
+    }
+    __syncthreads();
+    // ---- logits, loss, dlogits
+    const float inv_n = 1.0f / ((float)B * (float)NL);
+    for (int idx = warp; idx < HB * NL; idx += HT / 32) {
+        const int s = idx / NL, c = idx - s * NL;
+        float a = 0.f;
+        for (int k = lane; k < F; k += 32) a = fmaf(zcs[s][k], __ldg(wh + (size_t)c * F + k), a);
+        a = warp_sum(a);
+        if (lane == 0) {
+            float term = 0.f, dl = 0.f;
+            if (s < nb) {
+                const float x = a + __ldg(bh + c);
+                const float y = __ldg(target + (size_t)(b0 + s) * NL + c);
+                const float p = 1.0f / (1.0f + expf(-x));
+                term = fmaxf(x, 0.f) - x * y + log1pf(expf(-fabsf(x)));
+                dl = (p - y) * inv_n * gscale;
+                logits[(size_t)(b0 + s) * NL + c] = x;
+                dlogits[(size_t)(b0 + s) * NL + c] = dl;
+            }
+            dls[s][c] = dl;
+            lsum[idx] = term;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float t = 0.f;
+        for (int i = 0; i < HB * NL; ++i) t += lsum[i];
+        loss_part[blockIdx.x] = t;
+    }
+    // ---- dzc -> dz, dfilm
+    if (tid < 256 && o < F) {
+#pragma unroll
+        for (int s = 0; s < HB; ++s) acc[s] = 0.f;
+        for (int c = 0; c < NL; ++c) {
+            const float w = __ldg(wh + (size_t)c * F + o);
+#pragma unroll
+            for (int s = 0; s < HB; ++s) acc[s] = fmaf(dls[s][c], w, acc[s]);
+        }
+        float dzv[HB];
+#pragma unroll
+        for (int s = 0; s < HB; ++s) {
+            const float th = tanhf(films[s][o]);
+            dzv[s] = acc[s] * (1.0f + th);
+            const float dg = acc[s] * zs[s][o] * (1.0f - th * th);
+            films[s][o] = dg;                           // (s, o) and (s, F + o) belong to this thread only
+            films[s][F + o] = acc[s];
+            if (s < nb) {
+                dz[(size_t)(b0 + s) * F + o] = dzv[s];
+                dfilmg[(size_t)(b0 + s) * 2 * F + o] = dg;
+                dfilmg[(size_t)(b0 + s) * 2 * F + F + o] = acc[s];
+            }
+        }
+        dzs4[o] = make_float4(dzv[0], dzv[1], dzv[2], dzv[3]);
+    }
+    __syncthreads();
+    // ---- dh2 = (Wf^T dfilm) [h2 > 0]: 4 K-quarters x (HB x H) outputs, combined through `red`
+    {
+        const int q = tid >> 8, r = tid & 255;          // r -> (s, j)
+        const int s = r / H, j = r - s * H;
+        float a = 0.f;
+        if (r < HB * H) {
+            const int n0 = q * (2 * F / 4), n1 = n0 + 2 * F / 4;
+#pragma unroll 16
+            for (int n = n0; n < n1; ++n) a = fmaf(films[s][n], __ldg(wf + (size_t)n * H + j), a);
+        }
+        red[q][0][r] = a;
+        __syncthreads();
+        if (q == 0 && r < HB * H) {
+            float t = red[0][0][r] + red[1][0][r] + red[2][0][r] + red[3][0][r];
+            t = h2s[s][j] > 0.f ? t : 0.f;
+            dh2s[s][j] = t;
+            if (s < nb) dh2g[(size_t)(b0 + s) * H + j] = t;
+        }
+    }
+    __syncthreads();
+    // ---- dh1 = (W2^T dh2) [h1 > 0]
+    if (tid < HB * H) {
+        const int s = tid / H, i = tid - s * H;
+        float a = 0.f;
+#pragma unroll 8
+        for (int j = 0; j < H; ++j) a = fmaf(dh2s[s][j], __ldg(w2 + (size_t)j * H + i), a);
+        a = h1s[s][i] > 0.f ? a : 0.f;
+        if (s < nb) dh1g[(size_t)(b0 + s) * H + i] = a;
+    }
+    // ---- dgap = Wp^T dz
+    head_gemv4(dzs4, wp, F, Cin, red, acc);
+    if (tid < 256 && o < Cin) {
+#pragma unroll
+        for (int s = 0; s < HB; ++s)
+            if (s < nb) dgap[(size_t)(b0 + s) * Cin + o] = acc[s];
+    }
+}
+
+extern "C" int ecgb200_mm_head_fwd_bwd_f32(const float* gap, const float* demo, const float* wpT, const float* wp,
+                                           const float* bp, const float* w0, const float* b0, const float* w2,
+                                           const float* b2, const float* wf, const float* bf, const float* wh,
+                                           const float* bh, const float* target, float* z, float* h1, float* h2,
+                                           float* film, float* zc, float* logits, float* dlogits, float* dz,
+                                           float* dfilm, float* dh2, float* dh1, float* dgap, float* loss_part, int B,
+                                           int Cin, int F, int D, int H, int NL, float gscale, void* stream) {
+    if (!gap || !demo || !wpT || !wp || !bp || !w0 || !b0 || !w2 || !b2 || !wf || !bf || !wh || !bh || !target || !z ||
+        !h1 || !h2 || !film || !zc || !logits || !dlogits || !dz || !dfilm || !dh2 || !dh1 || !dgap || !loss_part || B <= 0)
+        return ECGB200_EINVAL;
+    if (Cin <= 0 || Cin > HMAXF || F <= 0 || F > HMAXF || NL <= 0 || NL > HMAXL || D <= 0 || D > MMD || H <= 0 ||
+        H > MMH || HB * H > 256)
+        return ECGB200_EUNSUPPORTED;
+    mm_head_fwd_bwd_kernel<<<(B + HB - 1) / HB, HT, 0, (cudaStream_t)stream>>>(
+        gap, demo, wpT, wp, bp, w0, b0, w2, b2, wf, bf, wh, bh, target, z, h1, h2, film, zc, logits, dlogits, dz, dfilm,
+        dh2, dh1, dgap, loss_part, B, Cin, F, D, H, NL, gscale);
+    return ecg_launch_status();
+}
+
+// ------------------------------------------------------------------ weight gradients of several small Linear layers
+// dW_p[n][k] = sum_s A_p[s][n] * X_p[s][k],  db_p[n] = sum_s A_p[s][n]   for up to 6 problems in ONE launch
+// (32x32 output tiles over K = B in a fixed order), plus loss = sum(loss_part) / (B * NL).
+constexpr int HW_MAXP = 6;
+struct HeadWgradProblems {
+    const float* a[HW_MAXP];     // (B, N) upstream gradient
+    const float* x[HW_MAXP];     // (B, K) layer input
+    float* dw[HW_MAXP];          // (N, K)
+    float* db[HW_MAXP];          // (N) or NULL
+    int n[HW_MAXP], k[HW_MAXP], tile0[HW_MAXP + 1];
+    int nprob;
+};
+
+__global__ void __launch_bounds__(256)
+head_wgrad_multi_kernel(const __grid_constant__ HeadWgradProblems Q, const float* __restrict__ loss_part, int nparts,
+                        float* __restrict__ loss, int B, int NL) {
+    __shared__ float As[32][33], Bs[32][33];
+    const int tid = threadIdx.x;
+    if ((int)blockIdx.x == Q.tile0[Q.nprob]) {               // extra block: the scalar loss
+        if (tid == 0 && loss != nullptr) {
+            double t = 0.0;
+            for (int i = 0; i < nparts; ++i) t += (double)__ldg(loss_part + i);
+            *loss = (float)(t / ((double)B * (double)NL));
+        }
+        return;
+    }
+    int p = 0;
+    while (p + 1 < Q.nprob && (int)blockIdx.x >= Q.tile0[p + 1]) ++p;
+    const int N = Q.n[p], K = Q.k[p];
+    const int tiles_k = (K + 31) / 32;
+    const int t = (int)blockIdx.x - Q.tile0[p];
+    const int n0 = (t / tiles_k) * 32, k0 = (t % tiles_k) * 32;
+    const float* __restrict__ A = Q.a[p];
+    const float* __restrict__ X = Q.x[p];
+    const int tx = tid & 31, ty = tid >> 5;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float colsum = 0.f;
+    for (int s0 = 0; s0 < B; s0 += 32) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int s = s0 + ty + 8 * r;
+            As[ty + 8 * r][tx] = (s < B && n0 + tx < N) ? __ldg(A + (size_t)s * N + n0 + tx) : 0.f;
+            Bs[ty + 8 * r][tx] = (s < B && k0 + tx < K) ? __ldg(X + (size_t)s * K + k0 + tx) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 32; ++kk) {
+            const float bv = Bs[kk][tx];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[r] = fmaf(As[kk][ty + 8 * r], bv, acc[r]);
+        }
+        if (k0 == 0 && ty == 0)
+#pragma unroll
+            for (int kk = 0; kk < 32; ++kk) colsum += As[kk][tx];
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int n = n0 + ty + 8 * r, k = k0 + tx;
+        if (n < N && k < K) Q.dw[p][(size_t)n * K + k] = acc[r];
+    }
+    if (k0 == 0 && ty == 0 && n0 + tx < N && Q.db[p] != nullptr) Q.db[p][n0 + tx] = colsum;
+}
+
+// a / x / dw / db / n / k: HOST arrays of nprob <= 6 entries.  loss_part may be NULL (then loss is not written).
+extern "C" int ecgb200_head_wgrad_multi_f32(int nprob, const float* const* a, const float* const* x, float* const* dw,
+                                            float* const* db, const int* n, const int* k, const float* loss_part,
+                                            float* loss, int B, int NL, void* stream) {
+    if (nprob <= 0 || nprob > HW_MAXP || !a || !x || !dw || !db || !n || !k || B <= 0) return ECGB200_EINVAL;
+    HeadWgradProblems Q;
+    int tiles = 0;
+    for (int p = 0; p < HW_MAXP; ++p) {
+        if (p < nprob) {
+            if (!a[p] || !x[p] || !dw[p] || n[p] <= 0 || k[p] <= 0) return ECGB200_EINVAL;
+            Q.a[p] = a[p]; Q.x[p] = x[p]; Q.dw[p] = dw[p]; Q.db[p] = db[p]; Q.n[p] = n[p]; Q.k[p] = k[p];
+            Q.tile0[p] = tiles;
+            tiles += ((n[p] + 31) / 32) * ((k[p] + 31) / 32);
+        } else {
+            Q.a[p] = Q.x[p] = nullptr; Q.dw[p] = Q.db[p] = nullptr; Q.n[p] = Q.k[p] = 0; Q.tile0[p] = tiles;
+        }
+    }
+    Q.tile0[HW_MAXP] = tiles;
+    for (int p = nprob; p <= HW_MAXP; ++p) Q.tile0[p] = tiles;
+    Q.nprob = nprob;
+    const int extra = (loss_part != nullptr && loss != nullptr) ? 1 : 0;
+    head_wgrad_multi_kernel<<<tiles + extra, 256, 0, (cudaStream_t)stream>>>(Q, loss_part, (B + HB - 1) / HB, loss, B, NL);
+    return ecg_launch_status();
+}

@@ -318,7 +318,7 @@ class TrainStep:
             self._k("prep_w", lib.ecgb200_step_prep_bf16, None, None, 0, 0, 0, 3,
                     PV(*[Pp(k) for k in wkeys[1:]], None), PV(*[_p(w) for w in self.wt[1:]], None),
                     PV(*[_p(w) for w in self.wd[1:]], None), I4(*self.chan[2:5], 0), I4(*self.chan[1:4], 0),
-                    None if self.mm else Pp(pre + "proj.weight"), None if self.mm else _p(self.wpT),
+                    Pp(pre + "proj.weight"), _p(self.wpT),
                     self.feat, self.chan[4], None, self.side.cuda_stream)
             prep_done = torch.cuda.Event()
             prep_done.record(self.side)
@@ -461,6 +461,30 @@ class TrainStep:
                         _p(self.dlogits), _p(self.loss_part), Gp("proj.weight"), Gp("proj.bias"), Gp("head.weight"),
                         Gp("head.bias"), _p(self.loss), B, c4, F_, NL, self.side.cuda_stream)
             n += 2
+        elif self.bf16 and self.mm and self._mm_head_ok():
+            # fused FiLM head (demo encoder, film, head, BCE and the whole chain rule) + one launch for the five
+            # Linear layers' weight gradients on the side branch
+            d0, hn = self.demo.shape[1], self.h1.shape[1]
+            self._k("mm_head_fwd_bwd", lib.ecgb200_mm_head_fwd_bwd_f32, _p(self.gap), _p(self.demo), _p(self.wpT),
+                    Pp(pre + "proj.weight"), Pp(pre + "proj.bias"), Pp("demo_encoder.mlp.0.weight"),
+                    Pp("demo_encoder.mlp.0.bias"), Pp("demo_encoder.mlp.2.weight"), Pp("demo_encoder.mlp.2.bias"),
+                    Pp("film_gen.weight"), Pp("film_gen.bias"), Pp("head.weight"), Pp("head.bias"), _p(self.y),
+                    _p(self.z), _p(self.h1), _p(self.h2), _p(self.film), _p(self.zc), _p(self.logits), _p(self.dlogits),
+                    _p(self.dz), _p(self.dfilm), _p(self.dh2), _p(self.dh1), _p(self.dgap), _p(self.loss_part),
+                    B, c4, F_, d0, hn, NL, 1.0, st)
+            self._fork_side(main)
+            with torch.cuda.stream(self.side):
+                V5, I5 = C.c_void_p * 5, C.c_int * 5
+                self._k("head_wgrad", lib.ecgb200_head_wgrad_multi_f32, 5,
+                        V5(_p(self.dz), _p(self.dlogits), _p(self.dfilm), _p(self.dh2), _p(self.dh1)),
+                        V5(_p(self.gap), _p(self.zc), _p(self.h2), _p(self.h1), _p(self.demo)),
+                        V5(Gp(pre + "proj.weight"), Gp("head.weight"), Gp("film_gen.weight"),
+                           Gp("demo_encoder.mlp.2.weight"), Gp("demo_encoder.mlp.0.weight")),
+                        V5(Gp(pre + "proj.bias"), Gp("head.bias"), Gp("film_gen.bias"), Gp("demo_encoder.mlp.2.bias"),
+                           Gp("demo_encoder.mlp.0.bias")),
+                        I5(F_, NL, 2 * F_, hn, hn), I5(c4, F_, hn, hn, d0), _p(self.loss_part), _p(self.loss), B, NL,
+                        self.side.cuda_stream)
+            n += 2
         else:
             n += self._head_unfused(st, pre, Pp, Gp)
         # ---- backward: conv blocks 4..1
@@ -506,6 +530,13 @@ class TrainStep:
                     one(self.V.data_ptr()), num, self.hyper.data_ptr(), self.step_dev.data_ptr(), st)
             n += 2
         self.launches_per_step = n
+
+    def _mm_head_ok(self):
+        """Shapes the fused multimodal head kernel covers (the reference's defaults: demo 5 -> 64 -> 64, feat 256)."""
+        dm = self.model.demo_encoder.mlp
+        return (dm[0].out_features == dm[2].out_features == dm[2].in_features and dm[0].out_features <= 64
+                and dm[0].in_features <= 8 and self.feat <= 256 and self.chan[4] <= 256 and self.nl <= 8
+                and self.model.film_gen.in_features == dm[2].out_features)
 
     def _head_unfused(self, st, pre, Pp, Gp):
         """proj / (demo encoder, FiLM) / head / BCE and their backward as separate launches (fp32 engine and

@@ -7,12 +7,14 @@ import ptbxl_multimodal_b200 as P
 from ptbxl_multimodal_b200.step import TrainStep
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
+kind = sys.argv[3] if len(sys.argv) > 3 else 'cnn'
 ITERS = 10
 torch.manual_seed(42)
-m = P.ECGCNN(12, 256, 5).cuda().train()
+m = (P.ECGCNN(12, 256, 5) if kind == 'cnn' else P.ECGMultimodal()).cuda().train()
 o = P.FusedAdamW(m.parameters(), lr=1.5e-3, weight_decay=1e-4)
 e = TrainStep(m, o, B, T, precision='bf16', use_graph=False)
 e.x.normal_(); e.y.bernoulli_(0.3)
+if kind != 'cnn': e.demo.uniform_()
 for _ in range(3): e.run()
 torch.cuda.synchronize()
 # record the call list of one step

@@ -16,5 +16,5 @@ for (kind, nl, B, T) in [('cnn', 5, 128, 1000), ('cnn', 5, 64, 1000), ('cnn', 1,
     e0.record()
     for _ in range(100): e.run()
     e1.record(); torch.cuda.synchronize()
-    print(f'{kind} nl={nl} B={B} T={T}: {e0.elapsed_time(e1) * 10:.1f} us/step', flush=True)
+    print(f'{kind} nl={nl} B={B} T={T}: {e0.elapsed_time(e1) * 10:.1f} us/step, {e.launches_per_step} launches', flush=True)
     del e, m, o

@@ -323,3 +323,58 @@ def test_bn_backward_fused_equals_two_kernel_path(B, C, L, use_gap):
     assert rel_inf(g1, g0) < 1e-5 and rel_inf(b1, b0) < 1e-5
     assert rel_inf(dy1, dy0) < 8e-3                      # same math, different partial-sum grouping: bf16 ties
     assert float((s1 - s0).abs().max()) <= 1e-3 * float(s0.abs().max()) + 1e-2
+
+
+@pytest.mark.parametrize("B", [256, 7])
+def test_fused_multimodal_head(B):
+    """mm_head_fwd_bwd + head_wgrad_multi == the FiLM head of ECGMultimodal.forward (ecg_multimodal.py:88-99) + BCE and
+    its autograd, for every parameter and for gap."""
+    Cin = F_ = 256; D, H, NL = 5, 64, 5
+    g = torch.Generator().manual_seed(4)
+    r = lambda *s: (torch.rand(*s, generator=g) - 0.5)        # noqa: E731
+    gap, demo = torch.rand(B, Cin, generator=g), torch.rand(B, D, generator=g)
+    prm = dict(wp=r(F_, Cin) / 8, bp=r(F_) / 8, w0=r(H, D), b0=r(H), w2=r(H, H) / 4, b2=r(H) / 4, wf=r(2 * F_, H) / 4,
+               bf=r(2 * F_) / 4, wh=r(NL, F_) / 8, bh=r(NL) / 8)
+    y = (torch.rand(B, NL, generator=g) < 0.3).float()
+    L = {k: v.clone().requires_grad_(True) for k, v in prm.items()}
+    gl = gap.clone().requires_grad_(True)
+    h1 = torch.relu(F.linear(demo, L["w0"], L["b0"]))
+    h2 = torch.relu(F.linear(h1, L["w2"], L["b2"]))
+    film = F.linear(h2, L["wf"], L["bf"])
+    z = F.linear(gl, L["wp"], L["bp"])
+    gam, bet = torch.chunk(film, 2, dim=-1)
+    zc = (1.0 + torch.tanh(gam)) * z + bet
+    logits = F.linear(zc, L["wh"], L["bh"])
+    loss = F.binary_cross_entropy_with_logits(logits, y)
+    loss.backward()
+    d = lambda t: t.to(DEV).contiguous()          # noqa: E731
+    G = {k: d(v) for k, v in prm.items()}
+    gap_g, demo_g, y_g = d(gap), d(demo), d(y)
+    wpT = G["wp"].t().contiguous()
+    e = lambda *s: torch.full(s, float("nan"), device=DEV)       # noqa: E731
+    bz, bh1, bh2, bfilm, bzc = e(B, F_), e(B, H), e(B, H), e(B, 2 * F_), e(B, F_)
+    lg, dl, dz, dfilm, dh2, dh1, dgap = e(B, NL), e(B, NL), e(B, F_), e(B, 2 * F_), e(B, H), e(B, H), e(B, Cin)
+    lp = e(lib.ecgb200_head_loss_parts(B))
+    check(lib.ecgb200_mm_head_fwd_bwd_f32(ptr(gap_g), ptr(demo_g), ptr(wpT), ptr(G["wp"]), ptr(G["bp"]), ptr(G["w0"]),
+                                          ptr(G["b0"]), ptr(G["w2"]), ptr(G["b2"]), ptr(G["wf"]), ptr(G["bf"]), ptr(G["wh"]),
+                                          ptr(G["bh"]), ptr(y_g), ptr(bz), ptr(bh1), ptr(bh2), ptr(bfilm), ptr(bzc), ptr(lg),
+                                          ptr(dl), ptr(dz), ptr(dfilm), ptr(dh2), ptr(dh1), ptr(dgap), ptr(lp), B, Cin, F_,
+                                          D, H, NL, 1.0, stream()), "mm_head")
+    import ctypes as C
+    V5, I5 = C.c_void_p * 5, C.c_int * 5
+    dw = [e(F_, Cin), e(NL, F_), e(2 * F_, H), e(H, H), e(H, D)]
+    db = [e(F_), e(NL), e(2 * F_), e(H), e(H)]
+    ls = e(1)
+    check(lib.ecgb200_head_wgrad_multi_f32(5, V5(ptr(dz), ptr(dl), ptr(dfilm), ptr(dh2), ptr(dh1)),
+                                           V5(ptr(gap_g), ptr(bzc), ptr(bh2), ptr(bh1), ptr(demo_g)),
+                                           V5(*[ptr(t) for t in dw]), V5(*[ptr(t) for t in db]),
+                                           I5(F_, NL, 2 * F_, H, H), I5(Cin, F_, H, H, D), ptr(lp), ptr(ls), B, NL,
+                                           stream()), "head_wgrad_multi")
+    torch.cuda.synchronize()
+    tol = 2e-5
+    assert rel_inf(lg, logits) < tol and rel_inf(bzc, zc) < tol and rel_inf(bfilm, film) < tol
+    assert abs(float(ls) - float(loss.detach())) < 1e-6 * max(1.0, abs(float(loss.detach())))
+    assert rel_inf(dgap, gl.grad) < tol
+    for (w, b), (kw, kb) in zip(zip(dw, db), (("wp", "bp"), ("wh", "bh"), ("wf", "bf"), ("w2", "b2"), ("w0", "b0"))):
+        assert rel_inf(w, L[kw].grad) < tol, kw
+        assert rel_inf(b, L[kb].grad) < tol, kb
