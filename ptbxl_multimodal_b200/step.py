@@ -313,15 +313,28 @@ class TrainStep:
         self._k("prep", lib.ecgb200_step_prep_bf16, _p(self.x), _p(self.acts[0]), B, self.chan[0], self.T, 1,
                 PV(Pp(wkeys[0]), None, None, None), PV(_p(self.wt[0]), None, None, None), PV(None, None, None, None),
                 I4(self.chan[1], 0, 0, 0), I4(self.chan[0], 0, 0, 0), None, None, 0, 0, self.step_dev.data_ptr(), st)
-        self._fork_side(main)
-        with torch.cuda.stream(self.side):
-            self._k("prep_w", lib.ecgb200_step_prep_bf16, None, None, 0, 0, 0, 3,
-                    PV(*[Pp(k) for k in wkeys[1:]], None), PV(*[_p(w) for w in self.wt[1:]], None),
-                    PV(*[_p(w) for w in self.wd[1:]], None), I4(*self.chan[2:5], 0), I4(*self.chan[1:4], 0),
-                    Pp(pre + "proj.weight"), _p(self.wpT),
-                    self.feat, self.chan[4], None, self.side.cuda_stream)
-            prep_done = torch.cuda.Event()
-            prep_done.record(self.side)
+        ev_prep = torch.cuda.Event()
+        ev_prep.record(main)
+
+        def prep_rest():
+            # released by `prep`, but enqueued AFTER conv 1 so that the critical node is created (and launched) first
+            if self.linear:
+                self.side = main
+            else:
+                self.side.wait_event(ev_prep)
+            with torch.cuda.stream(self.side):
+                self._k("prep_w", lib.ecgb200_step_prep_bf16, None, None, 0, 0, 0, 3,
+                        PV(*[Pp(k) for k in wkeys[1:]], None), PV(*[_p(w) for w in self.wt[1:]], None),
+                        PV(*[_p(w) for w in self.wd[1:]], None), I4(*self.chan[2:5], 0), I4(*self.chan[1:4], 0),
+                        Pp(pre + "proj.weight"), _p(self.wpT),
+                        self.feat, self.chan[4], None, self.side.cuda_stream)
+                done = torch.cuda.Event()
+                done.record(self.side)
+            return done
+        import os
+        # creating prep_w's node after conv 1's measured slower (462 vs 448 us): conv 2 then waits for it
+        prep_late = os.environ.get("ECGB200_PREPW_LATE", "0") == "1"
+        prep_done = None if prep_late else prep_rest()
         n += 2
         for l in range(4):
             cip, co, L = self.cip[l], self.chan[l + 1], self.L[l]
@@ -332,6 +345,10 @@ class TrainStep:
                 main.wait_event(prep_done)
             self._k("conv_fwd", lib.ecgb200_conv1d_fwd_stats_bf16, _p(self.acts[l]), _p(self.wt[l]), Pp(k + "0.bias"),
                     _p(self.ybuf[l]), _p(self.statp[l]), B, cip, co, L, st)
+            if l == 0 and prep_late:
+                self._prof_tag = ""
+                prep_done = prep_rest()
+                self._prof_tag = "_L1"
             self._k("bn_relu_pool", lib.ecgb200_bn_relu_pool_fwd_train_bf16, _p(self.ybuf[l]), _p(self.statp[l]),
                     self.nstat[l], Pp(k + "1.weight"), Pp(k + "1.bias"), bn.running_mean.data_ptr(),
                     bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(), _p(self.bnst[l]),
@@ -370,7 +387,26 @@ class TrainStep:
                     _p(self.dp) if l < 3 else None, _p(self.dgap) if l == 3 else None, _p(dy),
                     Gp(k + "1.weight"), Gp(k + "1.bias"), _p(self.dbpart[l]), _p(self.ws2), B, co, L, 1, st)
             n += 1 if self.bn_fused[l] else 2
-            self._fork_side(main)
+            # Order matters: the tensor kernels cannot share an SM (TMEM + shared memory), so whichever of dgrad_l
+            # (critical path) and wgrad_l (side) the graph launches first takes the GPU, and ready nodes are launched in
+            # creation order.  Measured (same box, us/step): wgrad node created first ("early") 476 -- or 456 when a
+            # slower head_wgrad happened to delay it; wgrad released only after dgrad completes ("after") 466;
+            # both released by bn_bwd_l with dgrad's node created first ("both", the default) 453.
+            import os
+            mode = os.environ.get("ECGB200_WGRAD_ORDER", "both")
+            early = mode == "early"
+            ev_bn = None
+            if mode == "both":                       # both released by bn_bwd_l, but dgrad's node is created first
+                ev_bn = torch.cuda.Event()
+                ev_bn.record(main)
+            if l > 0 and not early:
+                self._k("dgrad", lib.ecgb200_conv1d_fwd_bf16, _p(dy), _p(self.wd[l]), None, _p(self.dp),
+                        B, co, ci, L, st)
+                n += 1
+            if ev_bn is not None and not self.linear:
+                self.side.wait_event(ev_bn)
+            else:
+                self._fork_side(main)
             with torch.cuda.stream(self.side):
                 self._k("wgrad", lib.ecgb200_conv1d_wgrad_bf16, _p(dy), _p(self.acts[l]), Gp(k + "0.weight"),
                         Gp(k + "0.bias"), _p(self.dbpart[l]), self.ndb[l], _p(self.ws), B, ci, co, L,
@@ -383,7 +419,7 @@ class TrainStep:
                     with torch.cuda.stream(self.comm):
                         torch.distributed.all_reduce(self.G[self.bucket_a_off:], group=self.pg)
             n += 2
-            if l > 0:
+            if l > 0 and early:
                 self._k("dgrad", lib.ecgb200_conv1d_fwd_bf16, _p(dy), _p(self.wd[l]), None, _p(self.dp),
                         B, co, ci, L, st)
                 n += 1
@@ -457,9 +493,11 @@ class TrainStep:
                     _p(self.dlogits), _p(self.dz), _p(self.dgap), _p(self.loss_part), B, c4, F_, NL, 1.0, st)
             self._fork_side(main)
             with torch.cuda.stream(self.side):
-                self._k("head_wgrad", lib.ecgb200_head_wgrad_f32, _p(self.gap), _p(self.z), _p(self.dz),
-                        _p(self.dlogits), _p(self.loss_part), Gp("proj.weight"), Gp("proj.bias"), Gp("head.weight"),
-                        Gp("head.bias"), _p(self.loss), B, c4, F_, NL, self.side.cuda_stream)
+                V2, I2 = C.c_void_p * 2, C.c_int * 2
+                self._k("head_wgrad", lib.ecgb200_head_wgrad_multi_f32, 2, V2(_p(self.dz), _p(self.dlogits)),
+                        V2(_p(self.gap), _p(self.z)), V2(Gp("proj.weight"), Gp("head.weight")),
+                        V2(Gp("proj.bias"), Gp("head.bias")), I2(F_, NL), I2(c4, F_), _p(self.loss_part), _p(self.loss),
+                        B, NL, self.side.cuda_stream)
             n += 2
         elif self.bf16 and self.mm and self._mm_head_ok():
             # fused FiLM head (demo encoder, film, head, BCE and the whole chain rule) + one launch for the five
