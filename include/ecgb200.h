@@ -306,6 +306,35 @@ int ecgb200_zscore_f32(const float* x, float* out, int rows, int T, void* stream
 int ecgb200_wfdb16_zscore_f32(const void* dat, const float* gain, const int* baseline, float* out, int B,
                               int n_leads, int T, int normalize, void* stream);
 
+/* ------------------------------------------------- bf16 inference engine (eval) --
+ * model.eval() forward of the reference (src/training/loop.py:52-65, loop_demo.py:59-75,
+ * scripts/06_ecg_baseline_test.py:94-106) with nothing but the pooled activations leaving the SM.
+ *
+ * Eval-mode BatchNorm1d (ecg_cnn.py:14) and the conv bias folded to per-channel fp32
+ *   scale = gamma / sqrt(running_var + eps),  shift = (conv_bias - running_mean) * scale + beta. */
+int ecgb200_bn_fold_f32(const float* gamma, const float* beta, const float* running_mean,
+                        const float* running_var, const float* conv_bias, float* scale, float* shift,
+                        int C, float eps, void* stream);
+/* One ConvBlock in eval mode (ecg_cnn.py:18-20): pb = maxpool2(relu(scale * conv(xb, wprep) + shift)) in the
+ * epilogue of the tcgen05 conv kernel; xb / wprep as ecgb200_conv1d_fwd_bf16, pb [B][Co/8][L/2][8] bf16.
+ * gap_part != NULL (last block): pb is not written (may be NULL); gap_part[B * ceil(L/128)][4][Co] receives the
+ * per-(128-step tile, lane quarter) time sums of the pooled rows for AdaptiveAvgPool1d(1) (ecg_cnn.py:61-62). */
+int ecgb200_conv1d_bn_relu_pool_infer_bf16(const void* xb, const void* wprep, const float* scale,
+                                           const float* shift, void* pb, float* gap_part, int B, int Ci,
+                                           int Co, int L, void* stream);
+/* Fused inference head: gap = inv_lp * sum of a window's `nparts` partials; z = proj(gap) (wpT = proj.weight
+ * transposed, (C4, F)); with demo != NULL the DemoEncoder -> film_gen -> FiLM chain of
+ * src/models/ecg_multimodal.py:44-59,88-99 (w1 (H,D0); w2 and wf TRANSPOSED: (H_in,H_out) and (H,2F)); logits = head(.) (ecg_cnn.py:63-64);
+ * prob = sigmoid(logits) (loop.py:63).  z (B,F) (un-modulated features) and prob may be NULL.
+ * C4, F <= 256, H <= 64. */
+int ecgb200_infer_head_f32(const float* gap_part, int nparts, float inv_lp, const float* wpT,
+                           const float* bp, const float* demo, const float* w1, const float* b1,
+                           const float* w2, const float* b2, const float* wf, const float* bf,
+                           const float* wh, const float* bh, float* z, float* logits, float* prob,
+                           int B, int C4, int F, int D0, int H, int NL, void* stream);
+/* out (cols, rows) = in (rows, cols) transposed (proj.weight -> wpT, once per weight refresh). */
+int ecgb200_transpose_f32(const float* in, float* out, int rows, int cols, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -232,11 +232,20 @@ __device__ __forceinline__ void conv_issue_group_stream(uint32_t acc0, uint64_t 
 //            combined in a fixed order by the consumer => deterministic).  Two warps share each TMEM
 //            lane quarter and split the (tile, 32-channel block) items between them: the epilogue is
 //            bound by one warp's instruction latency, not by bandwidth.
+//
+// MODE 0 (training forward / dgrad): the epilogue above.
+// MODE 1 (inference): eval-mode BatchNorm folded into per-channel {scale, shift} (`bias` = scale), ReLU and
+//        MaxPool1d(2) in the epilogue -- the two time steps of a pool pair are adjacent TMEM lanes = adjacent
+//        threads, which swap half of their 32 channels with one shuffle each -- and only the POOLED bf16 rows go
+//        to HBM (`y` = pooled output [B][Co/8][L/2][8]): the conv output itself never leaves the SM.
+// MODE 2 (inference, last block): as MODE 1 but nothing is stored: the pooled rows are summed over time per
+//        (tile, lane quarter) for AdaptiveAvgPool1d(1) (`stat_part` = gap_part[tile][4][Co], fixed order).
 constexpr int C2_THREADS = 320;
+template <int MODE>
 __global__ void __launch_bounds__(C2_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __nv_bfloat16* __restrict__ wprep,
-               const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, float* __restrict__ stat_part,
-               const Conv2Cfg P) {
+               const float* __restrict__ bias, const float* __restrict__ shift, __nv_bfloat16* __restrict__ y,
+               float* __restrict__ stat_part, const Conv2Cfg P) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* wfull = reinterpret_cast<uint64_t*>(smem);           // [C2_MAXST]
     uint64_t* wempty = wfull + C2_MAXST;                            // [C2_MAXST]
@@ -387,7 +396,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __nv_bfloat16* __
         const int nblk = Co >> 5;
         const int row = 32 * q + lane;
         const size_t chunk_stride = (size_t)L * 8;     // elements between channel chunks
-        const bool want_stats = stat_part != nullptr;
+        const bool want_stats = MODE == 0 && stat_part != nullptr;
         float ssum[8], ssq[8];                         // lane j: channel 32*cb + j, over this warp's rows
 #pragma unroll
         for (int i = 0; i < 8; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
@@ -433,6 +442,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __nv_bfloat16* __
                     float bv[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) bv[i] = bias != nullptr ? __ldg(bias + c0 + i) : 0.f;
+                    float sh[MODE != 0 ? 32 : 1];
+                    if constexpr (MODE != 0) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) sh[i] = __ldg(shift + c0 + i);
+                    }
                     for (int r = 0; r < rcount; ++r) {
                         if (nblk == 1 && (r & 1) != half) continue;
                         const int tile = tile0 + r;
@@ -443,6 +457,49 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __nv_bfloat16* __
                         float v[32];
                         tc::tmem_ld32(taddr, v);
                         tc::tmem_ld_wait();
+                        if constexpr (MODE != 0) {
+                            // relu(scale * conv + shift), then max over the pool pair (lanes 2p, 2p+1): the even lane
+                            // keeps channels 0-15 of the block, the odd lane 16-31
+                            const bool even = (lane & 1) == 0;
+                            const int Lp = L >> 1, tp = t >> 1;
+                            const bool plive = tp < Lp;
+                            float m[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const float a = fmaxf(fmaf(v[i], bv[i], sh[i]), 0.f);
+                                const float c = fmaxf(fmaf(v[16 + i], bv[16 + i], sh[16 + i]), 0.f);
+                                const float send = even ? c : a, keep = even ? a : c;
+                                m[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+                            }
+                            if constexpr (MODE == 1) {
+                                if (plive) {
+                                    __nv_bfloat16* prow = y + ((size_t)b * (Co / 8) * Lp + tp) * 8 +
+                                                          (size_t)(c0 / 8 + (even ? 0 : 2)) * ((size_t)Lp * 8);
+                                    *reinterpret_cast<uint4*>(prow) =
+                                        make_uint4(tc::pack_bf16(m[0], m[1]), tc::pack_bf16(m[2], m[3]),
+                                                   tc::pack_bf16(m[4], m[5]), tc::pack_bf16(m[6], m[7]));
+                                    *reinterpret_cast<uint4*>(prow + (size_t)Lp * 8) =
+                                        make_uint4(tc::pack_bf16(m[8], m[9]), tc::pack_bf16(m[10], m[11]),
+                                                   tc::pack_bf16(m[12], m[13]), tc::pack_bf16(m[14], m[15]));
+                                }
+                            } else {
+                                // sum over the 16 pool pairs of this warp: transposing butterfly over lane bits 4..1,
+                                // after which lane l holds channel c0 + 16*(l&1) + (l>>1)
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) m[i] = plive ? m[i] : 0.f;
+#pragma unroll
+                                for (int o = 8; o > 0; o >>= 1) {
+                                    const bool up = (lane & (2 * o)) != 0;
+#pragma unroll
+                                    for (int i = 0; i < o; ++i) {
+                                        const float send = up ? m[i] : m[i + o], keep = up ? m[i + o] : m[i];
+                                        m[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2 * o);
+                                    }
+                                }
+                                stat_part[((size_t)tile * 4 + q) * Co + c0 + 16 * (lane & 1) + (lane >> 1)] = m[0];
+                            }
+                            continue;
+                        }
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             uint32_t pk[4];
@@ -577,9 +634,9 @@ extern "C" int ecgb200_conv1d_stat_parts_bf16(int B, int Ci, int Co, int L) {
 // yb [B][Co/8][L][8] bf16.  Co % 32 == 0, Co <= 256, Ci <= 256.
 // stat_part: NULL or float[parts][2][Co] (parts = ecgb200_conv1d_stat_parts_bf16) receiving per-CTA
 // {sum, sum of squares} of the bf16-rounded outputs.
-extern "C" int ecgb200_conv1d_fwd_stats_bf16(const void* xb, const void* wprep, const float* bias, void* yb,
-                                             float* stat_part, int B, int Ci, int Co, int L, void* stream) {
-    if (!xb || !wprep || !yb || B <= 0 || L <= 0) return ECGB200_EINVAL;
+template <int MODE>
+static int conv_tc_launch(const void* xb, const void* wprep, const float* bias, const float* shift, void* yb,
+                          float* stat_part, int B, int Ci, int Co, int L, void* stream) {
     if (Ci <= 0 || (Ci & 15) || Ci > 256 || (Ci > 64 && (Ci & 63)) || Co <= 0 || (Co & 31) || Co > 256) return ECGB200_EUNSUPPORTED;
     CUtensorMap xmap;
     int rc = ecg_make_act_tmap(&xmap, xb, B, Ci, L, TC_ROWS, Ci / 8);
@@ -588,14 +645,33 @@ extern "C" int ecgb200_conv1d_fwd_stats_bf16(const void* xb, const void* wprep, 
     size_t smem;
     const int grid = conv2_cfg(B, Ci, Co, L, &P, &smem);
     if (grid <= 0) return ECGB200_EUNSUPPORTED;
-    static size_t smem_set = 0;
+    static size_t smem_set = 0;                              // one per instantiation
     if (smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         smem_set = smem;
     }
-    return ecg_launch_pdl(conv_tc_kernel, dim3(grid), dim3(C2_THREADS), smem, (cudaStream_t)stream, xmap,
-                          (const __nv_bfloat16*)wprep, bias, (__nv_bfloat16*)yb, stat_part, P);
+    return ecg_launch_pdl(conv_tc_kernel<MODE>, dim3(grid), dim3(C2_THREADS), smem, (cudaStream_t)stream, xmap,
+                          (const __nv_bfloat16*)wprep, bias, shift, (__nv_bfloat16*)yb, stat_part, P);
+}
+
+extern "C" int ecgb200_conv1d_fwd_stats_bf16(const void* xb, const void* wprep, const float* bias, void* yb,
+                                             float* stat_part, int B, int Ci, int Co, int L, void* stream) {
+    if (!xb || !wprep || !yb || B <= 0 || L <= 0) return ECGB200_EINVAL;
+    return conv_tc_launch<0>(xb, wprep, bias, nullptr, yb, stat_part, B, Ci, Co, L, stream);
+}
+
+// Inference block: pb = maxpool2(relu(scale * conv(xb) + shift)), the eval-mode BatchNorm (and the conv bias)
+// folded into per-channel fp32 {scale, shift} (ecgb200_bn_fold_f32).  xb / wprep as above; pb [B][Co/8][L/2][8]
+// bf16.  gap_part != NULL (last block): nothing is stored to pb (may be NULL); instead
+// gap_part[B * ceil(L/128)][4][Co] receives the time sums of the pooled rows per (128-step tile, lane quarter):
+// mean over time = (sum of a window's 4 * ceil(L/128) partials) / (L/2).
+extern "C" int ecgb200_conv1d_bn_relu_pool_infer_bf16(const void* xb, const void* wprep, const float* scale,
+                                                      const float* shift, void* pb, float* gap_part, int B, int Ci,
+                                                      int Co, int L, void* stream) {
+    if (!xb || !wprep || !scale || !shift || (!pb && !gap_part) || B <= 0 || L < 2) return ECGB200_EINVAL;
+    if (gap_part != nullptr) return conv_tc_launch<2>(xb, wprep, scale, shift, nullptr, gap_part, B, Ci, Co, L, stream);
+    return conv_tc_launch<1>(xb, wprep, scale, shift, pb, nullptr, B, Ci, Co, L, stream);
 }
 
 extern "C" int ecgb200_conv1d_fwd_bf16(const void* xb, const void* wprep, const float* bias, void* yb,

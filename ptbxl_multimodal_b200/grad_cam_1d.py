@@ -99,11 +99,13 @@ def conv4_activations(model, x: torch.Tensor):
 @torch.no_grad()
 def gradcam_batch(model, x: torch.Tensor, x_demo: Optional[torch.Tensor] = None,
                   signal_length: Optional[int] = None, variant: str = "v1", eps: float = 1e-9,
-                  return_lowres: bool = False):
+                  return_lowres: bool = False, engine=None):
     """All-class Grad-CAM for a batch: returns (cam (N, K, T or L'), argmax (N, K) int32
     [, cam_lowres]).  variant 'v1' = GradCAM1D order; 'v2' = script order (upsample, then
     (cam-min)/(max+eps); eps 1e-9 in scripts 00/13, 1e-8 in script 12).  Per-sample
-    normalisation, i.e. each row equals the reference's single-sample call."""
+    normalisation, i.e. each row equals the reference's single-sample call.
+    `engine`: optional InferStep built for this model -- the forward up to the raw conv-4 output then runs on the
+    bf16 tensor-core path (throughput mode; bf16 tolerance instead of the fp32 path's exact peak indices)."""
     if isinstance(model, ECGCNN):
         wh, wp = model.head.weight, model.proj.weight
         if x_demo is not None:
@@ -114,7 +116,12 @@ def gradcam_batch(model, x: torch.Tensor, x_demo: Optional[torch.Tensor] = None,
             raise EcgB200Error("ECGMultimodal Grad-CAM needs x_demo")
     else:
         raise EcgB200Error("gradcam_batch supports ecgb200 ECGCNN / ECGMultimodal models")
-    A, bn_state = conv4_activations(model, x)
+    if engine is not None:
+        if engine.model is not model:
+            raise EcgB200Error("the InferStep engine was built for another model")
+        A, bn_state = engine.conv4(x)
+    else:
+        A, bn_state = conv4_activations(model, x)
     n = x.shape[0]
     k, f = wh.shape
     wpt = wp.detach().t().contiguous()                      # (256, F): v = Wh @ Wp as linear(Wh, Wp^T)

@@ -30,8 +30,12 @@ def train_one_epoch(model, loader, optimizer, device) -> float:
     return float(total.item()) / len(loader.dataset)
 
 
-def eval_one_epoch(model, loader, device) -> Dict[str, float]:
+def eval_one_epoch(model, loader, device, engine=None) -> Dict[str, float]:
+    """`engine`: optional ecgb200 InferStep built for this model (bf16 tensor-core forward as one CUDA graph);
+    without it the fp32-exact module forward runs, as in the reference."""
     model.eval()
+    if engine is not None:
+        engine.refresh()
     all_targets, all_probs = [], []
     total = torch.zeros((), dtype=torch.float64, device=device)
     counts = None
@@ -39,7 +43,7 @@ def eval_one_epoch(model, loader, device) -> Dict[str, float]:
         for x, y in loader:
             x = x.to(device, non_blocking=True)
             y = y.to(device, non_blocking=True)
-            logits = _logits(model(x))
+            logits = engine(x) if engine is not None else _logits(model(x))
             loss = Fn.binary_cross_entropy_with_logits(logits, y)
             total += loss.double() * x.size(0)
             if counts is None:

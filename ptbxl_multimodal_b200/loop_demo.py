@@ -26,8 +26,11 @@ def train_one_epoch_demo(model, loader, optimizer, device):
     return float(total.item()) / max(1, num_batches)
 
 
-def eval_one_epoch_demo(model, loader, device):
+def eval_one_epoch_demo(model, loader, device, engine=None):
+    """`engine`: optional ecgb200 InferStep built for this model (see loop.eval_one_epoch)."""
     model.eval()
+    if engine is not None:
+        engine.refresh()
     total = torch.zeros((), dtype=torch.float64, device=device)
     num_batches = 0
     all_probs, all_targets = [], []
@@ -36,7 +39,7 @@ def eval_one_epoch_demo(model, loader, device):
             x_ecg = x_ecg.to(device, non_blocking=True)
             x_demo = x_demo.to(device, non_blocking=True)
             y = y.to(device, non_blocking=True)
-            logits = model(x_ecg, x_demo)
+            logits = engine(x_ecg, x_demo) if engine is not None else model(x_ecg, x_demo)
             total += Fn.binary_cross_entropy_with_logits(logits, y).double()
             num_batches += 1
             all_probs.append(Fn.sigmoid(logits))
