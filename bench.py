@@ -329,6 +329,23 @@ def main():
                     "peak_source": pk["src"] + " (sustained, x n_gpus)", "algorithmic_flops": flops * B * world}
         line_extra["roofline"] = roof
 
+    # ---- side figure (N == 1): the eval forward of the same model through the bf16 inference engine (InferStep:
+    # BN/ReLU/pool/GAP fused into the conv epilogue), device-timed like `value`; not part of the train-step metric
+    if rank == 0 and world == 1 and precision == "bf16":
+        model.eval()
+        inf = P.InferStep(model, B, T)
+        inf.load_batch(dx[0], slot=0)
+        inf.load_batch(dx[1], slot=1)
+        inf.capture()
+        for i in range(5):
+            inf.run(slot=i & 1)
+        ms_inf = timed(lambda i: inf.run(slot=i & 1), 100)
+        line_extra["infer"] = {"value": B * 100 / (ms_inf / 1000.0), "unit": UNIT, "ms_per_batch": ms_inf / 100,
+                               "launches_per_batch": inf.launches_per_batch,
+                               "roofline_frac": 176.7 * T / 1000.0 * 1e-9 * B / (ms_inf / 100 * 1e-3),
+                               "note": "eval forward, bf16 tcgen05 engine, inputs resident; 176.7 ns/window fused-inference model"}
+        model.train()
+
     # ---- CPU baseline beside the GPU number (rank 0, N == 1 only; bounded sample)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, b, done, dt = cpu_train_steps(B, T, steps=80, warmup=2, budget_s=15.0)

@@ -9,6 +9,7 @@ from .loop import train_one_epoch, eval_one_epoch  # noqa: F401
 from .loop_demo import train_one_epoch_demo, eval_one_epoch_demo  # noqa: F401
 from .optim import FusedAdamW  # noqa: F401
 from .infer import InferStep  # noqa: F401
-from . import functional, parallel, wfdb16  # noqa: F401
+from .loader import Wfdb16BatchLoader, validate_records  # noqa: F401
+from . import functional, parallel, wfdb16, loader  # noqa: F401
 
 __version__ = "0.1.0"

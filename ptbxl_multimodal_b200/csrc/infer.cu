@@ -52,7 +52,7 @@ extern "C" int ecgb200_transpose_f32(const float* in, float* out, int rows, int 
 }
 
 // ------------------------------------------------------------------ fused inference head
-// IH_W windows per CTA, 256 threads.  Per window:
+// IH_W windows per CTA, 1024 threads (256 output features x 4 K-quarters).  Per window:
 //   gap[c]   = inv_lp * sum_p gap_part[b][p][c]                       (fixed order: deterministic)
 //   z[j]     = bp[j] + sum_k WpT[k][j] gap[k]                          (thread j, coalesced over j)
 //   demo != NULL:  h1 = relu(W1 d + b1), h2 = relu(W2 h1 + b2), film = Wf h2 + bf   (w2, wf passed TRANSPOSED:
@@ -74,27 +74,30 @@ struct InferHeadArgs {
     int B, C4, F, D0, H, NL;
 };
 
-__global__ void __launch_bounds__(256) infer_head_kernel(const InferHeadArgs a) {
-    __shared__ __align__(16) float gT[IH_MAXF][IH_W];      // gap, then reused for the (modulated) features
-    __shared__ __align__(16) float zT[IH_MAXF][IH_W];
+constexpr int IH_THREADS = 1024;   // 256 output features x 4 K-quarters
+
+__global__ void __launch_bounds__(IH_THREADS) infer_head_kernel(const InferHeadArgs a) {
+    __shared__ __align__(16) float gT[IH_MAXF][IH_W];      // gap
+    __shared__ __align__(16) float zT[IH_MAXF][IH_W];      // features (then FiLM-modulated in place)
+    __shared__ __align__(16) float part[4][IH_MAXF][IH_W]; // K-quarter partial sums of proj / film
     __shared__ __align__(16) float h1T[IH_MAXH][IH_W];
     __shared__ __align__(16) float h2T[IH_MAXH][IH_W];
     const int tid = threadIdx.x, b0 = blockIdx.x * IH_W;
     const int nw = min(IH_W, a.B - b0);
+    const int j = tid & 255, kq = tid >> 8;                // output feature, K-quarter
 
-    for (int c = tid; c < a.C4; c += 256) {
-#pragma unroll
-        for (int s = 0; s < IH_W; ++s) {
-            float acc = 0.f;
-            if (s < nw) {
-                const float* p = a.gap_part + (size_t)(b0 + s) * a.nparts * a.C4 + c;
-                for (int i = 0; i < a.nparts; ++i) acc += p[(size_t)i * a.C4];
-            }
-            gT[c][s] = acc * a.inv_lp;
+    // gap: (channel, window) items over all threads; the partials of a window are summed in a fixed order
+    for (int i = tid; i < a.C4 * IH_W; i += IH_THREADS) {
+        const int c = i % a.C4, s = i / a.C4;
+        float acc = 0.f;
+        if (s < nw) {
+            const float* p = a.gap_part + (size_t)(b0 + s) * a.nparts * a.C4 + c;
+            for (int n = 0; n < a.nparts; ++n) acc += __ldg(p + (size_t)n * a.C4);
         }
+        gT[c][s] = acc * a.inv_lp;
     }
     if (a.demo != nullptr) {
-        for (int i = tid; i < a.H * IH_W; i += 256) {
+        for (int i = tid; i < a.H * IH_W; i += IH_THREADS) {
             const int s = i % IH_W, r = i / IH_W;
             float acc = a.b1[r];
             if (s < nw)
@@ -103,55 +106,79 @@ __global__ void __launch_bounds__(256) infer_head_kernel(const InferHeadArgs a) 
         }
     }
     __syncthreads();
-    for (int j = tid; j < a.F; j += 256) {
-        float acc[IH_W];
-        const float bj = a.bp[j];
+    // proj: thread (j, kq) covers k in [kq*C4/4, (kq+1)*C4/4), weights fetched eight at a time (independent loads
+    // in flight: the loop is bound by L2 latency, not by bandwidth or FLOPs)
+    if (j < a.F) {
+        float acc[IH_W] = {0.f, 0.f, 0.f, 0.f};
+        const int kn = (a.C4 + 3) / 4, k0 = kq * kn, k1 = min(a.C4, k0 + kn);
+        for (int k = k0; k < k1; k += 8) {
+            float w[8];
 #pragma unroll
-        for (int s = 0; s < IH_W; ++s) acc[s] = bj;
-#pragma unroll 8
-        for (int k = 0; k < a.C4; ++k) {
-            const float w = __ldg(a.wpT + (size_t)k * a.F + j);
-            const float4 g = *reinterpret_cast<const float4*>(gT[k]);
-            acc[0] = fmaf(w, g.x, acc[0]); acc[1] = fmaf(w, g.y, acc[1]);
-            acc[2] = fmaf(w, g.z, acc[2]); acc[3] = fmaf(w, g.w, acc[3]);
-        }
+            for (int e = 0; e < 8; ++e) w[e] = k + e < k1 ? __ldg(a.wpT + (size_t)(k + e) * a.F + j) : 0.f;
 #pragma unroll
-        for (int s = 0; s < IH_W; ++s) {
-            zT[j][s] = acc[s];
-            if (a.z != nullptr && s < nw) a.z[(size_t)(b0 + s) * a.F + j] = acc[s];
+            for (int e = 0; e < 8; ++e) {
+                const float4 g = *reinterpret_cast<const float4*>(gT[min(k + e, a.C4 - 1)]);
+                acc[0] = fmaf(w[e], g.x, acc[0]); acc[1] = fmaf(w[e], g.y, acc[1]);
+                acc[2] = fmaf(w[e], g.z, acc[2]); acc[3] = fmaf(w[e], g.w, acc[3]);
+            }
         }
+        *reinterpret_cast<float4*>(part[kq][j]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
     }
     if (a.demo != nullptr) {
-        for (int i = tid; i < a.H * IH_W; i += 256) {
+        for (int i = tid; i < a.H * IH_W; i += IH_THREADS) {
             const int s = i % IH_W, r = i / IH_W;
             float acc = a.b2[r];
             for (int k = 0; k < a.H; ++k) acc = fmaf(__ldg(a.w2 + k * a.H + r), h1T[k][s], acc);
             h2T[r][s] = fmaxf(acc, 0.f);
         }
+    }
+    __syncthreads();
+    if (kq == 0 && j < a.F) {
+        const float bj = a.bp[j];
+#pragma unroll
+        for (int s = 0; s < IH_W; ++s) {
+            const float v = bj + ((part[0][j][s] + part[1][j][s]) + (part[2][j][s] + part[3][j][s]));
+            zT[j][s] = v;
+            if (a.z != nullptr && s < nw) a.z[(size_t)(b0 + s) * a.F + j] = v;
+        }
+    }
+    if (a.demo != nullptr) {
         __syncthreads();
-        for (int j = tid; j < a.F; j += 256) {
-            float ga[IH_W], be[IH_W];
+        // film: thread (j, kq) -> gamma_j (kq 0,1) / beta_j (kq 2,3) over one half of H; wf is (H, 2F)
+        if (j < a.F) {
+            const int col = (kq >> 1) * a.F + j;
+            const int hn = (a.H + 1) / 2, k0 = (kq & 1) * hn, k1 = min(a.H, k0 + hn);
+            float acc[IH_W] = {0.f, 0.f, 0.f, 0.f};
+            for (int k = k0; k < k1; k += 8) {
+                float w[8];
 #pragma unroll
-            for (int s = 0; s < IH_W; ++s) { ga[s] = a.bf[j]; be[s] = a.bf[a.F + j]; }
-            const float* wg = a.wf + j;                                   // wf is (H, 2F): coalesced over j
-            const float* wb = a.wf + a.F + j;
-#pragma unroll 8
-            for (int k = 0; k < a.H; ++k) {
-                const float4 h = *reinterpret_cast<const float4*>(h2T[k]);
-                const float g = __ldg(wg + (size_t)k * 2 * a.F), b = __ldg(wb + (size_t)k * 2 * a.F);
-                ga[0] = fmaf(g, h.x, ga[0]); ga[1] = fmaf(g, h.y, ga[1]); ga[2] = fmaf(g, h.z, ga[2]); ga[3] = fmaf(g, h.w, ga[3]);
-                be[0] = fmaf(b, h.x, be[0]); be[1] = fmaf(b, h.y, be[1]); be[2] = fmaf(b, h.z, be[2]); be[3] = fmaf(b, h.w, be[3]);
+                for (int e = 0; e < 8; ++e) w[e] = k + e < k1 ? __ldg(a.wf + (size_t)(k + e) * 2 * a.F + col) : 0.f;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float4 h = *reinterpret_cast<const float4*>(h2T[min(k + e, a.H - 1)]);
+                    acc[0] = fmaf(w[e], h.x, acc[0]); acc[1] = fmaf(w[e], h.y, acc[1]);
+                    acc[2] = fmaf(w[e], h.z, acc[2]); acc[3] = fmaf(w[e], h.w, acc[3]);
+                }
             }
+            *reinterpret_cast<float4*>(part[kq][j]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        }
+        __syncthreads();
+        if (kq == 0 && j < a.F) {
+            const float bg = a.bf[j], bb = a.bf[a.F + j];
 #pragma unroll
-            for (int s = 0; s < IH_W; ++s) zT[j][s] = fmaf(1.0f + tanhf(ga[s]), zT[j][s], be[s]);
+            for (int s = 0; s < IH_W; ++s) {
+                const float ga = bg + (part[0][j][s] + part[1][j][s]);
+                const float be = bb + (part[2][j][s] + part[3][j][s]);
+                zT[j][s] = fmaf(1.0f + tanhf(ga), zT[j][s], be);
+            }
         }
     }
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31;
-    for (int item = warp; item < nw * a.NL; item += 8) {
+    for (int item = warp; item < nw * a.NL; item += IH_THREADS / 32) {
         const int s = item % nw, c = item / nw;
         float acc = 0.f;
-        for (int j = lane; j < a.F; j += 32) acc = fmaf(__ldg(a.wh + (size_t)c * a.F + j), zT[j][s], acc);
+        for (int f = lane; f < a.F; f += 32) acc = fmaf(__ldg(a.wh + (size_t)c * a.F + f), zT[f][s], acc);
         acc = warp_sum(acc);
         if (lane == 0) {
             const float x = acc + a.bh[c];
@@ -174,6 +201,6 @@ extern "C" int ecgb200_infer_head_f32(const float* gap_part, int nparts, float i
     }
     InferHeadArgs a{gap_part, nparts, inv_lp, wpT, bp, demo, w1, b1, w2, b2, wf, bf, wh, bh, z, logits, prob,
                     B, C4, F, D0, H, NL};
-    infer_head_kernel<<<ecg_cdiv(B, IH_W), 256, 0, (cudaStream_t)stream>>>(a);
+    infer_head_kernel<<<ecg_cdiv(B, IH_W), IH_THREADS, 0, (cudaStream_t)stream>>>(a);
     return ecg_launch_status();
 }
