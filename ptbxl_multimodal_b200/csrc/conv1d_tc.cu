@@ -691,10 +691,12 @@ extern "C" int ecgb200_conv1d_fwd_bf16(const void* xb, const void* wprep, const 
 // channel chunks (4 x 128 = 512 TMEM columns), accumulated IN TMEM over the CTA's whole share of
 // (sample, 128-step time tile) work items; one epilogue per CTA writes a split-K partial
 // part[z][o][c/8][16][8] that wgrad_tc_reduce_kernel sums in a fixed order (deterministic).
-constexpr int WT_NST = 3;
-constexpr int WT_DY_BYTES = 16 * 128 * 16;       // [<=16 chunks][128 rows][8] bf16
-constexpr int WT_X_BYTES = 4 * TC_ROWS * 16;     // [<=4 chunks][144 rows][8] bf16
-constexpr int WT_STAGE = WT_DY_BYTES + WT_X_BYTES;
+// Stage = dY tile [ochunks][128 rows][8] + X tile [ncc][144 rows][8] bf16, sized per layer; the ring is as deep as
+// shared memory allows (<= WT_MAXST): a tile takes ~1.4 us to land, so the thin stem layers need 6-8 loads in
+// flight to keep the issuer busy (3 stages: 1480 cycles per item on L1 against 1024 of MMA time).
+constexpr int WT_MAXST = 8;
+constexpr int WT_SMEM_BUDGET = 215 * 1024;
+constexpr int WT_EPI_BYTES = 4 * 32 * 512;       // epilogue transposition scratch (re-uses the stage ring)
 
 // All MMAs of one (sample, 128-step tile) work item: NCC channel chunks x 8 K-steps, fully unrolled so every
 // descriptor is "item base + compile-time constant" (see conv_issue_stage for why).
@@ -721,11 +723,11 @@ __device__ __forceinline__ void wgrad_issue_item(uint32_t tmem_base, uint64_t al
 
 __global__ void __launch_bounds__(192, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant__ CUtensorMap xmap,
-                float* __restrict__ part, int Co, int Cip, int L, int B, int ncc, int ochunks) {
+                float* __restrict__ part, int Co, int Cip, int L, int B, int ncc, int ochunks, int nst) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
-    uint64_t* empty = full + WT_NST;
-    uint64_t* accfull = empty + WT_NST;
+    uint64_t* empty = full + WT_MAXST;
+    uint64_t* accfull = empty + WT_MAXST;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfull + 1);
     uint8_t* stages = smem + TC_HDR;
 
@@ -738,9 +740,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant
     const int nloc = (items - z + S - 1) / S;            // items z, z+S, ...   (host guarantees >= 1)
     const uint32_t dybytes = (uint32_t)ochunks * 128 * 16;
     const uint32_t xbytes = (uint32_t)ncc * TC_ROWS * 16;
+    const uint32_t stage_bytes = dybytes + xbytes;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < WT_NST; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(empty + i, 1); }
+        for (int i = 0; i < WT_MAXST; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(empty + i, 1); }
         tc::mbar_init(accfull, 1);
         tc::fence_barrier_init();
         tc::fence_proxy_async();
@@ -761,12 +764,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant
             const int db = S / tiles_t, dt = S - db * tiles_t;
             for (int n = 0; n < nloc; ++n) {
                 tc::mbar_wait(empty + slot, ephase);
-                uint8_t* st = stages + (size_t)slot * WT_STAGE;
+                uint8_t* st = stages + (size_t)slot * stage_bytes;
                 tc::mbar_arrive_expect_tx(full + slot, dybytes + xbytes);
                 tc::tma_load_4d(st, &dymap, full + slot, 0, tt * TC_TILE_M, ob * 16, b);
-                tc::tma_load_4d(st + WT_DY_BYTES, &xmap, full + slot, 0, tt * TC_TILE_M - ECG_PAD, cb * ncc, b);
+                tc::tma_load_4d(st + dybytes, &xmap, full + slot, 0, tt * TC_TILE_M - ECG_PAD, cb * ncc, b);
                 if (n < 8) CTR(8 + n);                           // loads of item n issued
-                if (++slot == WT_NST) { slot = 0; ephase ^= 1; }
+                if (++slot == nst) { slot = 0; ephase ^= 1; }
                 b += db; tt += dt;
                 if (tt >= tiles_t) { tt -= tiles_t; ++b; }
             }
@@ -780,46 +783,60 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant
             // B = X chunk: N chunk n = tap n = the chunk shifted by n rows (SBO = 16 B)
             const uint64_t bdesc0 = tc::make_desc(0, 128, 16);
             const uint64_t alo0 = adesc0 + (uint64_t)(tc::smem_u32(stages) >> 4);
-            const uint64_t blo0 = bdesc0 + (uint64_t)((tc::smem_u32(stages) + WT_DY_BYTES) >> 4);
+            const uint64_t blo0 = bdesc0 + (uint64_t)((tc::smem_u32(stages) + dybytes) >> 4);
             int slot = 0;
             uint32_t fphase = 0, accum = 0;
             for (int n = 0; n < nloc; ++n) {
                 tc::mbar_wait(full + slot, fphase);
                 if (n < 8) CTR(16 + n);                          // item n landed
                 tc::fence_after_sync();
-                const uint64_t alo = alo0 + (uint64_t)((uint32_t)slot * (WT_STAGE >> 4));
-                const uint64_t blo = blo0 + (uint64_t)((uint32_t)slot * (WT_STAGE >> 4));
+                const uint64_t alo = alo0 + (uint64_t)((uint32_t)slot * (stage_bytes >> 4));
+                const uint64_t blo = blo0 + (uint64_t)((uint32_t)slot * (stage_bytes >> 4));
                 if (ncc == 4) wgrad_issue_item<4>(tmem_base, alo, blo, idesc, accum != 0);
                 else if (ncc == 2) wgrad_issue_item<2>(tmem_base, alo, blo, idesc, accum != 0);
                 else wgrad_issue_item<1>(tmem_base, alo, blo, idesc, accum != 0);
                 accum = 1;
                 tc::mma_commit(empty + slot);
                 if (n < 8) CTR(24 + n);                          // MMAs of item n issued
-                if (++slot == WT_NST) { slot = 0; fphase ^= 1; }
+                if (++slot == nst) { slot = 0; fphase ^= 1; }
             }
             tc::mma_commit(accfull);
             CTR(32);
         }
     } else {
         const int q = warp & 3;
-        const int o = ob * 128 + 32 * q + lane;
         tc::mbar_wait(accfull, 0);
         if (threadIdx.x == 64) CTR(33);
         tc::fence_after_sync();
         const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16);
-        for (int i = 0; i < ncc; ++i) {
+        // A thread owns one output-channel row (TMEM lane) whose 512 bytes per channel chunk are contiguous in the
+        // partial layout, but neighbouring rows are kilobytes apart: storing straight from the registers makes every
+        // store instruction 32 separate 16-byte transactions (measured: 19 k cycles of epilogue per CTA).  So each
+        // warp transposes its 32 rows x 512 B through the (now idle) stage buffers, XOR-swizzled so that both the
+        // row-wise writes and the column-wise reads are bank-conflict free, and every global store instruction
+        // writes 512 contiguous bytes of one row.
+        uint8_t* stg = stages + (size_t)(warp - 2) * (32 * 512);
+        const int nchunk = ob * 128 + 32 * q < Co ? ncc : 0;         // a warp whose 32 rows lie beyond Co has nothing to store
+        for (int i = 0; i < nchunk; ++i) {
 #pragma unroll 1
             for (int g = 0; g < 4; ++g) {
                 float v[32];
                 tc::tmem_ld32(taddr + (uint32_t)(i * 128 + g * 32), v);
                 tc::tmem_ld_wait();
-                if (o < Co) {
-                    float* dst = part + ((((size_t)z * Co + o) * (Cip / 8) + cb * ncc + i) * 16 + 4 * g) * 8;
 #pragma unroll
-                    for (int e = 0; e < 32; e += 4)
-                        *reinterpret_cast<float4*>(dst + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-                }
+                for (int e = 0; e < 8; ++e)
+                    *reinterpret_cast<float4*>(stg + lane * 512 + (((g * 8 + e) ^ (lane & 7)) << 4)) =
+                        make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
             }
+            __syncwarp();
+            float* dst0 = part + (((size_t)z * Co + ob * 128 + 32 * q) * (Cip / 8) + cb * ncc + i) * 128 + lane * 4;
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr) {
+                const float4 t = *reinterpret_cast<const float4*>(stg + rr * 512 + ((lane ^ (rr & 7)) << 4));
+                if (ob * 128 + 32 * q + rr < Co)
+                    *reinterpret_cast<float4*>(dst0 + (size_t)rr * (Cip / 8) * 128) = t;
+            }
+            __syncwarp();
         }
     }
     if (threadIdx.x == 64) CTR(34);
@@ -829,13 +846,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant
 }
 
 // dW[o][c][k] = sum_z part[z][o][c/8][k][c%8]  (c < Ci, k < 15);  db[o] = sum_j db_part[o][j]
-// Block = 32 float4 columns of the partial layout x 8 z-lanes: every load is a coalesced 512-byte
-// row, the 8 z-lanes are combined through shared memory in a fixed order (deterministic).
-__global__ void __launch_bounds__(256)
+// Block = RC x 32 float4 columns of the partial layout x ZL z-lanes (ZL * RC = 32): every load is a coalesced
+// 512-byte row; few splits (S <= 24) -> 8 z-lanes x 4 column sets per thread (independent loads in flight, one wave
+// of blocks), many splits over a small weight tensor (the stem layers: S = 148) -> 32 z-lanes, so that no thread
+// walks more than ~5 partials serially.  The z-lanes are combined through shared memory in a fixed order
+// (deterministic for a given shape).
+template <int ZL>                                          // z-lanes per block; RC = 32 / ZL column sets per thread
+__global__ void __launch_bounds__(32 * ZL)
 wgrad_tc_reduce_kernel(const float4* __restrict__ part, const float* __restrict__ db_part,
                        float* __restrict__ dw, float* __restrict__ db, int S, int Co, int Ci, int Cip,
                        int ndb, int nblk_w) {
-    __shared__ float4 red[8][32];
+    constexpr int RC = 32 / ZL;
+    __shared__ float4 red[ZL][32 * RC];
     if ((int)blockIdx.x >= nblk_w) {                       // tail blocks: conv-bias gradient
         const int o = (blockIdx.x - nblk_w) * blockDim.x + threadIdx.x;
         if (o < Co && db != nullptr) {
@@ -848,29 +870,38 @@ wgrad_tc_reduce_kernel(const float4* __restrict__ part, const float* __restrict_
     }
     const int n4 = Co * Cip * 4;                           // float4 columns per partial
     const int lane = threadIdx.x & 31, zl = threadIdx.x >> 5;
-    const int col = blockIdx.x * 32 + lane;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (col < n4) {
-        for (int z = zl; z < S; z += 8) {
-            const float4 v = __ldg(part + (size_t)z * n4 + col);
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-        }
+    const int col0 = blockIdx.x * (32 * RC) + lane;
+    float4 acc[RC];
+#pragma unroll
+    for (int c = 0; c < RC; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+    for (int z = zl; z < S; z += ZL) {
+        float4 v[RC];
+#pragma unroll
+        for (int c = 0; c < RC; ++c)
+            v[c] = col0 + 32 * c < n4 ? __ldg(part + (size_t)z * n4 + col0 + 32 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < RC; ++c) { acc[c].x += v[c].x; acc[c].y += v[c].y; acc[c].z += v[c].z; acc[c].w += v[c].w; }
     }
-    red[zl][lane] = acc;
+#pragma unroll
+    for (int c = 0; c < RC; ++c) red[zl][32 * c + lane] = acc[c];
     __syncthreads();
-    if (zl == 0 && col < n4) {
-        float4 t = red[0][lane];
+    if (zl < RC) {                                         // z-lane c finishes column set c
+        const int col = col0 + 32 * zl;
+        if (col < n4) {
+            float4 t = red[0][32 * zl + lane];
 #pragma unroll
-        for (int i = 1; i < 8; ++i) { const float4 v = red[i][lane]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
-        const int idx = col * 4;                           // element index in [o][c/8][16][8]
-        const int c8 = idx & 7, k = (idx >> 3) & 15;
-        const int cc = (idx >> 7) % (Cip / 8), o = idx / (Cip * 16);
-        if (k < ECG_KS) {
-            const float v[4] = {t.x, t.y, t.z, t.w};
+            for (int i = 1; i < ZL; ++i) { const float4 v = red[i][32 * zl + lane]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+            const int idx = col * 4;                       // element index in [o][c/8][16][8]
+            const int c8 = idx & 7, k = (idx >> 3) & 15;
+            const int cc = (idx >> 7) % (Cip / 8), o = idx / (Cip * 16);
+            if (k < ECG_KS) {
+                const float v[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int c = cc * 8 + c8 + e;
-                if (c < Ci) dw[((size_t)o * Ci + c) * ECG_KS + k] = v[e];
+                for (int e = 0; e < 4; ++e) {
+                    const int c = cc * 8 + c8 + e;
+                    if (c < Ci) dw[((size_t)o * Ci + c) * ECG_KS + k] = v[e];
+                }
             }
         }
     }
@@ -909,20 +940,38 @@ extern "C" int ecgb200_conv1d_wgrad_bf16(const void* dyb, const void* xb, float*
     if (rc) return rc;
     rc = ecg_make_act_tmap(&xmap, xb, B, Cip, L, TC_ROWS, ncc);
     if (rc) return rc;
-    const size_t smem = TC_HDR + (size_t)WT_NST * WT_STAGE;
-    static bool attr_set = false;
-    if (!attr_set) {
+    const size_t stage = (size_t)ochunks * 128 * 16 + (size_t)ncc * TC_ROWS * 16;
+    // the A operand is always described as M = 128 rows = 16 chunks (rows >= Co are computed and discarded), so a
+    // thin dY tile is read 2 KB x (16 - ochunks) past its end: keep that much slack behind the last stage
+    const size_t slack = (size_t)(16 - ochunks) * 128 * 16;
+    int nst = (int)((WT_SMEM_BUDGET - slack) / stage);
+    if (nst > WT_MAXST) nst = WT_MAXST;
+    if (const char* e = getenv("ECGB200_WGRAD_NST")) { const int v = atoi(e); if (v >= 2 && v <= nst) nst = v; }
+    size_t smem = TC_HDR + (size_t)nst * stage + slack;
+    if (smem < TC_HDR + WT_EPI_BYTES) smem = TC_HDR + WT_EPI_BYTES;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
         cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        attr_set = true;
+        smem_set = smem;
     }
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid(Cip / 8 / ncc, ecg_cdiv(Co, 128), S);
-    wgrad_tc_kernel<<<grid, 192, smem, st>>>(dymap, xmap, (float*)ws, Co, Cip, L, B, ncc, ochunks);
+    wgrad_tc_kernel<<<grid, 192, smem, st>>>(dymap, xmap, (float*)ws, Co, Cip, L, B, ncc, ochunks, nst);
     rc = ecg_launch_status();
     if (rc) return rc;
-    const int nblk_w = ecg_cdiv(Co * Cip * 4, 32);
-    wgrad_tc_reduce_kernel<<<nblk_w + ecg_cdiv(Co, 256), 256, 0, st>>>((const float4*)ws, db_part, dw, db, S, Co, Ci,
-                                                                      Cip, ndb, nblk_w);
+    static const bool skip_reduce = getenv("ECGB200_DEBUG_SKIP_WGRAD_REDUCE") != nullptr;    // timing diagnostics only
+    if (skip_reduce) return 0;
+    const float4* pw = (const float4*)ws;
+    if (S <= 24) {
+        const int nblk_w = ecg_cdiv(Co * Cip * 4, 128);
+        wgrad_tc_reduce_kernel<8><<<nblk_w + ecg_cdiv(Co, 256), 256, 0, st>>>(pw, db_part, dw, db, S, Co, Ci, Cip, ndb, nblk_w);
+    } else if (S <= 80) {
+        const int nblk_w = ecg_cdiv(Co * Cip * 4, 64);
+        wgrad_tc_reduce_kernel<16><<<nblk_w + ecg_cdiv(Co, 512), 512, 0, st>>>(pw, db_part, dw, db, S, Co, Ci, Cip, ndb, nblk_w);
+    } else {
+        const int nblk_w = ecg_cdiv(Co * Cip * 4, 32);
+        wgrad_tc_reduce_kernel<32><<<nblk_w + ecg_cdiv(Co, 1024), 1024, 0, st>>>(pw, db_part, dw, db, S, Co, Ci, Cip, ndb, nblk_w);
+    }
     return ecg_launch_status();
 }
