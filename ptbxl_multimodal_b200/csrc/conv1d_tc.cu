@@ -233,7 +233,7 @@ __device__ __forceinline__ void conv_issue_group_stream(uint32_t acc0, uint64_t 
 //            lane quarter and split the (tile, 32-channel block) items between them: the epilogue is
 //            bound by one warp's instruction latency, not by bandwidth.
 //
-// MODE 0 (training forward / dgrad): the epilogue above.
+// MODE 0 (training forward): the epilogue above.   MODE 3 (dgrad / plain conv): the same without the statistics.
 // MODE 1 (inference): eval-mode BatchNorm folded into per-channel {scale, shift} (`bias` = scale), ReLU and
 //        MaxPool1d(2) in the epilogue -- the two time steps of a pool pair are adjacent TMEM lanes = adjacent
 //        threads, which swap half of their 32 channels with one shuffle each -- and only the POOLED bf16 rows go
@@ -442,8 +442,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __nv_bfloat16* __
                     float bv[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) bv[i] = bias != nullptr ? __ldg(bias + c0 + i) : 0.f;
-                    float sh[MODE != 0 ? 32 : 1];
-                    if constexpr (MODE != 0) {
+                    float sh[(MODE == 1 || MODE == 2) ? 32 : 1];
+                    if constexpr (MODE == 1 || MODE == 2) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) sh[i] = __ldg(shift + c0 + i);
                     }
@@ -457,7 +457,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __nv_bfloat16* __
                         float v[32];
                         tc::tmem_ld32(taddr, v);
                         tc::tmem_ld_wait();
-                        if constexpr (MODE != 0) {
+                        if constexpr (MODE == 1 || MODE == 2) {
                             // relu(scale * conv + shift), then max over the pool pair (lanes 2p, 2p+1): the even lane
                             // keeps channels 0-15 of the block, the odd lane 16-31
                             const bool even = (lane & 1) == 0;
@@ -507,10 +507,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __nv_bfloat16* __
                             for (int j = 0; j < 4; ++j) {
                                 const int c = 8 * i + 2 * j;
                                 pk[j] = tc::pack_bf16(v[c] + bv[c], v[c + 1] + bv[c + 1]);
-                                const float2 rr = tc::unpack_bf16(pk[j]);      // the value the next kernels will read
-                                if (live) {
-                                    vs[c] += rr.x; qs[c] = fmaf(rr.x, rr.x, qs[c]);
-                                    vs[c + 1] += rr.y; qs[c + 1] = fmaf(rr.y, rr.y, qs[c + 1]);
+                                if constexpr (MODE == 0) {
+                                    const float2 rr = tc::unpack_bf16(pk[j]);  // the value the next kernels will read
+                                    if (live) {
+                                        vs[c] += rr.x; qs[c] = fmaf(rr.x, rr.x, qs[c]);
+                                        vs[c + 1] += rr.y; qs[c + 1] = fmaf(rr.y, rr.y, qs[c + 1]);
+                                    }
                                 }
                             }
                             if (live)
@@ -658,6 +660,8 @@ static int conv_tc_launch(const void* xb, const void* wprep, const float* bias, 
 extern "C" int ecgb200_conv1d_fwd_stats_bf16(const void* xb, const void* wprep, const float* bias, void* yb,
                                              float* stat_part, int B, int Ci, int Co, int L, void* stream) {
     if (!xb || !wprep || !yb || B <= 0 || L <= 0) return ECGB200_EINVAL;
+    // no statistics wanted (dgrad, plain forward): the instantiation without the 64 column-sum accumulators
+    if (stat_part == nullptr) return conv_tc_launch<3>(xb, wprep, bias, nullptr, yb, nullptr, B, Ci, Co, L, stream);
     return conv_tc_launch<0>(xb, wprep, bias, nullptr, yb, stat_part, B, Ci, Co, L, stream);
 }
 
