@@ -110,6 +110,21 @@ def multimodal_forward(sd: StateDict, x: Tensor, d: Tensor, train: bool = False,
     return logits
 
 
+def concat_forward(sd: StateDict, x: Tensor, d: Tensor) -> Tensor:
+    """Legacy concat-fusion model, eval mode.  PARITY UNPINNED: the reference ships only this
+    model's checkpoints (outputs/ecg_demo/ckpts/ecg_demo_2025120618*_best.pth), not its source; the forward is
+    reconstructed from the state_dict keys/shapes -- ecg_encoder = ECGCNN (features z, ecg_cnn.py:66-67),
+    demo_encoder.net = Linear, ReLU, Linear, ReLU (the idiom of ecg_multimodal.py:50-55), classifier = Linear(320,256),
+    ReLU, Dropout (identity in eval), Linear(256,5)."""
+    enc = {k[len("ecg_encoder."):]: v for k, v in sd.items() if k.startswith("ecg_encoder.")}
+    _, z = ecgcnn_forward(enc, x, train=False, return_features=True)
+    h = F.relu(F.linear(d, sd["demo_encoder.net.0.weight"], sd["demo_encoder.net.0.bias"]))
+    h = F.relu(F.linear(h, sd["demo_encoder.net.2.weight"], sd["demo_encoder.net.2.bias"]))
+    f = torch.cat([z, h], dim=1)
+    f = F.relu(F.linear(f, sd["classifier.0.weight"], sd["classifier.0.bias"]))
+    return F.linear(f, sd["classifier.3.weight"], sd["classifier.3.bias"])
+
+
 def bce_with_logits(logits: Tensor, y: Tensor) -> Tensor:
     """Mean over all B*C elements; src/training/loop.py:32, loop_demo.py:10,33."""
     return F.binary_cross_entropy_with_logits(logits, y)

@@ -3,7 +3,7 @@ PTB-XL 1D-CNN ECG models of cyu0330/ptbxl-multimodal.  Importing the package loa
 libecgb200.so; there is no CPU or library fallback."""
 from ._lib import lib, EcgB200Error, EXPORTED  # noqa: F401
 from .ecg_cnn import ECGCNN, ConvBlock, B200Conv1d  # noqa: F401
-from .ecg_multimodal import ECGMultimodal, ECGBackbone, DemoEncoder  # noqa: F401
+from .ecg_multimodal import ECGMultimodal, ECGBackbone, DemoEncoder, ECGDemoConcat  # noqa: F401
 from .grad_cam_1d import GradCAM1D, gradcam_batch, compute_demo_importance  # noqa: F401
 from .loop import train_one_epoch, eval_one_epoch  # noqa: F401
 from .loop_demo import train_one_epoch_demo, eval_one_epoch_demo  # noqa: F401

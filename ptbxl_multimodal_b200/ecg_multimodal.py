@@ -67,3 +67,48 @@ class ECGMultimodal(nn.Module):
         film = Fn.linear(h_demo, self.film_gen.weight, self.film_gen.bias)
         z_cond = Fn.FilmFn.apply(z_ecg, film)          # (1 + tanh(gamma)) * z + beta
         return Fn.linear(z_cond, self.head.weight, self.head.bias)
+
+
+class _LegacyDemoEncoder(nn.Module):
+    """demo_encoder.net of the legacy concat-fusion checkpoints: Linear(5, 32) -> ReLU -> Linear(32, 64) -> ReLU."""
+
+    def __init__(self, demo_dim: int = 5, hidden_dim: int = 32, out_dim: int = 64):
+        super().__init__()
+        self.net = nn.Sequential(nn.Linear(demo_dim, hidden_dim), nn.ReLU(inplace=True),
+                                 nn.Linear(hidden_dim, out_dim), nn.ReLU(inplace=True))
+
+    def forward(self, x_demo: torch.Tensor) -> torch.Tensor:
+        h = Fn.linear(x_demo, self.net[0].weight, self.net[0].bias, act=1)
+        return Fn.linear(h, self.net[2].weight, self.net[2].bias, act=1)
+
+
+class ECGDemoConcat(nn.Module):
+    """Legacy concat-fusion model: logits = classifier(cat[z_ecg, demo_encoder(x_demo)]).
+
+    The reference no longer ships this model's source -- only its checkpoints
+    (outputs/ecg_demo/ckpts/ecg_demo_20251206_184339_best.pth, ..._213901_best.pth, ecg_demo_best.pth) -- so the
+    module tree is RECONSTRUCTED from their state_dict keys and shapes: ``ecg_encoder`` = ECGCNN including its
+    (unused here) head, ``demo_encoder.net`` = Linear(5,32), [1], Linear(32,64)[, 3], ``classifier`` =
+    Linear(256+64, 256), [1], [2], Linear(256, num_labels).  The parameter-free slots are taken to be ReLU
+    (net.1, net.3, classifier.1) and Dropout (classifier.2), the idiom of the reference's other models
+    (ecg_multimodal.py:50-55).  PARITY UNPINNED: no source, no shipped prediction of this model exists
+    (outputs/ecg_demo/preds/ecg_demo_test_preds.csv is byte-identical to the FiLM model's file); what is tested is
+    strict loading of those checkpoints' key/shape manifest and equality with the same reconstruction in torch."""
+
+    def __init__(self, in_leads: int = 12, feat_dim: int = 256, demo_dim: int = 5, num_labels: int = 5,
+                 demo_hidden_dim: int = 32, demo_out_dim: int = 64, fusion_hidden_dim: int = 256,
+                 dropout: float = 0.3):
+        super().__init__()
+        from .ecg_cnn import ECGCNN
+        self.ecg_encoder = ECGCNN(in_leads=in_leads, feat_dim=feat_dim, num_labels=num_labels)
+        self.demo_encoder = _LegacyDemoEncoder(demo_dim, demo_hidden_dim, demo_out_dim)
+        self.classifier = nn.Sequential(nn.Linear(feat_dim + demo_out_dim, fusion_hidden_dim), nn.ReLU(inplace=True),
+                                        nn.Dropout(dropout), nn.Linear(fusion_hidden_dim, num_labels))
+
+    def forward(self, x_ecg: torch.Tensor, x_demo: torch.Tensor) -> torch.Tensor:
+        _, z = self.ecg_encoder(x_ecg, return_features=True)
+        d = self.demo_encoder(x_demo)
+        h = torch.cat([z, d], dim=1).contiguous()
+        h = Fn.linear(h, self.classifier[0].weight, self.classifier[0].bias, act=1)
+        h = self.classifier[2](h)                      # identity in eval mode
+        return Fn.linear(h, self.classifier[3].weight, self.classifier[3].bias)

@@ -255,5 +255,15 @@ def main():
     print("wrote", len(out), "arrays")
 
 
+def legacy_concat_manifest():
+    """Key / shape / dtype manifest of the legacy concat-fusion checkpoint (the model's source is not
+    in the reference, so the manifest is the only pin): tests/golden/legacy_concat_manifest.json."""
+    import json
+    sd = torch.load(f"{REF}/outputs/ecg_demo/ckpts/ecg_demo_best.pth", map_location="cpu")["model_state"]
+    with open(os.path.join(HERE, "legacy_concat_manifest.json"), "w") as f:
+        json.dump({k: [list(v.shape), str(v.dtype).replace("torch.", "")] for k, v in sd.items()}, f, indent=0)
+
+
 if __name__ == "__main__":
     main()
+    legacy_concat_manifest()

@@ -95,3 +95,25 @@ def test_product_does_not_import_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "oracle" not in src.replace("# oracle", ""), fn
+
+
+def test_legacy_concat_model_matches_the_checkpoint_manifest():
+    """the reconstructed concat-fusion module has exactly the legacy checkpoints' state_dict
+    (tests/golden/legacy_concat_manifest.json, generated from outputs/ecg_demo/ckpts/ecg_demo_best.pth) and loads
+    such a state_dict strictly."""
+    import json
+    import os
+    import torch
+    import ptbxl_multimodal_b200 as P
+    from conftest import GOLDEN
+    with open(os.path.join(GOLDEN, "legacy_concat_manifest.json")) as f:
+        man = json.load(f)
+    model = P.ECGDemoConcat()
+    sd = model.state_dict()
+    assert list(sd.keys()) == list(man.keys())
+    for k, (shape, dtype) in man.items():
+        assert list(sd[k].shape) == shape and str(sd[k].dtype) == "torch." + dtype, k
+    g = torch.Generator().manual_seed(0)
+    fake = {k: (torch.randn(shape, generator=g) if dtype == "float32" else torch.zeros(shape, dtype=torch.int64))
+            for k, (shape, dtype) in man.items()}
+    model.load_state_dict(fake, strict=True)

@@ -493,3 +493,22 @@ def test_eval_counts_match_sklearn():
     assert (c[:, 0] == (y_pred & yt).sum(0)).all() and (c[:, 1] == (y_pred & (1 - yt)).sum(0)).all()
     assert (c[:, 2] == ((1 - y_pred) & yt).sum(0)).all() and (c.sum(1) == 1000).all()
     assert abs(f1_macro_from_counts(c) - f1_score(yt, y_pred, average="macro", zero_division=0)) < 1e-12
+
+
+def test_legacy_concat_fusion_model_equals_its_reconstruction():
+    """SURVEY 8f N4 (parity unpinned: the reference ships no source for this model): the ecgb200 module equals
+    the oracle's torch restatement of the same reconstruction, forward and w.r.t. the demographic input."""
+    torch.manual_seed(11)
+    model = P.ECGDemoConcat().to(DEV).eval()
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    x = gen(5, 12, 1000, seed=61)
+    d = gen(5, 5, seed=62).abs()
+    ref = O.concat_forward(sd, x, d)
+    dg = d.to(DEV).requires_grad_(True)
+    logits = model(x.to(DEV), dg)
+    assert rel_inf(logits, ref) < TOL, rel_inf(logits, ref)
+    logits[:, 2].sum().backward()
+    dr = d.clone().requires_grad_(True)
+    O.concat_forward(sd, x, dr)[:, 2].sum().backward()
+    assert rel_inf(dg.grad, dr.grad) < TOL
+    assert model.classifier[0].weight.grad is not None and model.ecg_encoder.proj.weight.grad is not None
