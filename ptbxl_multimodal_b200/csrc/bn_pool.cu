@@ -5,6 +5,7 @@
 // max_pool2d_with_indices(+_backward), adaptive_avg_pool1d reached from
 // /root/reference/src/models/ecg_cnn.py:14-16,46,62.
 #include "common.cuh"
+#include <cstdlib>
 
 // bn_state layout: [0:C) mean, [C:2C) rstd, [2C:3C) scale = gamma*rstd, [3C:4C) shift = beta - mean*scale
 
@@ -686,6 +687,7 @@ bn_bwd_reduce_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__
                           const uint4* __restrict__ dp, const float* __restrict__ dgap,
                           float* __restrict__ part, int B, int C, int L, int Lp, int tile_b) {
     __shared__ float sh[8 * 16];
+    ecg_pdl_launch_dependents();            // the apply kernel may be scheduled (and run its prologue) under this one
     const int cc = blockIdx.x, NS = gridDim.y;
     const int b0 = blockIdx.y * tile_b, nb = min(tile_b, B - b0);
     const float inv_lp = 1.0f / (float)Lp;
@@ -759,6 +761,7 @@ bn_bwd_apply_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__ 
     const int cc = blockIdx.x, NS = gridDim.y;
     const int b0 = blockIdx.y * tile_b, nb = min(tile_b, B - b0);
     const float inv_lp = 1.0f / (float)Lp;
+    ecg_pdl_wait();                         // `part` comes from the reduce kernel launched just before
     merge_parts8(part, NS, C, cc, shd, mom);
     if (threadIdx.x < 8) {
         const int c = cc * 8 + threadIdx.x;
@@ -1028,8 +1031,10 @@ extern "C" int ecgb200_bn_relu_pool_bwd_bf16(const void* yb, const float* bn_sta
     int rc = ecg_launch_status();
     if (rc) return rc;
     const float inv_n = 1.0f / ((float)B * (float)L);
-    bn_bwd_apply_bf16_kernel<<<dim3(C / 8, NS), 256, 0, st>>>((const uint4*)yb, bn_state, (const uint4*)dpb, dgap,
-                                                             part, (uint4*)dyb, dgamma, dbeta, db_part, B, C, L, Lp,
-                                                             inv_n, train, tile_b);
-    return ecg_launch_status();
+    // programmatic dependent launch of the apply pass: its blocks are scheduled while the reduce pass drains and
+    // wait (griddepcontrol.wait = full completion + flush of the reduce kernel) before they read `part`
+    static const bool pdl = getenv("ECGB200_BN_PDL") == nullptr || atoi(getenv("ECGB200_BN_PDL")) != 0;
+    return ecg_launch_pdl_if(pdl, bn_bwd_apply_bf16_kernel, dim3(C / 8, NS), dim3(256), 0, st, (const uint4*)yb, bn_state,
+                             (const uint4*)dpb, dgap, (const float*)part, (uint4*)dyb, dgamma, dbeta, db_part, B, C, L, Lp,
+                             inv_n, train, tile_b);
 }

@@ -28,16 +28,21 @@ __device__ __forceinline__ void ecg_pdl_wait() { asm volatile("griddepcontrol.wa
 __device__ __forceinline__ void ecg_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 template <typename... KP, typename... KA>
-static inline int ecg_launch_pdl(void (*kernel)(KP...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, KA... args) {
+static inline int ecg_launch_pdl_if(bool on, void (*kernel)(KP...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                    KA... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = g_ecg_pdl ? 1 : 0;
+    cfg.numAttrs = on ? 1 : 0;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
     return e == cudaSuccess ? ecg_launch_status() : (int)e;
+}
+template <typename... KP, typename... KA>
+static inline int ecg_launch_pdl(void (*kernel)(KP...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, KA... args) {
+    return ecg_launch_pdl_if(g_ecg_pdl != 0, kernel, grid, block, smem, st, args...);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

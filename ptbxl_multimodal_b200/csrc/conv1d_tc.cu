@@ -603,6 +603,8 @@ static int conv2_cfg(int B, int Ci, int Co, int L, Conv2Cfg* P, size_t* smem_out
         if (resident ? R * (P->kch / 16) <= 4 : ng >= nsm) break;
     }
     if (const char* e = getenv("ECGB200_CONV_R")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) bestR = v; }
+    if (!resident)
+        if (const char* e = getenv("ECGB200_CONV_R_STREAM")) { const int v = atoi(e); if (v == 1 || v == 2) bestR = v; }
     if (bestR * Co > 512) bestR = 512 / Co;
     P->R = bestR;
     P->AS = 2 * bestR * Co <= 512 ? 2 : 1;
