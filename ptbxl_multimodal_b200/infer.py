@@ -171,6 +171,7 @@ class InferStep:
             self.A = torch.empty(B, c4, L4, dtype=F32, device=self.dev)
             self.bnst4 = torch.empty(4, c4, dtype=F32, device=self.dev)
         self.xs[0][:n].copy_(x, non_blocking=True)
+        self.rows[0] = n
         check(lib.ecgb200_pack_input_bf16(_p(self.xs[0]), _p(self.acts[0]), B, self.chan[0], self.T, st), "pack")
         for l in range(3):
             check(lib.ecgb200_conv1d_bn_relu_pool_infer_bf16(

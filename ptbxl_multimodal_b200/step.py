@@ -481,7 +481,17 @@ class TrainStep:
         blocks = list(self.bb.backbone)
         # ---- forward
         if self.bf16:
-            n += self._fwd_blocks_bf16(st, pre, Pp, blocks)
+            # ECGB200_PDL=fwd: programmatic dependent launch for the forward chain only (no weight-gradient branch
+            # competes for SM slots there)
+            import os
+            fwd_pdl = self.use_graph and os.environ.get("ECGB200_PDL", "0") == "fwd"
+            if fwd_pdl:
+                old_pdl = lib.ecgb200_set_pdl(1)
+            try:
+                n += self._fwd_blocks_bf16(st, pre, Pp, blocks)
+            finally:
+                if fwd_pdl:
+                    lib.ecgb200_set_pdl(old_pdl)
         else:
             n += self._fwd_blocks_fp32(st, pre, Pp, blocks)
         self._prof_tag = ""

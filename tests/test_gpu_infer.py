@@ -274,3 +274,26 @@ def test_gradcam_batch_on_the_bf16_engine(demo_inputs):
     # the fp32 module path on the same inputs (exact peaks) for comparison of the two modes
     cam32, arg32 = P.gradcam_batch(model, xs.to(DEV), signal_length=5000)
     assert float((cam32.cpu() - ref).abs().max()) < 1e-3
+
+
+@pytest.mark.parametrize("kind,nl,B,T", [("cnn", 5, 256, 1000), ("cnn", 1, 64, 5000), ("mm", 5, 256, 1000)])
+def test_engine_at_benchmark_sizes_vs_fp32_module_path(kind, nl, B, T):
+    """BASELINE.json sizes (configs 2-4, one rank's share): the bf16 engine against the fp32-exact module forward of the
+    same model on the same device (itself pinned to the CPU oracle at 1e-4 in test_gpu_parity.py), plus size-independent
+    properties: per-window independence (a permuted batch gives permuted logits, bit for bit) and prob = sigmoid(logits)."""
+    sd = O.init_state_dict(kind, nl, seed=42)
+    _randomise_bn(sd, 3)
+    model = (P.ECGMultimodal() if kind == "mm" else P.ECGCNN(12, 256, nl))
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV).eval()
+    x = gen(B, 12, T, seed=71).to(DEV)
+    demo = gen(B, 5, seed=72).abs().to(DEV) if kind == "mm" else None
+    with torch.no_grad():
+        ref = model(x) if demo is None else model(x, demo)
+    eng = P.InferStep(model, B, T)
+    logits = eng(x, demo).clone()
+    assert rel_inf(logits, ref) < 2e-2, rel_inf(logits, ref)
+    assert torch.allclose(eng.prob, torch.sigmoid(logits), atol=1e-6)
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(1)).to(DEV)
+    again = eng(x[perm].contiguous(), None if demo is None else demo[perm].contiguous())
+    assert torch.equal(again, logits[perm])
