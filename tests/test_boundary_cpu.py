@@ -117,3 +117,18 @@ def test_legacy_concat_model_matches_the_checkpoint_manifest():
     fake = {k: (torch.randn(shape, generator=g) if dtype == "float32" else torch.zeros(shape, dtype=torch.int64))
             for k, (shape, dtype) in man.items()}
     model.load_state_dict(fake, strict=True)
+
+
+def test_engines_refuse_cpu_models():
+    """No CPU fallback: the CUDA-graph engines raise on a CPU model before touching the library."""
+    import pytest
+    import ptbxl_multimodal_b200 as P
+    from ptbxl_multimodal_b200.step import TrainStep
+    model = P.ECGCNN(12, 256, 5)
+    with pytest.raises(P.EcgB200Error):
+        P.InferStep(model, 4, 1000)
+    with pytest.raises(P.EcgB200Error):
+        P.InferStep(object(), 4, 1000)
+    opt = P.FusedAdamW(model.parameters(), lr=1e-3)
+    with pytest.raises(P.EcgB200Error):
+        TrainStep(model, opt, 4, 1000)
