@@ -15,9 +15,21 @@ def _logits(out):
     return out[0] if isinstance(out, tuple) else out
 
 
-def train_one_epoch(model, loader, optimizer, device) -> float:
+def train_one_epoch(model, loader, optimizer, device, engine=None) -> float:
+    """`engine`: optional ecgb200 TrainStep built for (model, optimizer, batch size): every step is then one CUDA-graph
+    replay (zero_grad, forward, BCE, backward, AdamW).  The engine has static shapes: the loader must yield full batches
+    (drop_last=True)."""
     model.train()
     total = torch.zeros((), dtype=torch.float64, device=device)
+    if engine is not None:
+        n = 0
+        for x, y in loader:
+            if x.shape[0] != engine.B:
+                raise ValueError(f"TrainStep was built for batches of {engine.B} windows, the loader produced {x.shape[0]}: "
+                                 "use drop_last=True")
+            total += engine(x, y).double() * x.size(0)            # device scalar: no per-step sync
+            n += x.size(0)
+        return float(total.item()) / max(n, 1)
     for x, y in loader:
         x = x.to(device, non_blocking=True)
         y = y.to(device, non_blocking=True)

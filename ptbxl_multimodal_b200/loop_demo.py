@@ -8,10 +8,19 @@ from . import functional as Fn
 from .metrics import compute_metrics
 
 
-def train_one_epoch_demo(model, loader, optimizer, device):
+def train_one_epoch_demo(model, loader, optimizer, device, engine=None):
+    """`engine`: optional ecgb200 TrainStep built for (model, optimizer, batch size); needs full batches (drop_last=True)."""
     model.train()
     total = torch.zeros((), dtype=torch.float64, device=device)
     num_batches = 0
+    if engine is not None:
+        for x_ecg, x_demo, y in loader:
+            if x_ecg.shape[0] != engine.B:
+                raise ValueError(f"TrainStep was built for batches of {engine.B} windows, the loader produced "
+                                 f"{x_ecg.shape[0]}: use drop_last=True")
+            total += engine(x_ecg, y, x_demo).double()
+            num_batches += 1
+        return float(total.item()) / max(1, num_batches)
     for x_ecg, x_demo, y in loader:
         x_ecg = x_ecg.to(device, non_blocking=True)
         x_demo = x_demo.to(device, non_blocking=True)

@@ -178,3 +178,30 @@ def test_bf16_engine_at_benchmark_sizes(nl, B, T):
         worst = max(worst, c)
         assert c < 3e-2, (k, c)
     print(f"bf16 vs fp32 engine at B={B}, T={T}: logits rel_inf {rel_inf(lg16, lg32):.2e}, worst gradient 1-cos {worst:.2e}")
+
+
+def test_reference_shaped_loops_run_on_the_engines():
+    """train_one_epoch(..., engine=TrainStep) / eval_one_epoch(..., engine=InferStep): same return contracts as the
+    reference loops (loop.py:14-38,41-73); the engine epoch equals the same steps driven by hand."""
+    B, T, n = 8, 1000, 24
+    xs = torch.randn(n, 12, T, generator=torch.Generator().manual_seed(3))
+    ys = (torch.rand(n, 5, generator=torch.Generator().manual_seed(4)) < 0.3).float()
+    loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(xs, ys), batch_size=B, drop_last=True)
+    model = _mk("cnn", 5)
+    opt = P.FusedAdamW(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    eng = TrainStep(model, opt, B, T, precision="bf16")
+    loss = P.train_one_epoch(model, loader, opt, DEV, engine=eng)
+    m2 = _mk("cnn", 5)
+    o2 = P.FusedAdamW(m2.parameters(), lr=1e-3, weight_decay=1e-4)
+    e2 = TrainStep(m2, o2, B, T, precision="bf16")
+    tot = 0.0
+    for x, y in loader:
+        tot += float(e2(x.to(DEV), y.to(DEV))) * B
+    assert abs(loss - tot / n) < 1e-6 * max(1.0, abs(loss))
+    for (k, a), (_, b) in zip(model.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
+    metrics = P.eval_one_epoch(model, loader, DEV, engine=P.InferStep(model, B, T))
+    assert set(metrics) == {"auroc_macro", "auprc_macro", "f1_macro", "bce_loss"}
+    ragged = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(xs[:12], ys[:12]), batch_size=B)
+    with pytest.raises(ValueError):
+        P.train_one_epoch(model, ragged, opt, DEV, engine=eng)
