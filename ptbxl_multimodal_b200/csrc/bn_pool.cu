@@ -615,17 +615,29 @@ bn_fwd_train_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__ 
             float acc[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-            for (int j = lane; j < Lp; j += 32) {
-                float a0[8], a1[8], m[8];
-                bf8_unpack(__ldg(y + row * L + 2 * j), a0);
-                bf8_unpack(__ldg(y + row * L + 2 * j + 1), a1);
+            for (int j0 = lane; j0 < Lp; j0 += 64) {
+                uint4 u0[2], u1[2];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float r0 = fmaxf(fmaf(a0[i], sc[i], sf[i]), 0.f), r1 = fmaxf(fmaf(a1[i], sc[i], sf[i]), 0.f);
-                    m[i] = fmaxf(r0, r1);
-                    acc[i] += m[i];
+                for (int e = 0; e < 2; ++e) {
+                    const int j = min(j0 + 32 * e, Lp - 1);
+                    u0[e] = __ldg(y + row * L + 2 * j);
+                    u1[e] = __ldg(y + row * L + 2 * j + 1);
                 }
-                if (p != nullptr) p[row * Lp + j] = bf8_pack(m);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int j = j0 + 32 * e;
+                    if (j >= Lp) break;
+                    float a0[8], a1[8], m[8];
+                    bf8_unpack(u0[e], a0);
+                    bf8_unpack(u1[e], a1);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float r0 = fmaxf(fmaf(a0[i], sc[i], sf[i]), 0.f), r1 = fmaxf(fmaf(a1[i], sc[i], sf[i]), 0.f);
+                        m[i] = fmaxf(r0, r1);
+                        acc[i] += m[i];
+                    }
+                    if (p != nullptr) p[row * Lp + j] = bf8_pack(m);
+                }
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc[i] = warp_sum(acc[i]);
