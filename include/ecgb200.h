@@ -121,6 +121,18 @@ int ecgb200_bn_relu_pool_bwd_bf16(const void* yb, const float* bn_state, const v
 /* The same backward as ONE cooperative launch (reduce -> grid barrier -> apply from a shared-memory copy of the
  * block's slice).  ecgb200_bn_bwd_fused_nsplit returns the second dim of db_part for it, or 0 when the slice does
  * not fit shared memory for this shape (then use the two-kernel call above). */
+/* dgrad of block l+1 fused with the first pass of block l's BatchNorm backward: dpb = conv(dyb, wd) as
+ * ecgb200_conv1d_fwd_bf16, and part[parts][2][Co] (parts = ecgb200_conv1d_stat_parts_bf16(B,Ci,Co,L)) = per-CTA
+ * {sum g, sum g*a}: g = dp routed through MaxPool1d(2)/ReLU of block l (conv output y_prev [B][Co/8][L_prev][8],
+ * L == L_prev/2, bn_state_prev {mean,rstd,scale,shift}).  The second pass then takes the partials directly
+ * (autograd of ecg_cnn.py:13-16, same result as the reduce + apply pair above). */
+int ecgb200_conv1d_dgrad_bnstats_bf16(const void* dyb, const void* wd, void* dpb, const void* y_prev,
+                                      const float* bn_state_prev, float* part, int B, int Ci, int Co,
+                                      int L, int L_prev, void* stream);
+int ecgb200_bn_relu_pool_bwd_apply_bf16(const void* yb, const float* bn_state, const void* dpb,
+                                        const float* part, int nparts, void* dyb, float* dgamma,
+                                        float* dbeta, float* db_part, int B, int C, int L, int train,
+                                        void* stream);
 int ecgb200_bn_relu_pool_bwd_fused_bf16(const void* yb, const float* bn_state, const void* dpb, const float* dgap,
                                         void* dyb, float* dgamma, float* dbeta, float* db_part, void* ws,
                                         int B, int C, int L, int train, void* stream);

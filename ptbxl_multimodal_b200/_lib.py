@@ -69,6 +69,8 @@ _SIGS = {
     "ecgb200_debug_set_trace": (_I, [_P]),
     "ecgb200_debug_set_diag": (_I, [_P]),
     "ecgb200_adamw_flat_f32": (_I, [_P, _P, _P, _P, C.c_int64, _P, _P, _P]),
+    "ecgb200_conv1d_dgrad_bnstats_bf16": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "ecgb200_bn_relu_pool_bwd_apply_bf16": (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "ecgb200_bn_fold_f32": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _F, _P]),
     "ecgb200_conv1d_bn_relu_pool_infer_bf16": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "ecgb200_infer_head_f32": (_I, [_P, _I, _F] + [_P] * 14 + [_I] * 6 + [_P]),

@@ -766,7 +766,7 @@ bn_bwd_apply_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__ 
                          const uint4* __restrict__ dp, const float* __restrict__ dgap,
                          const float* __restrict__ part, uint4* __restrict__ dy, float* __restrict__ dgamma,
                          float* __restrict__ dbeta, float* __restrict__ db_part, int B, int C, int L, int Lp,
-                         float inv_n, int train, int tile_b) {
+                         float inv_n, int train, int tile_b, int nparts) {
     __shared__ float sh[8 * 8];
     __shared__ float cA[8], cB[8];
     __shared__ double shd[32 * 16], mom[16];
@@ -774,7 +774,7 @@ bn_bwd_apply_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__ 
     const int b0 = blockIdx.y * tile_b, nb = min(tile_b, B - b0);
     const float inv_lp = 1.0f / (float)Lp;
     ecg_pdl_wait();                         // `part` comes from the reduce kernel launched just before
-    merge_parts8(part, NS, C, cc, shd, mom);
+    merge_parts8(part, nparts > 0 ? nparts : NS, C, cc, shd, mom);     // nparts > 0: partials of conv_tc_kernel<4>
     if (threadIdx.x < 8) {
         const int c = cc * 8 + threadIdx.x;
         const double sg = mom[threadIdx.x], sga = mom[8 + threadIdx.x];
@@ -1048,5 +1048,20 @@ extern "C" int ecgb200_bn_relu_pool_bwd_bf16(const void* yb, const float* bn_sta
     static const bool pdl = getenv("ECGB200_BN_PDL") == nullptr || atoi(getenv("ECGB200_BN_PDL")) != 0;
     return ecg_launch_pdl_if(pdl, bn_bwd_apply_bf16_kernel, dim3(C / 8, NS), dim3(256), 0, st, (const uint4*)yb, bn_state,
                              (const uint4*)dpb, dgap, (const float*)part, (uint4*)dyb, dgamma, dbeta, db_part, B, C, L, Lp,
-                             inv_n, train, tile_b);
+                             inv_n, train, tile_b, 0);
+}
+
+// Second pass only: `part` [nparts][2][C] = {sum g, sum g*a} partials already produced by the dgrad of the block above
+// (ecgb200_conv1d_dgrad_bnstats_bf16).  Same outputs as ecgb200_bn_relu_pool_bwd_bf16; db_part is [C][ecgb200_bn_nsplit].
+extern "C" int ecgb200_bn_relu_pool_bwd_apply_bf16(const void* yb, const float* bn_state, const void* dpb,
+                                                   const float* part, int nparts, void* dyb, float* dgamma,
+                                                   float* dbeta, float* db_part, int B, int C, int L, int train,
+                                                   void* stream) {
+    if (!yb || !bn_state || !dpb || !part || nparts <= 0 || !dyb || B <= 0 || C <= 0 || (C & 7) || L < 2) return ECGB200_EINVAL;
+    const int Lp = L / 2;
+    const int tile_b = bnb_tile_b(B, C, 3), NS = (B + tile_b - 1) / tile_b;
+    const float inv_n = 1.0f / ((float)B * (float)L);
+    return ecg_launch_pdl_if(false, bn_bwd_apply_bf16_kernel, dim3(C / 8, NS), dim3(256), 0, (cudaStream_t)stream,
+                             (const uint4*)yb, bn_state, (const uint4*)dpb, (const float*)nullptr, part, (uint4*)dyb, dgamma,
+                             dbeta, db_part, B, C, L, Lp, inv_n, train, tile_b, nparts);
 }

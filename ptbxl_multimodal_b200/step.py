@@ -218,6 +218,17 @@ class TrainStep:
                              for l in range(4)]
             self.ndb = [self.bn_fused[l] or lib.ecgb200_bn_nsplit(B, self.chan[l + 1]) for l in range(4)]
             self.dbpart = [e(self.chan[l + 1], self.ndb[l]) for l in range(4)]
+            # Option (off): dgrad of block l+1 also produces block l's BatchNorm-backward sums in its epilogue
+            # (conv_tc_kernel<4>), so that the separate reduce launch disappears.  Measured SLOWER at batch 256 (0.462 vs
+            # 0.431 ms/step): each dgrad grows by 10.5 us -- as much as the reduce kernel it replaces -- and that time is
+            # spent in the exposed, SM-exclusive epilogue of a tensor kernel, while the reduce kernel could share the SMs
+            # with the weight-gradient branch.  ECGB200_BN_DGRAD_FUSE=1 enables it.
+            self.bn_dgrad_fuse = os.environ.get("ECGB200_BN_DGRAD_FUSE", "0") == "1" and not use
+            self.nbw = [lib.ecgb200_conv1d_stat_parts_bf16(B, self.chan[l + 2], self.chan[l + 1], self.L[l + 1])
+                        if self.bn_dgrad_fuse else 0 for l in range(3)]
+            if self.bn_dgrad_fuse and min(self.nbw) <= 0:
+                self.bn_dgrad_fuse = False
+            self.bwpart = [e(self.nbw[l], 2, self.chan[l + 1]) if self.bn_dgrad_fuse else None for l in range(3)]
             self.stat = [None] * 4
             # per-CTA {sum, sumsq} partials written by the conv epilogue
             self.nstat = [lib.ecgb200_conv1d_stat_parts_bf16(B, self.cip[l], self.chan[l + 1], self.L[l]) for l in range(4)]
@@ -382,11 +393,18 @@ class TrainStep:
             dy = dys[l & 1]
             if wg_done[l & 1] is not None:
                 main.wait_event(wg_done[l & 1])                # wgrad of block l+2 has finished reading this dy
-            self._k("bn_bwd", lib.ecgb200_bn_relu_pool_bwd_fused_bf16 if self.bn_fused[l] else lib.ecgb200_bn_relu_pool_bwd_bf16,
-                    _p(self.ybuf[l]), _p(self.bnst[l]),
-                    _p(self.dp) if l < 3 else None, _p(self.dgap) if l == 3 else None, _p(dy),
-                    Gp(k + "1.weight"), Gp(k + "1.bias"), _p(self.dbpart[l]), _p(self.ws2), B, co, L, 1, st)
-            n += 1 if self.bn_fused[l] else 2
+            if self.bn_dgrad_fuse and l < 3:
+                # the sums came out of dgrad_{l+1}'s epilogue: second pass only
+                self._k("bn_bwd", lib.ecgb200_bn_relu_pool_bwd_apply_bf16, _p(self.ybuf[l]), _p(self.bnst[l]), _p(self.dp),
+                        _p(self.bwpart[l]), self.nbw[l], _p(dy), Gp(k + "1.weight"), Gp(k + "1.bias"), _p(self.dbpart[l]),
+                        B, co, L, 1, st)
+                n += 1
+            else:
+                self._k("bn_bwd", lib.ecgb200_bn_relu_pool_bwd_fused_bf16 if self.bn_fused[l] else lib.ecgb200_bn_relu_pool_bwd_bf16,
+                        _p(self.ybuf[l]), _p(self.bnst[l]),
+                        _p(self.dp) if l < 3 else None, _p(self.dgap) if l == 3 else None, _p(dy),
+                        Gp(k + "1.weight"), Gp(k + "1.bias"), _p(self.dbpart[l]), _p(self.ws2), B, co, L, 1, st)
+                n += 1 if self.bn_fused[l] else 2
             # Order matters: the tensor kernels cannot share an SM (TMEM + shared memory), so whichever of dgrad_l
             # (critical path) and wgrad_l (side) the graph launches first takes the GPU, and ready nodes are launched in
             # creation order.  Measured (same box, us/step): wgrad node created first ("early") 476 -- or 456 when a
@@ -400,8 +418,7 @@ class TrainStep:
                 ev_bn = torch.cuda.Event()
                 ev_bn.record(main)
             if l > 0 and not early:
-                self._k("dgrad", lib.ecgb200_conv1d_fwd_bf16, _p(dy), _p(self.wd[l]), None, _p(self.dp),
-                        B, co, ci, L, st)
+                self._dgrad(l, dy, st)
                 n += 1
             if ev_bn is not None and not self.linear:
                 self.side.wait_event(ev_bn)
@@ -420,10 +437,19 @@ class TrainStep:
                         torch.distributed.all_reduce(self.G[self.bucket_a_off:], group=self.pg)
             n += 2
             if l > 0 and early:
-                self._k("dgrad", lib.ecgb200_conv1d_fwd_bf16, _p(dy), _p(self.wd[l]), None, _p(self.dp),
-                        B, co, ci, L, st)
+                self._dgrad(l, dy, st)
                 n += 1
         return n
+
+    def _dgrad(self, l, dy, st):
+        """Input gradient of block l (= dp of block l-1); with bn_dgrad_fuse its epilogue also leaves block l-1's
+        BatchNorm-backward sums in bwpart[l-1]."""
+        B, ci, co, L = self.B, self.chan[l], self.chan[l + 1], self.L[l]
+        if self.bn_dgrad_fuse:
+            self._k("dgrad", lib.ecgb200_conv1d_dgrad_bnstats_bf16, _p(dy), _p(self.wd[l]), _p(self.dp), _p(self.ybuf[l - 1]),
+                    _p(self.bnst[l - 1]), _p(self.bwpart[l - 1]), B, co, ci, L, self.L[l - 1], st)
+        else:
+            self._k("dgrad", lib.ecgb200_conv1d_fwd_bf16, _p(dy), _p(self.wd[l]), None, _p(self.dp), B, co, ci, L, st)
 
     def _bwd_blocks(self, st, pre, Pp, Gp):
         B = self.B

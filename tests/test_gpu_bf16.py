@@ -378,3 +378,63 @@ def test_fused_multimodal_head(B):
     for (w, b), (kw, kb) in zip(zip(dw, db), (("wp", "bp"), ("wh", "bh"), ("wf", "bf"), ("w2", "b2"), ("w0", "b0"))):
         assert rel_inf(w, L[kw].grad) < tol, kw
         assert rel_inf(b, L[kb].grad) < tol, kb
+
+
+@pytest.mark.parametrize("B,Cn,C,Lprev", [(3, 64, 32, 1000), (2, 128, 64, 500), (3, 256, 128, 250), (2, 256, 128, 251),
+                                          (1, 64, 32, 41), (256, 64, 32, 1000), (200, 256, 128, 250)])
+def test_dgrad_with_bn_backward_sums_equals_separate_reduce(B, Cn, C, Lprev):
+    """conv_tc_kernel<4>: dgrad of block l+1 whose epilogue also produces block l's {sum g, sum g*a} == plain dgrad
+    (bit-exact dp) followed by bn_bwd_reduce (sums to fp32 round-off), and the apply pass fed with those partials
+    gives the reduce + apply pair's dy / dgamma / dbeta."""
+    L = Lprev // 2
+    y = gen(B, C, Lprev, seed=5) * 1.7 + 0.3
+    gamma, beta = (1 + 0.2 * gen(C, seed=6)).to(DEV), (0.1 * gen(C, seed=7)).to(DEV)
+    gamma[::5] *= -1.0
+    yb = to_blocked(y).to(DEV)
+    rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    nbt = torch.zeros((), dtype=torch.int64, device=DEV)
+    st = torch.empty(4, C, device=DEV)
+    ws = torch.zeros(lib.ecgb200_bn_bwd_ws_bytes(B, C), dtype=torch.uint8, device=DEV)
+    check(lib.ecgb200_bn_train_stats_bf16(ptr(yb), ptr(gamma), ptr(beta), ptr(rm), ptr(rv), ptr(nbt), ptr(st), ptr(ws),
+                                          B, C, Lprev, 0.1, 1e-5, stream()), "stats")
+    # dgrad of the block above: dy (B, Cn, L) with weights (Cn, C, 15)
+    w = gen(Cn, C, 15, seed=3, scale=0.05).to(DEV)
+    wf = torch.empty(15, C // 8, Cn, 8, dtype=BF, device=DEV)
+    wd = torch.empty(15, Cn // 8, C, 8, dtype=BF, device=DEV)
+    check(lib.ecgb200_conv1d_prep_weights_bf16(ptr(w), ptr(wf), ptr(wd), Cn, C, stream()), "prep")
+    dyn = to_blocked(gen(B, Cn, L, seed=8)).to(DEV)
+    dp0 = torch.full((B, C // 8, L, 8), float("nan"), dtype=BF, device=DEV)
+    check(lib.ecgb200_conv1d_fwd_bf16(ptr(dyn), ptr(wd), None, ptr(dp0), B, Cn, C, L, stream()), "dgrad")
+    nparts = lib.ecgb200_conv1d_stat_parts_bf16(B, Cn, C, L)
+    assert nparts > 0
+    part = torch.full((nparts, 2, C), float("nan"), device=DEV)
+    dp1 = torch.full((B, C // 8, L, 8), float("nan"), dtype=BF, device=DEV)
+    check(lib.ecgb200_conv1d_dgrad_bnstats_bf16(ptr(dyn), ptr(wd), ptr(dp1), ptr(yb), ptr(st), ptr(part), B, Cn, C, L,
+                                                Lprev, stream()), "dgrad_bnstats")
+    torch.cuda.synchronize()
+    assert torch.equal(dp0, dp1)
+    assert torch.isfinite(part).all()
+    # reference path: reduce + apply on the same dp
+    nsp = lib.ecgb200_bn_nsplit(B, C)
+    outs = []
+    for fused in (False, True):
+        dyb = torch.full((B, C // 8, Lprev, 8), float("nan"), dtype=BF, device=DEV)
+        dgm, dbt = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+        dbp = torch.empty(C, nsp, device=DEV)
+        if fused:
+            check(lib.ecgb200_bn_relu_pool_bwd_apply_bf16(ptr(yb), ptr(st), ptr(dp1), ptr(part), nparts, ptr(dyb), ptr(dgm),
+                                                          ptr(dbt), ptr(dbp), B, C, Lprev, 1, stream()), "apply")
+        else:
+            check(lib.ecgb200_bn_relu_pool_bwd_bf16(ptr(yb), ptr(st), ptr(dp0), None, ptr(dyb), ptr(dgm), ptr(dbt),
+                                                    ptr(dbp), ptr(ws), B, C, Lprev, 1, stream()), "bn_bwd")
+        torch.cuda.synchronize()
+        outs.append((dyb.float().cpu(), dgm.cpu(), dbt.cpu(), dbp.sum(dim=1).cpu()))
+    ref_part = ws.view(torch.float32)[:nsp * 2 * C].view(nsp, 2, C).sum(dim=0).cpu()
+    got_part = part.sum(dim=0).cpu()
+    assert rel_inf(got_part[0], ref_part[0]) < 1e-5 and rel_inf(got_part[1], ref_part[1]) < 1e-5
+    (dy0, g0, b0, s0), (dy1, g1, b1, s1) = outs
+    assert torch.isfinite(dy1).all()
+    assert rel_inf(g1, g0) < 1e-5 and rel_inf(b1, b0) < 1e-5
+    assert rel_inf(dy1, dy0) < 8e-3                      # same math, different partial-sum grouping: bf16 ties
+    assert float((dy1 != dy0).float().mean()) < 1e-3
+    assert float((s1 - s0).abs().max()) <= 1e-3 * float(s0.abs().max()) + 1e-2
