@@ -126,3 +126,21 @@ def test_explicit_forms():
     cam = torch.rand(3, 125, generator=g)
     np.testing.assert_allclose(O.linear_upsample(cam, 1000).numpy(),
                                O.linear_upsample_explicit(cam, 1000).numpy(), atol=1e-6)
+
+
+def test_numpy_restatement_matches_the_live_reference_and_shipped_rows(golden, demo_inputs, expected_probs):
+    """oracle/np_oracle.py (the ops themselves in numpy, float64 accumulation) against the golden logits of the
+    unmodified reference (fp32: 2e-5 relative of the largest logit) and the shipped prediction rows."""
+    from oracle import np_oracle as N
+    x, d = demo_inputs
+    xs, ds = x.numpy(), d.numpy()
+    cases = [("ecg_baseline_best.pth", "eval/baseline_logits", "baseline_prob", lambda sd: N.ecgcnn_logits(sd, xs[:4]), slice(0, 4)),
+             ("af_binary_best.pth", "eval/af_logits", "af_prob", lambda sd: N.ecgcnn_logits(sd, xs[:3]), slice(0, 3)),
+             ("ecg_multimodal_best.pth", "eval/mm_logits", "mm_prob", lambda sd: N.multimodal_logits(sd, xs[3:6], ds[:3]), slice(0, 3))]
+    for ckpt, lk, pk, fn, sl in cases:
+        sd = {k: v.numpy() for k, v in load_ckpt(ckpt).items()}
+        logits = fn(sd)
+        ref = golden[lk][sl]
+        assert np.abs(logits - ref).max() < 2e-5 * max(1.0, np.abs(ref).max()), ckpt
+        exp = np.array(expected_probs[pk])[sl]
+        assert np.abs(N.sigmoid(logits) - exp).max() < 5e-4, ckpt
