@@ -63,7 +63,7 @@ class _Records:
 class Wfdb16BatchLoader:
     def __init__(self, base_dir: str, rel_paths: Sequence[str], labels, batch_size: int, device,
                  demo=None, normalize: str = "per_lead", shuffle: bool = False, seed: int = 0,
-                 drop_last: bool = False, depth: int = 2, n_leads: int = 12):
+                 drop_last: bool = False, depth: int = 2, n_leads: int = 12, rank: int = 0, world_size: int = 1):
         if len(rel_paths) == 0:
             raise EcgB200Error("no records")
         if batch_size <= 0 or depth < 2:
@@ -73,6 +73,11 @@ class Wfdb16BatchLoader:
         self.B, self.depth, self.n_leads = int(batch_size), int(depth), int(n_leads)
         self.shuffle, self.seed, self.drop_last = bool(shuffle), int(seed), bool(drop_last)
         self.normalize = normalize == "per_lead"
+        # data parallel: every rank builds the same loader and reads its own interleaved share of each epoch's order
+        # (equal counts on all ranks, so that the collective steps line up; the remainder is dropped)
+        if world_size < 1 or not (0 <= rank < world_size):
+            raise EcgB200Error("need 0 <= rank < world_size")
+        self.rank, self.world = int(rank), int(world_size)
         self.epoch = 0
         h = read_header(self.paths[0])
         if h.n_sig != n_leads:
@@ -90,16 +95,20 @@ class Wfdb16BatchLoader:
             if demo.shape[0] != len(self.paths):
                 raise EcgB200Error("one demographic row per record")
             self.demo = demo.to(self.device) if self.cuda else demo
-        self.dataset = _Records(len(self.paths))
+        self.dataset = _Records(len(self.paths) // self.world)      # what this rank sees per epoch
         self._hdr_ok = np.zeros(len(self.paths), dtype=bool)      # headers are checked once, not once per epoch
 
     def __len__(self) -> int:
-        n = len(self.paths)
+        n = len(self.paths) // self.world
         return n // self.B if self.drop_last else (n + self.B - 1) // self.B
 
     def _batches(self) -> List[np.ndarray]:
         n = len(self.paths)
         order = np.random.default_rng(self.seed + self.epoch).permutation(n) if self.shuffle else np.arange(n)
+        if self.world > 1:
+            per = n // self.world
+            order = order[:per * self.world][self.rank::self.world]
+            n = per
         out = [order[i:i + self.B] for i in range(0, n, self.B)]
         if self.drop_last and out and len(out[-1]) < self.B:
             out.pop()

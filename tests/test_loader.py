@@ -130,3 +130,24 @@ def test_loader_end_to_end_matches_oracle_and_feeds_the_eval_loops(tmp_path):
     loss = P.train_one_epoch(model, ld2, opt, "cuda:0")
     m = P.eval_one_epoch(model, ld2, "cuda:0", engine=P.InferStep(model, 8, 1000))
     assert np.isfinite(loss) and np.isfinite(m["bce_loss"]) and "auroc_macro" in m
+
+
+def test_rank_shards_are_disjoint_equal_and_cover_the_epoch(records):
+    from ptbxl_multimodal_b200.loader import Wfdb16BatchLoader
+    base, rels, frames = records
+    y = np.zeros((11, 5), dtype=np.float32)
+    seen = []
+    for r in range(3):
+        ld = Wfdb16BatchLoader(base, rels, y, 2, "cpu", shuffle=True, seed=9, rank=r, world_size=3)
+        assert len(ld.dataset) == 3 and len(ld) == 2
+        mine = []
+        for buf, idx, _ in ld.iter_host_batches():
+            for j, rec in enumerate(idx):
+                assert np.array_equal(buf[j], frames[rec])
+            mine += [int(i) for i in idx]
+        assert len(mine) == 3
+        seen.append(mine)
+    flat = sum(seen, [])
+    assert len(set(flat)) == 9                                   # disjoint; 11 // 3 * 3 records per epoch
+    with pytest.raises(Exception):
+        Wfdb16BatchLoader(base, rels, y, 2, "cpu", rank=3, world_size=3)
