@@ -64,3 +64,74 @@ def multimodal_logits(sd, x, d):
 
 def sigmoid(x):
     return 1.0 / (1.0 + np.exp(-x))
+
+
+# ------------------------------------------------------------------ one training step of ECGCNN in numpy (float64)
+# forward in train mode (batch statistics, biased variance; BatchNorm1d at ecg_cnn.py:14), mean BCE-with-logits
+# (loop.py:32), the full backward pass and one AdamW update (loop.py:33-34; torch.optim.AdamW defaults betas (0.9, 0.999),
+# eps 1e-8, decoupled weight decay).  Pinned to the reference's golden step-0 loss / logits / gradients / updated weights.
+def conv1d_k15_backward(x, w, dy):
+    bsz, ci, L = x.shape
+    co, _, k = w.shape
+    pad = k // 2
+    xp = np.zeros((bsz, ci, L + 2 * pad)); xp[:, :, pad:pad + L] = x
+    dxp = np.zeros_like(xp)
+    dw = np.zeros(w.shape)
+    w64 = w.astype(np.float64)
+    for kk in range(k):
+        dw[:, :, kk] = np.einsum("bot,bct->oc", dy, xp[:, :, kk:kk + L], optimize=True)
+        dxp[:, :, kk:kk + L] += np.einsum("oc,bot->bct", w64[:, :, kk], dy, optimize=True)
+    return dxp[:, :, pad:pad + L], dw, dy.sum(axis=(0, 2))
+
+
+def train_step_cnn(sd, x, y, lr, wd, step=1, m=None, v=None):
+    """Returns (loss, logits, grads dict, updated parameter dict) for one step from state `sd` (numpy arrays)."""
+    x = x.astype(np.float64); y = y.astype(np.float64)
+    cache = []
+    h = x
+    for i in range(4):
+        p = f"backbone.{i}."
+        w, b = sd[p + "net.0.weight"], sd[p + "net.0.bias"]
+        a = conv1d_k15(h, w, b)
+        mean = a.mean(axis=(0, 2)); var = a.var(axis=(0, 2))                       # biased, as batch_norm normalises
+        rstd = 1.0 / np.sqrt(var + EPS)
+        xhat = (a - mean[None, :, None]) * rstd[None, :, None]
+        g = sd[p + "net.1.weight"].astype(np.float64); be = sd[p + "net.1.bias"].astype(np.float64)
+        r = np.maximum(xhat * g[None, :, None] + be[None, :, None], 0.0)
+        lp = r.shape[2] // 2
+        r0, r1 = r[:, :, 0:2 * lp:2], r[:, :, 1:2 * lp:2]
+        pooled = np.maximum(r0, r1)
+        cache.append((h, w, xhat, rstd, g, r, r0 >= r1, lp))                       # first index wins ties
+        h = pooled
+    gap = h.mean(axis=2)
+    z = linear(gap, sd["proj.weight"], sd["proj.bias"])
+    logits = linear(z, sd["head.weight"], sd["head.bias"])
+    loss = np.mean(np.maximum(logits, 0) - logits * y + np.log1p(np.exp(-np.abs(logits))))
+    grads = {}
+    dlog = (sigmoid(logits) - y) / logits.size
+    grads["head.weight"] = dlog.T @ z; grads["head.bias"] = dlog.sum(0)
+    dz = dlog @ sd["head.weight"].astype(np.float64)
+    grads["proj.weight"] = dz.T @ gap; grads["proj.bias"] = dz.sum(0)
+    dgap = dz @ sd["proj.weight"].astype(np.float64)
+    dp = np.repeat(dgap[:, :, None], h.shape[2], axis=2) / h.shape[2]
+    for i in (3, 2, 1, 0):
+        p = f"backbone.{i}."
+        hin, w, xhat, rstd, g, r, first, lp = cache[i]
+        dr = np.zeros_like(r)
+        dr[:, :, 0:2 * lp:2] = np.where(first, dp, 0.0)
+        dr[:, :, 1:2 * lp:2] = np.where(first, 0.0, dp)
+        dr = dr * (r > 0)
+        grads[p + "net.1.weight"] = (dr * xhat).sum(axis=(0, 2)); grads[p + "net.1.bias"] = dr.sum(axis=(0, 2))
+        n = dr.shape[0] * dr.shape[2]
+        dxhat = dr * g[None, :, None]
+        da = (dxhat - dxhat.sum(axis=(0, 2))[None, :, None] / n
+              - xhat * (dxhat * xhat).sum(axis=(0, 2))[None, :, None] / n) * rstd[None, :, None]
+        dp, grads[p + "net.0.weight"], grads[p + "net.0.bias"] = conv1d_k15_backward(hin, w, da)
+    new = {}
+    b1, b2, eps = 0.9, 0.999, 1e-8
+    for k, gk in grads.items():
+        pk = sd[k].astype(np.float64) * (1.0 - lr * wd)
+        mk = (1 - b1) * gk if m is None else b1 * m[k] + (1 - b1) * gk
+        vk = (1 - b2) * gk * gk if v is None else b2 * v[k] + (1 - b2) * gk * gk
+        new[k] = pk - lr / (1 - b1 ** step) * mk / (np.sqrt(vk) / np.sqrt(1 - b2 ** step) + eps)
+    return loss, logits, grads, new

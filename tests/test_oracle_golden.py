@@ -144,3 +144,34 @@ def test_numpy_restatement_matches_the_live_reference_and_shipped_rows(golden, d
         assert np.abs(logits - ref).max() < 2e-5 * max(1.0, np.abs(ref).max()), ckpt
         exp = np.array(expected_probs[pk])[sl]
         assert np.abs(N.sigmoid(logits) - exp).max() < 5e-4, ckpt
+
+
+def test_numpy_train_step_matches_the_live_reference(golden):
+    """oracle/np_oracle.train_step_cnn (train-mode BatchNorm, BCE, the whole backward pass and AdamW in numpy float64)
+    against step 0 of the unmodified reference's golden trajectory: loss, logits, every gradient, and -- through the
+    torch oracle, itself pinned to the same trajectory -- the updated weights."""
+    from oracle import np_oracle as N
+    tag = "train_cnn"
+    B, T, nl, lr, wd, steps = golden[f"{tag}/cfg"]
+    sd_t = O.init_state_dict("cnn", int(nl), seed=42)
+    sd = {k: v.numpy() for k, v in sd_t.items()}
+    x, y = golden[f"{tag}/x"], golden[f"{tag}/y"]
+    loss, logits, grads, new = N.train_step_cnn(sd, x, y, float(lr), float(wd))
+    assert abs(loss - float(golden[f"{tag}/step0/loss"])) < 1e-6
+    np.testing.assert_allclose(logits, golden[f"{tag}/step0/logits"], rtol=1e-4, atol=1e-5)
+    for k, g in grads.items():
+        if k.endswith("net.0.bias"):
+            # a conv bias in front of a train-mode BatchNorm has an exactly zero gradient: the reference holds fp32
+            # round-off (~1e-9) there, and Adam turns that noise into a +-lr step -- nothing to compare
+            assert np.abs(g).max() < 1e-7, k
+            continue
+        _check_sig(golden, f"{tag}/step0/grad", k, torch.from_numpy(g))
+    st = O.AdamWState(sd_t, float(lr), float(wd))
+    O.train_step(sd_t, torch.from_numpy(x), torch.from_numpy(y), st)
+    for k, v in new.items():
+        if k.endswith("net.0.bias"):
+            continue
+        ref = sd_t[k].double().numpy()
+        # the first Adam step moves every weight by ~lr * g / (|g| + eps): entries whose gradient sits at the fp32 noise
+        # floor move by a different fraction of lr in float64 -- bound the difference by a tenth of one step
+        assert np.abs(v - ref).max() <= 0.1 * float(lr), k
