@@ -132,3 +132,32 @@ def test_engines_refuse_cpu_models():
     opt = P.FusedAdamW(model.parameters(), lr=1e-3)
     with pytest.raises(P.EcgB200Error):
         TrainStep(model, opt, 4, 1000)
+
+
+def test_committed_bench_lines_follow_the_driver_contract():
+    """The bench lines kept under profiles/ carry every key the driver / judge read (bench.py's JSON contract)."""
+    import glob
+    import json
+    import os
+    from conftest import ROOT
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_bench_v8_final.json")) +
+                   glob.glob(os.path.join(ROOT, "profiles", "r01_bench_n*_v2.json")))
+    assert files
+    for f in files:
+        with open(f) as fh:
+            d = json.loads(fh.read().strip().splitlines()[-1])
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                  "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"):
+            assert k in d, (f, k)
+        assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
+        assert "workload" in d["config"] and d["dtype"] == "bf16" and d["data"] == "synthetic"
+        assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
+        assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["gpu_launches"] > 0
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        if d["n_gpus"] == 1:
+            assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
+            assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9
+    with open(os.path.join(ROOT, "profiles", "r01_bench_reference_arm.json")) as fh:
+        r = json.loads(fh.read().strip().splitlines()[-1])
+    assert r["impl"] == "reference" and r["e2e"]["h2d_bytes_per_step"] == 0 and r["cpu_baseline"]["kind"] == "port"
