@@ -94,11 +94,13 @@ int ecgb200_conv1d_fwd_stats_bf16(const void* xb, const void* wprep, const float
 int ecgb200_conv1d_stat_parts_bf16(int B, int Ci, int Co, int L);
 /* Train-mode BatchNorm1d + ReLU + MaxPool1d(2) (+GAP) in ONE pass over yb: finalises the statistics from
  * the conv partials (mean, biased var -> bn_state {mean,rstd,scale,shift}; running stats with momentum and
- * the unbiased variance; *num_batches_tracked += 1), then applies them.  ecg_cnn.py:14-16,46,62. */
+ * the unbiased variance; *num_batches_tracked += 1), then applies them.  ecg_cnn.py:14-16,46,62.
+ * nrep = number of replicas whose B*L samples stat_part covers: 1, or the world size after
+ * ecgb200_dp_bn_sync_f32 (SyncBN: statistics over the global batch, as the single-device reference). */
 int ecgb200_bn_relu_pool_fwd_train_bf16(const void* yb, const float* stat_part, int nparts, const float* gamma,
                                         const float* beta, float* running_mean, float* running_var,
                                         int64_t* num_batches_tracked, float* bn_state, void* pb, float* gap,
-                                        int B, int C, int L, float momentum, float eps, void* stream);
+                                        int B, int C, int L, float momentum, float eps, int nrep, void* stream);
 
 /* dW (Co,Ci,15) fp32 and db (Co) fp32 from blocked-bf16 dy [B][Co/8][L][8] and x [B][Cip/8][L][8]
  * (Cip = Ci rounded up to 16) on tcgen05, accumulators resident in TMEM across the whole batch
@@ -118,25 +120,17 @@ int ecgb200_bn_relu_pool_fwd_bf16(const void* yb, const float* bn_state, void* p
 int ecgb200_bn_relu_pool_bwd_bf16(const void* yb, const float* bn_state, const void* dpb, const float* dgap,
                                   void* dyb, float* dgamma, float* dbeta, float* db_part, void* ws,
                                   int B, int C, int L, int train, void* stream);
-/* The same backward as ONE cooperative launch (reduce -> grid barrier -> apply from a shared-memory copy of the
- * block's slice).  ecgb200_bn_bwd_fused_nsplit returns the second dim of db_part for it, or 0 when the slice does
- * not fit shared memory for this shape (then use the two-kernel call above). */
-/* dgrad of block l+1 fused with the first pass of block l's BatchNorm backward: dpb = conv(dyb, wd) as
- * ecgb200_conv1d_fwd_bf16, and part[parts][2][Co] (parts = ecgb200_conv1d_stat_parts_bf16(B,Ci,Co,L)) = per-CTA
- * {sum g, sum g*a}: g = dp routed through MaxPool1d(2)/ReLU of block l (conv output y_prev [B][Co/8][L_prev][8],
- * L == L_prev/2, bn_state_prev {mean,rstd,scale,shift}).  The second pass then takes the partials directly
- * (autograd of ecg_cnn.py:13-16, same result as the reduce + apply pair above). */
-int ecgb200_conv1d_dgrad_bnstats_bf16(const void* dyb, const void* wd, void* dpb, const void* y_prev,
-                                      const float* bn_state_prev, float* part, int B, int Ci, int Co,
-                                      int L, int L_prev, void* stream);
+/* The two passes of that backward as separate calls (SyncBN under data parallel): pass 1 leaves this replica's
+ * partials part[ecgb200_bn_nsplit(B,C)][2][C] = {sum g, sum g*a}; after ecgb200_dp_bn_sync_f32 pass 2 takes the
+ * exchanged list (one pair per replica): batch means over all nrep replicas' B*L samples, dgamma / dbeta from pair
+ * local_idx (this replica's own) only -- the gradient exchange sums them.  local_idx < 0: affine gradients from the
+ * merged sums (single device).  Autograd of torch.nn.SyncBatchNorm semantics for ecg_cnn.py:14-16. */
+int ecgb200_bn_relu_pool_bwd_reduce_bf16(const void* yb, const float* bn_state, const void* dpb,
+                                         const float* dgap, float* part, int B, int C, int L, void* stream);
 int ecgb200_bn_relu_pool_bwd_apply_bf16(const void* yb, const float* bn_state, const void* dpb,
-                                        const float* part, int nparts, void* dyb, float* dgamma,
-                                        float* dbeta, float* db_part, int B, int C, int L, int train,
-                                        void* stream);
-int ecgb200_bn_relu_pool_bwd_fused_bf16(const void* yb, const float* bn_state, const void* dpb, const float* dgap,
-                                        void* dyb, float* dgamma, float* dbeta, float* db_part, void* ws,
+                                        const float* dgap, const float* part, int nparts, int local_idx,
+                                        int nrep, void* dyb, float* dgamma, float* dbeta, float* db_part,
                                         int B, int C, int L, int train, void* stream);
-int ecgb200_bn_bwd_fused_nsplit(int B, int C, int L, int has_dp);
 /* number of per-channel partials the bf16 BN kernels produce (second dim of db_part) */
 int ecgb200_bn_nsplit(int B, int C);
 
@@ -273,6 +267,20 @@ int ecgb200_dp_adamw_fused_f32(float* const* p, const float* const* g, unsigned 
                                float* v, int64_t n, int rank, int world, const float* hyper, const int* step_now,
                                void* stream);
 int ecgb200_dp_flag_words(int world);
+/* The same for ONE BUCKET [off, off + n) of the flat space (off % 4 == 0, n % (4*world) == 0; rank r owns the r-th
+ * 1/world of the bucket), so that the block-4 parameters -- 65 % of the bytes, final as soon as wgrad_4 is -- are
+ * exchanged and stepped while blocks 3..1 still run backward.  One flag pad per bucket. */
+int ecgb200_dp_adamw_fused_range_f32(float* const* p, const float* const* g, unsigned int* const* flags, float* m,
+                                     float* v, int64_t off, int64_t n, int rank, int world, const float* hyper,
+                                     const int* step_now, void* stream);
+/* SyncBN statistics exchange over NVLink peer memory (one tiny launch per BatchNorm pass): reduces this replica's
+ * local_part[nparts][2][C] to one pair, publishes it in slots[rank] (>= 2*C floats of peer-mapped memory), passes a
+ * cross-rank barrier and gathers all replicas' pairs in rank order into out[world][2][C] (device memory of this
+ * rank), which the BatchNorm kernels merge like per-CTA partials (nparts = nrep = world).  A slot must not be reused
+ * before a later cross-rank barrier (the optimizer exchange); flags: one pad shared by all BatchNorm exchanges.
+ * Gives the reference's single-device batch statistics (ecg_cnn.py:14) under data parallel.  C <= 256. */
+int ecgb200_dp_bn_sync_f32(const float* local_part, int nparts, int C, float* const* slots,
+                           unsigned int* const* flags, float* out, int rank, int world, void* stream);
 
 /* Programmatic dependent launch for the kernels of the bf16 step's critical path (conv, BatchNorm forward): when on,
  * they are launched with cudaLaunchAttributeProgrammaticStreamSerialization and overlap their prologue with the
@@ -283,9 +291,20 @@ int ecgb200_set_pdl(int on);
 /* Debug only: when buf != NULL, CTA 0 of the bf16 conv kernel writes clock64() stamps of its pipeline
  * events into buf[0..63] (device memory).  NULL switches tracing off (the default). */
 int ecgb200_debug_set_trace(long long* buf);
-/* Debug only: pinned (device-visible) host buffer of >= 4 words; a barrier wait that exceeds its 2 s deadlock
+/* Debug only: when buf != NULL every CTA of the tcgen05 conv / wgrad kernels writes %globaltimer (ns) at its first
+ * and after its last instruction to buf[2 * linear block id + {0, 1}] (launch ramp, spread and tail of a grid). */
+int ecgb200_debug_set_cta_span(unsigned long long* buf);
+/* Debug only: pinned (device-visible) host buffer of >= 4 words; a barrier wait that exceeds its deadlock
  * limit records {0xDEAD, block<<32|thread, smem address<<32|parity} there before the kernel traps. */
 int ecgb200_debug_set_diag(unsigned long long* pinned_host);
+/* Limits of the bounded spin waits, in milliseconds, 0 = wait for ever: `mbarrier_ms` for the producer / issuer /
+ * epilogue barriers inside the tcgen05 kernels (default 30 s), `peer_ms` for the cross-rank flag waits of
+ * ecgb200_dp_adamw_fused_f32 / ecgb200_dp_bn_sync_f32 (default 10 min: ranks may drift apart by a validation pass or
+ * a checkpoint write).  A wait that exceeds its limit traps the kernel instead of hanging the GPU. */
+int ecgb200_set_spin_timeout_ms(unsigned int mbarrier_ms, unsigned int peer_ms);
+/* Debug only: one-thread kernel that writes %globaltimer (ns) to buf[idx] in stream order -- placed between the
+ * nodes of a captured step it gives the schedule the graph really runs (TrainStep.trace_schedule). */
+int ecgb200_debug_stamp(unsigned long long* buf, int idx, void* stream);
 
 /* --------------------------------------------------------------- Grad-CAM --
  * All-class batched Grad-CAM from the raw 4th-conv output A (B,C,L') in eval mode,
@@ -317,6 +336,11 @@ int ecgb200_zscore_f32(const float* x, float* out, int rows, int T, void* stream
  * dat (B,T,n_leads) int16 little-endian frames; normalize = 0 returns the physical signal.  n_leads <= 16. */
 int ecgb200_wfdb16_zscore_f32(const void* dat, const float* gain, const int* baseline, float* out, int B,
                               int n_leads, int T, int normalize, void* stream);
+/* The same decode + z-score written straight to the first conv's input: blocked channels-last bf16
+ * xb [B][Cp/8][T][8], Cp = n_leads rounded up to 16 (padding leads zero) -- N1 fused into the input pack; the fp32
+ * (B, leads, T) tensor never exists.  T * n_leads must be even. */
+int ecgb200_wfdb16_zscore_pack_bf16(const void* dat, const float* gain, const int* baseline, void* xb, int B,
+                                    int n_leads, int T, void* stream);
 
 /* ------------------------------------------------- bf16 inference engine (eval) --
  * model.eval() forward of the reference (src/training/loop.py:52-65, loop_demo.py:59-75,

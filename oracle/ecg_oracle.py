@@ -245,9 +245,27 @@ def _rb(t, round_grad=True):
     return _RoundBF16.apply(t, round_grad)
 
 
-def bf16_train_step(sd: StateDict, x: Tensor, y: Tensor, demo: Optional[Tensor] = None):
+class _Replace(torch.autograd.Function):
+    """Forward: the given value; backward: the gradient passes to the tensor it replaces."""
+    @staticmethod
+    def forward(ctx, t, value):
+        return value.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
+def bf16_train_step(sd: StateDict, x: Tensor, y: Tensor, demo: Optional[Tensor] = None,
+                    forced_conv: Optional[Sequence[Tensor]] = None, forced_pool: Optional[Sequence[Tensor]] = None):
     """One forward + backward in the emulated bf16 mode (no optimizer, running stats untouched).
-    Returns dict(loss, logits, grads) like train_step."""
+    Returns dict(loss, logits, grads) like train_step.
+
+    forced_conv / forced_pool: the bf16 conv outputs (4 tensors (B, C, L)) and pooled activations (3 tensors) an
+    implementation under test actually STORED.  They replace this function's own forward values (the gradient still
+    flows through the convolution / the pool), so that every ReLU / MaxPool routing decision and every value a weight
+    gradient multiplies is the implementation's own: what remains between its gradients and the ones returned here is
+    rounding and summation order only, not routing flips at bf16 rounding boundaries."""
     keys = param_keys(sd)
     leaves = {k: sd[k].detach().clone().requires_grad_(True) for k in keys}
     work = dict(sd)
@@ -259,12 +277,16 @@ def bf16_train_step(sd: StateDict, x: Tensor, y: Tensor, demo: Optional[Tensor] 
         p = f"{prefix}backbone.{i}."
         a = F.conv1d(h, _rb(work[p + "net.0.weight"], False), work[p + "net.0.bias"], padding=KSIZE // 2)
         a = _rb(a)                                                # conv output stored as bf16; dy rounded
+        if forced_conv is not None:
+            a = _Replace.apply(a, forced_conv[i])
         bn = F.batch_norm(a, work[p + "net.1.running_mean"].clone(), work[p + "net.1.running_var"].clone(),
                           work[p + "net.1.weight"], work[p + "net.1.bias"], training=True,
                           momentum=BN_MOMENTUM, eps=BN_EPS)
         pooled = F.max_pool1d(F.relu(bn), 2)
         if i < len(CHANNELS) - 1:
             h = _rb(pooled)                                       # next conv's input; dp rounded
+            if forced_pool is not None:
+                h = _Replace.apply(h, forced_pool[i])
         else:
             g = pooled.mean(dim=2)                                # gap from the unrounded fp32 values
     z = F.linear(g, work[prefix + "proj.weight"], work[prefix + "proj.bias"])

@@ -41,6 +41,7 @@ _SIGS = {
     "ecgb200_gradcam_f32": (_I, [_P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P]),
     "ecgb200_zscore_f32": (_I, [_P, _P, _I, _I, _P]),
     "ecgb200_wfdb16_zscore_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "ecgb200_wfdb16_zscore_pack_bf16": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "ecgb200_row_mean_f32": (_I, [_P, _P, _I, _I, _P]),
     "ecgb200_pack_input_bf16": (_I, [_P, _P, _I, _I, _I, _P]),
     "ecgb200_unpack_act_bf16": (_I, [_P, _P, _I, _I, _I, _P]),
@@ -52,11 +53,10 @@ _SIGS = {
     "ecgb200_bn_relu_pool_fwd_bf16": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "ecgb200_bn_relu_pool_bwd_bf16": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "ecgb200_bn_nsplit": (_I, [_I, _I]),
-    "ecgb200_bn_relu_pool_bwd_fused_bf16": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
-    "ecgb200_bn_bwd_fused_nsplit": (_I, [_I, _I, _I, _I]),
+    "ecgb200_bn_relu_pool_bwd_reduce_bf16": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "ecgb200_conv1d_fwd_stats_bf16": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "ecgb200_conv1d_stat_parts_bf16": (_I, [_I, _I, _I, _I]),
-    "ecgb200_bn_relu_pool_fwd_train_bf16": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _P]),
+    "ecgb200_bn_relu_pool_fwd_train_bf16": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _I, _P]),
     "ecgb200_step_prep_bf16": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
     "ecgb200_head_fwd_bwd_f32": (_I, [_P] * 13 + [_I, _I, _I, _I, _F, _P]),
     "ecgb200_head_loss_parts": (_I, [_I]),
@@ -65,12 +65,16 @@ _SIGS = {
     "ecgb200_head_wgrad_f32": (_I, [_P] * 10 + [_I, _I, _I, _I, _P]),
     "ecgb200_dp_adamw_fused_f32": (_I, [_P, _P, _P, _P, _P, C.c_int64, _I, _I, _P, _P, _P]),
     "ecgb200_dp_flag_words": (_I, [_I]),
+    "ecgb200_dp_adamw_fused_range_f32": (_I, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, _I, _I, _P, _P, _P]),
+    "ecgb200_dp_bn_sync_f32": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _P]),
     "ecgb200_set_pdl": (_I, [_I]),
     "ecgb200_debug_set_trace": (_I, [_P]),
     "ecgb200_debug_set_diag": (_I, [_P]),
+    "ecgb200_debug_set_cta_span": (_I, [_P]),
+    "ecgb200_set_spin_timeout_ms": (_I, [C.c_uint, C.c_uint]),
+    "ecgb200_debug_stamp": (_I, [_P, _I, _P]),
     "ecgb200_adamw_flat_f32": (_I, [_P, _P, _P, _P, C.c_int64, _P, _P, _P]),
-    "ecgb200_conv1d_dgrad_bnstats_bf16": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
-    "ecgb200_bn_relu_pool_bwd_apply_bf16": (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "ecgb200_bn_relu_pool_bwd_apply_bf16": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "ecgb200_bn_fold_f32": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _F, _P]),
     "ecgb200_conv1d_bn_relu_pool_infer_bf16": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "ecgb200_infer_head_f32": (_I, [_P, _I, _F] + [_P] * 14 + [_I] * 6 + [_P]),
@@ -110,6 +114,25 @@ def check(rc: int, what: str) -> None:
         if rc > 0:
             raise EcgB200Error(f"{what}: CUDA error {rc} ({torch.cuda.get_device_name() if torch.cuda.is_available() else 'no device'})")
         raise EcgB200Error(f"{what}: invalid/unsupported arguments (code {rc})")
+
+
+_timeouts_done = False
+
+
+def configure_timeouts(force: bool = False) -> None:
+    """Apply ECGB200_SPIN_TIMEOUT_MS="<mbarrier ms>[,<peer ms>]" (0 = never trap) to the bounded spin waits of the
+    kernels; needs a CUDA context, so the engines call it when they are built.  Unset: the library defaults
+    (30 s for in-kernel barriers, 10 min for cross-rank waits)."""
+    global _timeouts_done
+    if _timeouts_done and not force:
+        return
+    _timeouts_done = True
+    spec = os.environ.get("ECGB200_SPIN_TIMEOUT_MS")
+    if not spec:
+        return
+    parts = [int(v) for v in spec.split(",")]
+    mbar, peer = parts[0], parts[1] if len(parts) > 1 else parts[0]
+    check(lib.ecgb200_set_spin_timeout_ms(mbar, peer), "set_spin_timeout")
 
 
 def ptr(t):

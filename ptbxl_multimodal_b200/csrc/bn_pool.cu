@@ -556,7 +556,7 @@ bn_fwd_train_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__ 
                          float* __restrict__ running_mean, float* __restrict__ running_var,
                          int64_t* __restrict__ nbt, float* __restrict__ bn_state, uint4* __restrict__ p,
                          float* __restrict__ gap, int B, int C, int L, int Lp, int tile_b, float momentum,
-                         float eps) {
+                         float eps, int nrep) {
     __shared__ double shd[32 * 16], mom[16];
     __shared__ float scs[8], sfs[8];
     const int cc = blockIdx.x;
@@ -566,7 +566,7 @@ bn_fwd_train_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__ 
     merge_parts8(part, nparts, C, cc, shd, mom);
     if (threadIdx.x < 8) {
         const int c = cc * 8 + threadIdx.x;
-        const double n = (double)B * (double)L;
+        const double n = (double)B * (double)L * (double)nrep;   // nrep > 1: the partials cover nrep replicas (SyncBN)
         const double mean = mom[threadIdx.x] / n;
         double var = mom[8 + threadIdx.x] / n - mean * mean;          // biased
         if (var < 0.0) var = 0.0;
@@ -656,9 +656,9 @@ extern "C" int ecgb200_bn_relu_pool_fwd_train_bf16(const void* yb, const float* 
                                                    const float* gamma, const float* beta, float* running_mean,
                                                    float* running_var, int64_t* nbt, float* bn_state, void* pb,
                                                    float* gap, int B, int C, int L, float momentum, float eps,
-                                                   void* stream) {
+                                                   int nrep, void* stream) {
     if (!yb || !stat_part || nparts <= 0 || !gamma || !beta || !bn_state || (!pb && !gap) || B <= 0 || C <= 0 ||
-        (C & 7) || L < 2)
+        (C & 7) || L < 2 || nrep < 1)
         return ECGB200_EINVAL;
     const int Lp = L / 2;
     const int tile_b = bnb_tile_b(B, C, 4), NS = (B + tile_b - 1) / tile_b;
@@ -666,10 +666,10 @@ extern "C" int ecgb200_bn_relu_pool_fwd_train_bf16(const void* yb, const float* 
     if (gap != nullptr)
         return ecg_launch_pdl(bn_fwd_train_bf16_kernel<true>, dim3(C / 8, NS), dim3(256), 0, st, (const uint4*)yb,
                               stat_part, nparts, gamma, beta, running_mean, running_var, nbt, bn_state, (uint4*)pb, gap,
-                              B, C, L, Lp, tile_b, momentum, eps);
+                              B, C, L, Lp, tile_b, momentum, eps, nrep);
     return ecg_launch_pdl(bn_fwd_train_bf16_kernel<false>, dim3(C / 8, NS), dim3(256), 0, st, (const uint4*)yb,
                           stat_part, nparts, gamma, beta, running_mean, running_var, nbt, bn_state, (uint4*)pb,
-                          (float*)nullptr, B, C, L, Lp, tile_b, momentum, eps);
+                          (float*)nullptr, B, C, L, Lp, tile_b, momentum, eps, nrep);
 }
 
 // Routing of one pool pair in terms of the raw conv outputs a0, a1 (first index wins ties, ReLU mask):
@@ -766,7 +766,7 @@ bn_bwd_apply_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__ 
                          const uint4* __restrict__ dp, const float* __restrict__ dgap,
                          const float* __restrict__ part, uint4* __restrict__ dy, float* __restrict__ dgamma,
                          float* __restrict__ dbeta, float* __restrict__ db_part, int B, int C, int L, int Lp,
-                         float inv_n, int train, int tile_b, int nparts) {
+                         float inv_n, int train, int tile_b, int nparts, int local_idx) {
     __shared__ float sh[8 * 8];
     __shared__ float cA[8], cB[8];
     __shared__ double shd[32 * 16], mom[16];
@@ -774,15 +774,22 @@ bn_bwd_apply_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__ 
     const int b0 = blockIdx.y * tile_b, nb = min(tile_b, B - b0);
     const float inv_lp = 1.0f / (float)Lp;
     ecg_pdl_wait();                         // `part` comes from the reduce kernel launched just before
-    merge_parts8(part, nparts > 0 ? nparts : NS, C, cc, shd, mom);     // nparts > 0: partials of conv_tc_kernel<4>
+    merge_parts8(part, nparts > 0 ? nparts : NS, C, cc, shd, mom);     // nparts > 0: an exchanged (SyncBN) partial list
     if (threadIdx.x < 8) {
         const int c = cc * 8 + threadIdx.x;
         const double sg = mom[threadIdx.x], sga = mom[8 + threadIdx.x];
         const float mean = __ldg(bn_state + c), rstd = __ldg(bn_state + C + c), scl = __ldg(bn_state + 2 * C + c);
         const double sgx = (double)rstd * (sga - (double)mean * sg);       // sum g * xhat
         if (blockIdx.y == 0) {
-            if (dbeta != nullptr) dbeta[c] = (float)sg;
-            if (dgamma != nullptr) dgamma[c] = (float)sgx;
+            // SyncBN (local_idx >= 0): `part` holds one {sum g, sum g*a} pair per replica; the batch means below use all
+            // of them, the affine gradients only this replica's own pair (the gradient exchange sums them over replicas)
+            double lg = sg, lgx = sgx;
+            if (local_idx >= 0) {
+                lg = (double)__ldg(part + ((size_t)local_idx * 2 + 0) * C + c);
+                lgx = (double)rstd * ((double)__ldg(part + ((size_t)local_idx * 2 + 1) * C + c) - (double)mean * lg);
+            }
+            if (dbeta != nullptr) dbeta[c] = (float)lg;
+            if (dgamma != nullptr) dgamma[c] = (float)lgx;
         }
         const float m1 = train ? (float)sg * inv_n : 0.f, m2 = train ? (float)sgx * inv_n : 0.f;
         const float A = -scl * rstd * m2;
@@ -839,193 +846,6 @@ bn_bwd_apply_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__ 
     }
 }
 
-// ---------------------------------------------------------------- fused backward (one cooperative launch)
-// reduce + apply in ONE kernel: every block first copies its slice of (y pair, dp) from L2 into shared
-// memory while accumulating {sum g, sum g*a}; after a grid-wide barrier it merges the partials and produces dy
-// from the shared-memory copy.  Saves a launch, the second read of y / dp and the second prologue per block.
-// Grid = (C/8, NS) with at most 2 blocks per SM resident (cooperative launch: all blocks run concurrently).
-#include <cooperative_groups.h>
-namespace cg = cooperative_groups;
-
-constexpr int BNF_MAX_SLICE = 100 * 1024;      // bytes of shared memory per block (2 blocks per SM)
-
-__host__ __device__ inline int bnf_tile_b(int B, int C) { return bnb_tile_b(B, C, 2); }
-static size_t bnf_slice_bytes(int B, int C, int L, bool has_dp) {
-    const int tb = bnf_tile_b(B, C);
-    return (size_t)tb * (L / 2) * (has_dp ? 48 : 32);
-}
-
-__global__ void __launch_bounds__(256, 2)
-bn_bwd_fused_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__ bn_state,
-                         const uint4* __restrict__ dp, const float* __restrict__ dgap, float* __restrict__ part,
-                         uint4* __restrict__ dy, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                         float* __restrict__ db_part, int B, int C, int L, int Lp, float inv_n, int train, int tile_b) {
-    extern __shared__ __align__(16) uint4 slice[];              // [n][3] = {y[2j], y[2j+1], dp[j]}  ([n][2] with dgap)
-    __shared__ float sh[8 * 16];
-    __shared__ float cA[8], cB[8];
-    __shared__ double shd[32 * 16], mom[16];
-    const int cc = blockIdx.x, NS = gridDim.y;
-    const int b0 = blockIdx.y * tile_b, nb = min(tile_b, B - b0);
-    const int n = nb * Lp;
-    const int stride = dp != nullptr ? 3 : 2;
-    const float inv_lp = 1.0f / (float)Lp;
-    float sc[8], sf[8], s[16];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        sc[i] = __ldg(bn_state + 2 * C + cc * 8 + i);
-        sf[i] = __ldg(bn_state + 3 * C + cc * 8 + i);
-        s[i] = 0.f; s[8 + i] = 0.f;
-    }
-    // ---- pass 1: stream the slice in (two pairs per iteration), keep it in shared memory
-    for (int idx = threadIdx.x; idx < n; idx += 2 * blockDim.x) {
-        const int idx2 = idx + blockDim.x;
-        const bool has2 = idx2 < n;
-        const int bl = idx / Lp, j = idx - bl * Lp;
-        const int bl2 = has2 ? idx2 / Lp : bl, j2 = has2 ? idx2 - bl2 * Lp : j;
-        const size_t row = (size_t)(b0 + bl) * (C / 8) + cc, row2 = (size_t)(b0 + bl2) * (C / 8) + cc;
-        const uint4 u0 = __ldg(y + row * L + 2 * j), u1 = __ldg(y + row * L + 2 * j + 1);
-        const uint4 w0 = __ldg(y + row2 * L + 2 * j2), w1 = __ldg(y + row2 * L + 2 * j2 + 1);
-        uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
-        if (dp != nullptr) { q0 = __ldg(dp + row * Lp + j); q1 = __ldg(dp + row2 * Lp + j2); }
-        slice[(size_t)idx * stride] = u0;
-        slice[(size_t)idx * stride + 1] = u1;
-        if (dp != nullptr) slice[(size_t)idx * stride + 2] = q0;
-        float d[8], a0[8], a1[8];
-        if (dp != nullptr) bf8_unpack(q0, d); else load_dgrad8(nullptr, dgap, row, Lp, j, b0 + bl, C, cc, inv_lp, d);
-        bf8_unpack(u0, a0);
-        bf8_unpack(u1, a1);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            bool s0, s1;
-            pool_sel(a0[i], a1[i], sc[i], sf[i], s0, s1);
-            const float g = (s0 || s1) ? d[i] : 0.f;
-            s[i] += g;
-            s[8 + i] = fmaf(g, s0 ? a0[i] : a1[i], s[8 + i]);
-        }
-        if (has2) {
-            slice[(size_t)idx2 * stride] = w0;
-            slice[(size_t)idx2 * stride + 1] = w1;
-            if (dp != nullptr) slice[(size_t)idx2 * stride + 2] = q1;
-            if (dp != nullptr) bf8_unpack(q1, d); else load_dgrad8(nullptr, dgap, row2, Lp, j2, b0 + bl2, C, cc, inv_lp, d);
-            bf8_unpack(w0, a0);
-            bf8_unpack(w1, a1);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                bool s0, s1;
-                pool_sel(a0[i], a1[i], sc[i], sf[i], s0, s1);
-                const float g = (s0 || s1) ? d[i] : 0.f;
-                s[i] += g;
-                s[8 + i] = fmaf(g, s0 ? a0[i] : a1[i], s[8 + i]);
-            }
-        }
-    }
-    block_sum_vec<16>(s, sh);
-    if (threadIdx.x < 8) {
-        float t1 = 0.f, t2 = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) if (i == threadIdx.x) { t1 = s[i]; t2 = s[8 + i]; }
-        part[((size_t)blockIdx.y * 2 + 0) * C + cc * 8 + threadIdx.x] = t1;
-        part[((size_t)blockIdx.y * 2 + 1) * C + cc * 8 + threadIdx.x] = t2;
-    }
-    __threadfence();
-    cg::this_grid().sync();
-    // ---- merge (identical in every block; block row 0 publishes dgamma / dbeta)
-    merge_parts8(part, NS, C, cc, shd, mom);
-    if (threadIdx.x < 8) {
-        const int c = cc * 8 + threadIdx.x;
-        const double sg = mom[threadIdx.x], sga = mom[8 + threadIdx.x];
-        const float mean = __ldg(bn_state + c), rstd = __ldg(bn_state + C + c), scl = __ldg(bn_state + 2 * C + c);
-        const double sgx = (double)rstd * (sga - (double)mean * sg);       // sum g * xhat
-        if (blockIdx.y == 0) {
-            if (dbeta != nullptr) dbeta[c] = (float)sg;
-            if (dgamma != nullptr) dgamma[c] = (float)sgx;
-        }
-        const float m1 = train ? (float)sg * inv_n : 0.f, m2 = train ? (float)sgx * inv_n : 0.f;
-        const float A = -scl * rstd * m2;
-        cA[threadIdx.x] = A;
-        cB[threadIdx.x] = -scl * m1 - A * mean;
-    }
-    __syncthreads();
-    float A[8], Bc[8], sdy[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { A[i] = cA[i]; Bc[i] = cB[i]; sdy[i] = 0.f; }
-    // ---- pass 2: dy from the shared-memory copy
-    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
-        const int bl = idx / Lp, j = idx - bl * Lp;
-        const size_t row = (size_t)(b0 + bl) * (C / 8) + cc;
-        float a0[8], a1[8], d[8], o0[8], o1[8];
-        bf8_unpack(slice[(size_t)idx * stride], a0);
-        bf8_unpack(slice[(size_t)idx * stride + 1], a1);
-        if (dp != nullptr) bf8_unpack(slice[(size_t)idx * stride + 2], d);
-        else load_dgrad8(nullptr, dgap, row, Lp, j, b0 + bl, C, cc, inv_lp, d);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            bool s0, s1;
-            pool_sel(a0[i], a1[i], sc[i], sf[i], s0, s1);
-            const float gd = sc[i] * d[i];
-            o0[i] = fmaf(A[i], a0[i], Bc[i]) + (s0 ? gd : 0.f);
-            o1[i] = fmaf(A[i], a1[i], Bc[i]) + (s1 ? gd : 0.f);
-            sdy[i] += o0[i] + o1[i];
-        }
-        dy[row * L + 2 * j] = bf8_pack(o0);
-        dy[row * L + 2 * j + 1] = bf8_pack(o1);
-        if (j == Lp - 1 && (L & 1)) {
-            float a[8], o[8];
-            bf8_unpack(__ldg(y + row * L + L - 1), a);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { o[i] = fmaf(A[i], a[i], Bc[i]); sdy[i] += o[i]; }
-            dy[row * L + L - 1] = bf8_pack(o);
-        }
-    }
-    if (db_part != nullptr) {
-        block_sum_vec<8>(sdy, sh);
-        if (threadIdx.x < 8) {
-            float t = 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) if (i == threadIdx.x) t = sdy[i];
-            db_part[(size_t)(cc * 8 + threadIdx.x) * NS + blockIdx.y] = t;
-        }
-    }
-}
-
-// Number of per-channel partials (second dim of db_part) the fused backward produces for this shape, or 0 when
-// the per-block slice does not fit shared memory (then use ecgb200_bn_relu_pool_bwd_bf16 / ecgb200_bn_nsplit).
-extern "C" int ecgb200_bn_bwd_fused_nsplit(int B, int C, int L, int has_dp) {
-    if (B <= 0 || C <= 0 || (C & 7) || L < 2) return 0;
-    if (bnf_slice_bytes(B, C, L, has_dp != 0) > (size_t)BNF_MAX_SLICE) return 0;
-    const int tb = bnf_tile_b(B, C);
-    return (B + tb - 1) / tb;
-}
-
-// Same contract as ecgb200_bn_relu_pool_bwd_bf16, one cooperative launch; db_part is [C][ecgb200_bn_bwd_fused_nsplit].
-extern "C" int ecgb200_bn_relu_pool_bwd_fused_bf16(const void* yb, const float* bn_state, const void* dpb,
-                                                   const float* dgap, void* dyb, float* dgamma, float* dbeta,
-                                                   float* db_part, void* ws, int B, int C, int L, int train,
-                                                   void* stream) {
-    if (!yb || !bn_state || (!dpb && !dgap) || !dyb || !ws || B <= 0 || C <= 0 || (C & 7) || L < 2) return ECGB200_EINVAL;
-    if (dgap != nullptr && (((uintptr_t)dgap & 15) != 0)) return ECGB200_EINVAL;
-    const size_t smem = bnf_slice_bytes(B, C, L, dpb != nullptr);
-    if (smem > (size_t)BNF_MAX_SLICE) return ECGB200_EUNSUPPORTED;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(bn_bwd_fused_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             BNF_MAX_SLICE);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
-    int Lp = L / 2;
-    int tile_b = bnf_tile_b(B, C), NS = (B + tile_b - 1) / tile_b;
-    float inv_n = 1.0f / ((float)B * (float)L);
-    const uint4* y4 = (const uint4*)yb;
-    const uint4* dp4 = (const uint4*)dpb;
-    uint4* dy4 = (uint4*)dyb;
-    float* part = (float*)ws;
-    void* args[] = {&y4, &bn_state, &dp4, &dgap, &part, &dy4, &dgamma, &dbeta, &db_part, &B, &C, &L, &Lp, &inv_n, &train, &tile_b};
-    cudaError_t e = cudaLaunchCooperativeKernel((const void*)bn_bwd_fused_bf16_kernel, dim3(C / 8, NS), dim3(256), args,
-                                                smem, (cudaStream_t)stream);
-    return e == cudaSuccess ? ecg_launch_status() : (int)e;
-}
-
 // yb, dpb, dyb blocked bf16; dgap fp32 (B,C) [layer 4]; db_part fp32 [C][ecgb200_bn_nsplit(B,C)] or
 // NULL; ws: ecgb200_bn_bwd_ws_bytes(B,C).
 extern "C" int ecgb200_bn_relu_pool_bwd_bf16(const void* yb, const float* bn_state, const void* dpb,
@@ -1045,23 +865,38 @@ extern "C" int ecgb200_bn_relu_pool_bwd_bf16(const void* yb, const float* bn_sta
     const float inv_n = 1.0f / ((float)B * (float)L);
     // programmatic dependent launch of the apply pass: its blocks are scheduled while the reduce pass drains and
     // wait (griddepcontrol.wait = full completion + flush of the reduce kernel) before they read `part`
-    static const bool pdl = getenv("ECGB200_BN_PDL") == nullptr || atoi(getenv("ECGB200_BN_PDL")) != 0;
-    return ecg_launch_pdl_if(pdl, bn_bwd_apply_bf16_kernel, dim3(C / 8, NS), dim3(256), 0, st, (const uint4*)yb, bn_state,
+    return ecg_launch_pdl_if(true, bn_bwd_apply_bf16_kernel, dim3(C / 8, NS), dim3(256), 0, st, (const uint4*)yb, bn_state,
                              (const uint4*)dpb, dgap, (const float*)part, (uint4*)dyb, dgamma, dbeta, db_part, B, C, L, Lp,
-                             inv_n, train, tile_b, 0);
+                             inv_n, train, tile_b, 0, -1);
 }
 
-// Second pass only: `part` [nparts][2][C] = {sum g, sum g*a} partials already produced by the dgrad of the block above
-// (ecgb200_conv1d_dgrad_bnstats_bf16).  Same outputs as ecgb200_bn_relu_pool_bwd_bf16; db_part is [C][ecgb200_bn_nsplit].
-extern "C" int ecgb200_bn_relu_pool_bwd_apply_bf16(const void* yb, const float* bn_state, const void* dpb,
-                                                   const float* part, int nparts, void* dyb, float* dgamma,
-                                                   float* dbeta, float* db_part, int B, int C, int L, int train,
-                                                   void* stream) {
-    if (!yb || !bn_state || !dpb || !part || nparts <= 0 || !dyb || B <= 0 || C <= 0 || (C & 7) || L < 2) return ECGB200_EINVAL;
+// The two passes as separate calls, for SyncBN under data parallel: pass 1 leaves this replica's partials
+// part[ecgb200_bn_nsplit(B,C)][2][C] = {sum g, sum g*a}; the caller exchanges them (ecgb200_dp_bn_sync_f32 -> one pair per
+// replica) and pass 2 takes the exchanged list: batch means over all `nrep` replicas' B*L samples, affine gradients from
+// pair `local_idx` (this replica's own) only.
+extern "C" int ecgb200_bn_relu_pool_bwd_reduce_bf16(const void* yb, const float* bn_state, const void* dpb,
+                                                    const float* dgap, float* part, int B, int C, int L,
+                                                    void* stream) {
+    if (!yb || !bn_state || (!dpb && !dgap) || !part || B <= 0 || C <= 0 || (C & 7) || L < 2) return ECGB200_EINVAL;
+    if (dgap != nullptr && (((uintptr_t)dgap & 15) != 0)) return ECGB200_EINVAL;
     const int Lp = L / 2;
     const int tile_b = bnb_tile_b(B, C, 3), NS = (B + tile_b - 1) / tile_b;
-    const float inv_n = 1.0f / ((float)B * (float)L);
+    bn_bwd_reduce_bf16_kernel<<<dim3(C / 8, NS), 256, 0, (cudaStream_t)stream>>>((const uint4*)yb, bn_state, (const uint4*)dpb,
+                                                                                dgap, part, B, C, L, Lp, tile_b);
+    return ecg_launch_status();
+}
+extern "C" int ecgb200_bn_relu_pool_bwd_apply_bf16(const void* yb, const float* bn_state, const void* dpb,
+                                                   const float* dgap, const float* part, int nparts, int local_idx,
+                                                   int nrep, void* dyb, float* dgamma, float* dbeta, float* db_part,
+                                                   int B, int C, int L, int train, void* stream) {
+    if (!yb || !bn_state || (!dpb && !dgap) || !part || nparts <= 0 || local_idx >= nparts || nrep < 1 || !dyb || B <= 0 ||
+        C <= 0 || (C & 7) || L < 2)
+        return ECGB200_EINVAL;
+    if (dgap != nullptr && (((uintptr_t)dgap & 15) != 0)) return ECGB200_EINVAL;
+    const int Lp = L / 2;
+    const int tile_b = bnb_tile_b(B, C, 3), NS = (B + tile_b - 1) / tile_b;
+    const float inv_n = 1.0f / ((float)B * (float)L * (float)nrep);
     return ecg_launch_pdl_if(false, bn_bwd_apply_bf16_kernel, dim3(C / 8, NS), dim3(256), 0, (cudaStream_t)stream,
-                             (const uint4*)yb, bn_state, (const uint4*)dpb, (const float*)nullptr, part, (uint4*)dyb, dgamma,
-                             dbeta, db_part, B, C, L, Lp, inv_n, train, tile_b, nparts);
+                             (const uint4*)yb, bn_state, (const uint4*)dpb, dgap, part, (uint4*)dyb, dgamma,
+                             dbeta, db_part, B, C, L, Lp, inv_n, train, tile_b, nparts, local_idx);
 }

@@ -134,6 +134,8 @@ constexpr int TC_HDR = 1024;        // barriers + TMEM slot
 constexpr int C2_MAXST = 8;         // weight ring depth (max)
 constexpr int C2_STATB = 8 * 2 * 256 * 4;   // per-epilogue-warp {sum, sumsq} x 256 channels
 
+void ecg_set_timeout_conv(unsigned long long ns) { cudaMemcpyToSymbol(tc::g_mbar_timeout_ns, &ns, sizeof(ns)); }
+
 extern "C" int ecgb200_debug_set_diag(unsigned long long* pinned_host) {
     cudaError_t e = cudaMemcpyToSymbol(tc::g_mbar_diag, &pinned_host, sizeof(pinned_host));
     return e == cudaSuccess ? 0 : (int)e;
@@ -146,6 +148,14 @@ extern "C" int ecgb200_debug_set_trace(long long* buf) {
     cudaError_t e = cudaMemcpyToSymbol(g_conv_trace, &buf, sizeof(buf));
     return e == cudaSuccess ? 0 : (int)e;
 }
+// Per-CTA {first instruction, last instruction} %globaltimer stamps of the tcgen05 kernels (buf[2 * linear block id]).
+__device__ unsigned long long* g_cta_span = nullptr;
+extern "C" int ecgb200_debug_set_cta_span(unsigned long long* buf) {
+    cudaError_t e = cudaMemcpyToSymbol(g_cta_span, &buf, sizeof(buf));
+    return e == cudaSuccess ? 0 : (int)e;
+}
+#define CTA_SPAN(which) do { unsigned long long* sp_ = g_cta_span; if (sp_ != nullptr) { \
+    sp_[2 * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) + (which)] = tc::globaltimer_ns(); } } while (0)
 
 struct Conv2Cfg {
     int Ci, Co, L, kch;              // kch = input channels per weight stage
@@ -155,11 +165,6 @@ struct Conv2Cfg {
     int NST;                         // weight ring depth; 0 = whole weight tensor resident in shared memory
     int total_tiles, tiles_t, ngroups;
     uint32_t tmem_cols, xbytes_al;
-    // MODE 4 (dgrad + BatchNorm-backward sums of the block below): that block's conv output, its {scale, shift}, its length
-    const __nv_bfloat16* aux_y;
-    const float* aux_scale;
-    const float* aux_shift;
-    int Laux;
 };
 
 // All MMAs of one weight stage: RC tiles x NJ K-steps, fully unrolled so that every descriptor is
@@ -239,11 +244,6 @@ __device__ __forceinline__ void conv_issue_group_stream(uint32_t acc0, uint64_t 
 //            bound by one warp's instruction latency, not by bandwidth.
 //
 // MODE 0 (training forward): the epilogue above.   MODE 3 (dgrad / plain conv): the same without the statistics.
-// MODE 4 (dgrad of block l+1 + first pass of block l's BatchNorm backward): the tile just computed IS dp_l, the gradient
-//        w.r.t. block l's pooled output, so the epilogue also reads the two conv outputs y_l[2t], y_l[2t+1] of each pool
-//        pair, routes the (bf16-rounded) gradient through MaxPool / ReLU exactly like bn_bwd_reduce_bf16_kernel and leaves
-//        the per-CTA {sum g, sum g*a} per channel in stat_part -- the separate reduce launch (and its read of dp and y)
-//        disappears from the critical path.
 // MODE 1 (inference): eval-mode BatchNorm folded into per-channel {scale, shift} (`bias` = scale), ReLU and
 //        MaxPool1d(2) in the epilogue -- the two time steps of a pool pair are adjacent TMEM lanes = adjacent
 //        threads, which swap half of their 32 channels with one shuffle each -- and only the POOLED bf16 rows go
@@ -279,7 +279,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __nv_bfloat16* __
     const int ngl = ((int)blockIdx.x < P.ngroups) ? (P.ngroups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     ecg_pdl_launch_dependents();
     long long* const trace = g_conv_trace;
-    if (threadIdx.x == 0) CTR(0);
+    if (threadIdx.x == 0) { CTR(0); CTA_SPAN(0); }
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < C2_MAXST; ++i) { tc::mbar_init(wfull + i, 1); tc::mbar_init(wempty + i, 1); }
@@ -406,7 +406,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __nv_bfloat16* __
         const int nblk = Co >> 5;
         const int row = 32 * q + lane;
         const size_t chunk_stride = (size_t)L * 8;     // elements between channel chunks
-        const bool want_stats = (MODE == 0 || MODE == 4) && stat_part != nullptr;
+        const bool want_stats = MODE == 0 && stat_part != nullptr;
         float ssum[8], ssq[8];                         // lane j: channel 32*cb + j, over this warp's rows
 #pragma unroll
         for (int i = 0; i < 8; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
@@ -466,18 +466,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __nv_bfloat16* __
                         __nv_bfloat16* yrow = y + ((size_t)b * (Co / 8) * L + t) * 8;
                         float v[32];
                         tc::tmem_ld32(taddr, v);
-                        // MODE 4: the pool pairs of the block below (2 rows x 4 chunks of 8 channels), requested before the
-                        // TMEM read-out is waited for so that the L2 round trip hides under it
-                        uint4 yq0[MODE == 4 ? 4 : 1], yq1[MODE == 4 ? 4 : 1];
-                        if constexpr (MODE == 4) {
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const uint4* ya = reinterpret_cast<const uint4*>(
-                                    P.aux_y + (((size_t)b * (Co / 8) + c0 / 8 + i) * P.Laux + 2 * (live ? t : 0)) * 8);
-                                yq0[i] = __ldg(ya);
-                                yq1[i] = __ldg(ya + 1);
-                            }
-                        }
                         tc::tmem_ld_wait();
                         if constexpr (MODE == 1 || MODE == 2) {
                             // relu(scale * conv + shift), then max over the pool pair (lanes 2p, 2p+1): the even lane
@@ -522,8 +510,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __nv_bfloat16* __
                             }
                             continue;
                         }
-                        uint4 y0 = make_uint4(0u, 0u, 0u, 0u), y1 = y0;        // MODE 4: the pool pair of the block below
-                        (void)y0; (void)y1;
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             uint32_t pk[4];
@@ -531,28 +517,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __nv_bfloat16* __
                             for (int j = 0; j < 4; ++j) {
                                 const int c = 8 * i + 2 * j;
                                 pk[j] = tc::pack_bf16(v[c] + bv[c], v[c + 1] + bv[c + 1]);
-                                if constexpr (MODE == 4) {
-                                    if (j == 0) { y0 = yq0[i]; y1 = yq1[i]; }    // the pool pair under this gradient row
-                                    if (live) {
-                                        const uint32_t w0 = j == 0 ? y0.x : j == 1 ? y0.y : j == 2 ? y0.z : y0.w;
-                                        const uint32_t w1 = j == 0 ? y1.x : j == 1 ? y1.y : j == 2 ? y1.z : y1.w;
-                                        const float2 a0 = tc::unpack_bf16(w0), a1 = tc::unpack_bf16(w1), d = tc::unpack_bf16(pk[j]);
-                                        const float2 sc = __ldg(reinterpret_cast<const float2*>(P.aux_scale + c0 + c));
-                                        const float2 sf = __ldg(reinterpret_cast<const float2*>(P.aux_shift + c0 + c));
-                                        {
-                                            const float r0 = fmaxf(fmaf(a0.x, sc.x, sf.x), 0.f), r1 = fmaxf(fmaf(a1.x, sc.x, sf.x), 0.f);
-                                            const bool s0 = (r0 >= r1) && (r0 > 0.f), s1 = r1 > r0;
-                                            const float g = (s0 || s1) ? d.x : 0.f;
-                                            vs[c] += g; qs[c] = fmaf(g, s0 ? a0.x : a1.x, qs[c]);
-                                        }
-                                        {
-                                            const float r0 = fmaxf(fmaf(a0.y, sc.y, sf.y), 0.f), r1 = fmaxf(fmaf(a1.y, sc.y, sf.y), 0.f);
-                                            const bool s0 = (r0 >= r1) && (r0 > 0.f), s1 = r1 > r0;
-                                            const float g = (s0 || s1) ? d.y : 0.f;
-                                            vs[c + 1] += g; qs[c + 1] = fmaf(g, s0 ? a0.y : a1.y, qs[c + 1]);
-                                        }
-                                    }
-                                }
                                 if constexpr (MODE == 0) {
                                     const float2 rr = tc::unpack_bf16(pk[j]);  // the value the next kernels will read
                                     if (live) {
@@ -600,7 +564,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __nv_bfloat16* __
     tc::fence_before_sync();
     __syncthreads();
     if (threadIdx.x == 0) CTR(2);
-    if (warp == 2) tc::tmem_dealloc(tmem_base, P.tmem_cols);
+    if (warp == 2) {
+        tc::tmem_dealloc(tmem_base, P.tmem_cols);
+        if (lane == 0) CTA_SPAN(1);
+    }
 }
 
 static uint32_t tmem_cols_for(int n) {
@@ -609,15 +576,18 @@ static uint32_t tmem_cols_for(int n) {
     return c;
 }
 
+// SM count of the CURRENT device (cached per device index: one process may drive several GPUs)
 static int ecg_num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0, v = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
-        else { (void)cudaGetLastError(); return 148; }
+    static int cache[64] = {0};
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return 148; }
+    if (dev >= 0 && dev < 64 && cache[dev] > 0) return cache[dev];
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) {
+        (void)cudaGetLastError();
+        return 148;
     }
-    return n;
+    if (dev >= 0 && dev < 64) cache[dev] = v;
+    return v;
 }
 
 // Shape -> schedule.  Returns the grid size (number of persistent CTAs = number of stat partials).
@@ -648,9 +618,6 @@ static int conv2_cfg(int B, int Ci, int Co, int L, Conv2Cfg* P, size_t* smem_out
         // R * (kch/16) >= 4 MMAs per issue batch
         if (resident ? R * (P->kch / 16) <= 4 : ng >= nsm) break;
     }
-    if (const char* e = getenv("ECGB200_CONV_R")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) bestR = v; }
-    if (!resident)
-        if (const char* e = getenv("ECGB200_CONV_R_STREAM")) { const int v = atoi(e); if (v == 1 || v == 2) bestR = v; }
     if (bestR * Co > 512) bestR = 512 / Co;
     P->R = bestR;
     P->AS = 2 * bestR * Co <= 512 ? 2 : 1;
@@ -686,9 +653,7 @@ extern "C" int ecgb200_conv1d_stat_parts_bf16(int B, int Ci, int Co, int L) {
 // {sum, sum of squares} of the bf16-rounded outputs.
 template <int MODE>
 static int conv_tc_launch(const void* xb, const void* wprep, const float* bias, const float* shift, void* yb,
-                          float* stat_part, int B, int Ci, int Co, int L, void* stream,
-                          const void* aux_y = nullptr, const float* aux_scale = nullptr,
-                          const float* aux_shift = nullptr, int Laux = 0) {
+                          float* stat_part, int B, int Ci, int Co, int L, void* stream) {
     if (Ci <= 0 || (Ci & 15) || Ci > 256 || (Ci > 64 && (Ci & 63)) || Co <= 0 || (Co & 31) || Co > 256) return ECGB200_EUNSUPPORTED;
     CUtensorMap xmap;
     int rc = ecg_make_act_tmap(&xmap, xb, B, Ci, L, TC_ROWS, Ci / 8);
@@ -697,12 +662,9 @@ static int conv_tc_launch(const void* xb, const void* wprep, const float* bias, 
     size_t smem;
     const int grid = conv2_cfg(B, Ci, Co, L, &P, &smem);
     if (grid <= 0) return ECGB200_EUNSUPPORTED;
-    P.aux_y = (const __nv_bfloat16*)aux_y; P.aux_scale = aux_scale; P.aux_shift = aux_shift; P.Laux = Laux;
-    static size_t smem_set = 0;                              // one per instantiation
-    if (smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {   // the attribute is per device: set it on every call (cheap, legal during stream capture)
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
         if (e != cudaSuccess) return (int)e;
-        smem_set = smem;
     }
     return ecg_launch_pdl(conv_tc_kernel<MODE>, dim3(grid), dim3(C2_THREADS), smem, (cudaStream_t)stream, xmap,
                           (const __nv_bfloat16*)wprep, bias, shift, (__nv_bfloat16*)yb, stat_part, P);
@@ -727,20 +689,6 @@ extern "C" int ecgb200_conv1d_bn_relu_pool_infer_bf16(const void* xb, const void
     if (!xb || !wprep || !scale || !shift || (!pb && !gap_part) || B <= 0 || L < 2) return ECGB200_EINVAL;
     if (gap_part != nullptr) return conv_tc_launch<2>(xb, wprep, scale, shift, nullptr, gap_part, B, Ci, Co, L, stream);
     return conv_tc_launch<1>(xb, wprep, scale, shift, pb, nullptr, B, Ci, Co, L, stream);
-}
-
-// dgrad of block l+1 fused with the first pass of block l's BatchNorm backward (conv_tc_kernel<4>):
-//   dpb [B][Co/8][L][8] = conv(dyb, wd)            (Ci = channels of dy, Co = channels of block l, L = pooled length of block l)
-//   part[parts][2][Co]  = per-CTA {sum g, sum g*a} over the pool pairs of y_prev [B][Co/8][L_prev][8], g = dp routed through
-//                         MaxPool1d(2) / ReLU with block l's bn_state {mean, rstd, scale, shift}; parts =
-//                         ecgb200_conv1d_stat_parts_bf16(B, Ci, Co, L).  Feed part to ecgb200_bn_relu_pool_bwd_apply_bf16.
-extern "C" int ecgb200_conv1d_dgrad_bnstats_bf16(const void* dyb, const void* wd, void* dpb, const void* y_prev,
-                                                 const float* bn_state_prev, float* part, int B, int Ci, int Co,
-                                                 int L, int L_prev, void* stream) {
-    if (!dyb || !wd || !dpb || !y_prev || !bn_state_prev || !part || B <= 0 || L <= 0) return ECGB200_EINVAL;
-    if (L_prev / 2 != L) return ECGB200_EINVAL;
-    return conv_tc_launch<4>(dyb, wd, nullptr, nullptr, dpb, part, B, Ci, Co, L, stream, y_prev,
-                             bn_state_prev + 2 * (size_t)Co, bn_state_prev + 3 * (size_t)Co, L_prev);
 }
 
 extern "C" int ecgb200_conv1d_fwd_bf16(const void* xb, const void* wprep, const float* bias, void* yb,
@@ -803,7 +751,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cb = blockIdx.x, ob = blockIdx.y, z = blockIdx.z, S = gridDim.z;
     long long* const trace = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? g_conv_trace : nullptr;
-    if (threadIdx.x == 0) CTR(0);
+    if (threadIdx.x == 0) { CTR(0); CTA_SPAN(0); }
     const int tiles_t = (L + TC_TILE_M - 1) / TC_TILE_M;
     const int items = B * tiles_t;
     const int nloc = (items - z + S - 1) / S;            // items z, z+S, ...   (host guarantees >= 1)
@@ -911,7 +859,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant
     if (threadIdx.x == 64) CTR(34);
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 2) tc::tmem_dealloc(tmem_base, 512);
+    if (warp == 2) {
+        tc::tmem_dealloc(tmem_base, 512);
+        if (lane == 0) CTA_SPAN(1);
+    }
 }
 
 // dW[o][c][k] = sum_z part[z][o][c/8][k][c%8]  (c < Ci, k < 15);  db[o] = sum_j db_part[o][j]
@@ -978,6 +929,10 @@ wgrad_tc_reduce_kernel(const float4* __restrict__ part, const float* __restrict_
 
 static void wgrad_tc_cfg(int B, int Cip, int Co, int L, int* ncc, int* S) {
     *ncc = Cip / 8 < 4 ? Cip / 8 : 4;
+    // thin layers (<= 64 output channels): two chunks per CTA -- half the split-K partial bytes for the same MMA count
+    // (measured at B=256: block 2 26.7 -> 23.4 us); wide layers are bound by re-reading the dY tile per chunk group and
+    // stay at four (two chunks: block 4 41.5 -> 51.1 us, block 3 27.9 -> 30.0 us)
+    if (Co <= 64 && *ncc > 2) *ncc = 2;
     const int blocks_oc = (Cip / 8 / *ncc) * ecg_cdiv(Co, 128);
     const int items = B * ecg_cdiv(L, TC_TILE_M);
     int s = 148 / blocks_oc;
@@ -1015,22 +970,17 @@ extern "C" int ecgb200_conv1d_wgrad_bf16(const void* dyb, const void* xb, float*
     const size_t slack = (size_t)(16 - ochunks) * 128 * 16;
     int nst = (int)((WT_SMEM_BUDGET - slack) / stage);
     if (nst > WT_MAXST) nst = WT_MAXST;
-    if (const char* e = getenv("ECGB200_WGRAD_NST")) { const int v = atoi(e); if (v >= 2 && v <= nst) nst = v; }
     size_t smem = TC_HDR + (size_t)nst * stage + slack;
     if (smem < TC_HDR + WT_EPI_BYTES) smem = TC_HDR + WT_EPI_BYTES;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
         if (e != cudaSuccess) return (int)e;
-        smem_set = smem;
     }
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid(Cip / 8 / ncc, ecg_cdiv(Co, 128), S);
     wgrad_tc_kernel<<<grid, 192, smem, st>>>(dymap, xmap, (float*)ws, Co, Cip, L, B, ncc, ochunks, nst);
     rc = ecg_launch_status();
     if (rc) return rc;
-    static const bool skip_reduce = getenv("ECGB200_DEBUG_SKIP_WGRAD_REDUCE") != nullptr;    // timing diagnostics only
-    if (skip_reduce) return 0;
     const float4* pw = (const float4*)ws;
     if (S <= 24) {
         const int nblk_w = ecg_cdiv(Co * Cip * 4, 128);

@@ -35,22 +35,29 @@ __device__ __forceinline__ unsigned long long dp_globaltimer() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-// wait until flag >= epoch (monotonic epochs: no reset race); traps after 10 s instead of hanging the GPU
+// Cross-rank waits: a rank may legitimately arrive much later than its peers (rank 0 runs validation or writes a
+// checkpoint between epochs, a loader stalls), so the limit is minutes by default -- NCCL would simply wait -- and
+// ecgb200_set_spin_timeout_ms(0) switches it off.  It exists so that a protocol bug or a dead peer ends in a trap
+// instead of a GPU that spins for ever.
+static __device__ unsigned long long g_dp_timeout_ns = 600000000000ull;
+void ecg_set_timeout_dp(unsigned long long ns) { cudaMemcpyToSymbol(g_dp_timeout_ns, &ns, sizeof(ns)); }
+// wait until flag >= epoch (monotonic epochs: no reset race)
 __device__ __forceinline__ void dp_wait_flag(const unsigned int* f, unsigned int epoch) {
     unsigned long long t0 = 0;
     for (unsigned it = 0;; ++it) {
         if ((int)(dp_ld_acquire_sys(f) - epoch) >= 0) return;
         if ((it & 255u) == 255u) {
-            const unsigned long long now = dp_globaltimer();
+            const unsigned long long now = dp_globaltimer(), limit = g_dp_timeout_ns;
             if (t0 == 0) t0 = now;
-            else if (now - t0 > 10000000000ull) __trap();
+            else if (limit != 0 && now - t0 > limit) __trap();
         }
     }
 }
 
 __global__ void __launch_bounds__(256)
-dp_adamw_fused_kernel(const __grid_constant__ DpPeers Q, float* __restrict__ m, float* __restrict__ v, long long n,
-                      int rank, int world, const float* __restrict__ hyper, const int* __restrict__ step_now) {
+dp_adamw_fused_kernel(const __grid_constant__ DpPeers Q, float* __restrict__ m, float* __restrict__ v, long long off,
+                      long long n, int rank, int world, const float* __restrict__ hyper,
+                      const int* __restrict__ step_now) {
     __shared__ float S[8];
     unsigned int* myflags = Q.flags[rank];
     // barrier epoch = number of this call (1-based), kept in the flag pad so that it does not depend on the
@@ -77,10 +84,10 @@ dp_adamw_fused_kernel(const __grid_constant__ DpPeers Q, float* __restrict__ m, 
     __syncthreads();
     const float decay = S[0], one_m_b1 = S[1], b2 = S[2], one_m_b2 = S[3], bc2 = S[4], eps = S[5], ss = S[6],
                 gscale = S[7];
-    // ---- owned shard, in float4 units (n is padded to a multiple of 4 * world by the caller)
+    // ---- owned shard of the bucket [off, off + n), in float4 units (off % 4 == 0, n % (4 * world) == 0)
     const long long n4 = n >> 2;
     const long long per = n4 / world;
-    const long long lo = per * rank, hi = lo + per;
+    const long long lo = (off >> 2) + per * rank, hi = lo + per;
     const long long stride = (long long)gridDim.x * blockDim.x;
     float* myp = Q.p[rank];
     for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride) {
@@ -128,17 +135,26 @@ dp_adamw_fused_kernel(const __grid_constant__ DpPeers Q, float* __restrict__ m, 
 
 extern "C" int ecgb200_dp_flag_words(int world) { return 2 * world + 2; }
 
+// fixed grid per (bucket size, world): the exit barrier counts epoch * gridDim.x block arrivals, so a flag pad must
+// always be used with the same bucket
+static int dp_grid(long long n, int world) {
+    long long b = (n / 4 / world + 255) / 256;
+    return (int)(b < 8 ? 8 : (b > 96 ? 96 : b));
+}
+
 // p / g / flags: HOST arrays of `world` peer-mapped device pointers (this rank's own buffers at index `rank`).
-// m, v: this rank's Adam moments (full length n; only the owned shard [rank*n/world, (rank+1)*n/world) is used).
-// n must be a multiple of 4*world (pad the flat buffers); flags: >= ecgb200_dp_flag_words(world) zero-initialised
-// uint32 per rank.  hyper[5] must hold 1/world.  *step_now is the 1-based optimizer step index (bias correction),
-// identical on every rank.  Every rank must make the same sequence of calls (the call count is the barrier epoch).
-extern "C" int ecgb200_dp_adamw_fused_f32(float* const* p, const float* const* g, unsigned int* const* flags,
-                                          float* m, float* v, int64_t n, int rank, int world, const float* hyper,
-                                          const int* step_now, void* stream) {
-    if (!p || !g || !flags || !m || !v || !hyper || !step_now || n <= 0) return ECGB200_EINVAL;
+// m, v: this rank's Adam moments (full length; only the owned shard of the bucket is used).  The bucket is the
+// element range [off, off + n) of the flat buffers: off % 4 == 0, n % (4 * world) == 0; rank r owns
+// [off + r*n/world, off + (r+1)*n/world).  flags: >= ecgb200_dp_flag_words(world) zero-initialised uint32 per rank,
+// ONE PAD PER BUCKET (the call count on a pad is its barrier epoch).  hyper[5] must hold 1/world.  *step_now is the
+// 1-based optimizer step index (bias correction), identical on every rank.  Every rank must make the same sequence of
+// calls on a pad.
+extern "C" int ecgb200_dp_adamw_fused_range_f32(float* const* p, const float* const* g, unsigned int* const* flags,
+                                                float* m, float* v, int64_t off, int64_t n, int rank, int world,
+                                                const float* hyper, const int* step_now, void* stream) {
+    if (!p || !g || !flags || !m || !v || !hyper || !step_now || n <= 0 || off < 0) return ECGB200_EINVAL;
     if (world < 1 || world > DP_MAX_WORLD || rank < 0 || rank >= world) return ECGB200_EUNSUPPORTED;
-    if (n % (4LL * world) != 0) return ECGB200_EINVAL;
+    if (n % (4LL * world) != 0 || (off & 3) != 0) return ECGB200_EINVAL;
     DpPeers Q;
     for (int r = 0; r < DP_MAX_WORLD; ++r) {
         Q.p[r] = r < world ? p[r] : nullptr;
@@ -148,7 +164,71 @@ extern "C" int ecgb200_dp_adamw_fused_f32(float* const* p, const float* const* g
         if (r < world && ((((uintptr_t)Q.p[r] | (uintptr_t)Q.g[r]) & 15) != 0)) return ECGB200_EINVAL;
     }
     if ((((uintptr_t)m | (uintptr_t)v) & 15) != 0) return ECGB200_EINVAL;
-    // fixed grid (the exit barrier counts epoch * gridDim.x block arrivals): enough loads in flight to cover NVLink latency
-    dp_adamw_fused_kernel<<<96, 256, 0, (cudaStream_t)stream>>>(Q, m, v, (long long)n, rank, world, hyper, step_now);
+    dp_adamw_fused_kernel<<<dp_grid(n, world), 256, 0, (cudaStream_t)stream>>>(Q, m, v, (long long)off, (long long)n, rank,
+                                                                             world, hyper, step_now);
+    return ecg_launch_status();
+}
+
+// The whole flat space as one bucket.
+extern "C" int ecgb200_dp_adamw_fused_f32(float* const* p, const float* const* g, unsigned int* const* flags,
+                                          float* m, float* v, int64_t n, int rank, int world, const float* hyper,
+                                          const int* step_now, void* stream) {
+    return ecgb200_dp_adamw_fused_range_f32(p, g, flags, m, v, 0, n, rank, world, hyper, step_now, stream);
+}
+
+// ---------------------------------------------------------------- SyncBN statistics exchange
+// Train-mode BatchNorm over the GLOBAL batch under data parallel (the reference is single-device: its statistics
+// cover the whole batch, src/models/ecg_cnn.py:14): every replica reduces its own partial pairs
+// local_part[nparts][2][C] (forward: {sum y, sum y^2} from the conv epilogue; backward: {sum g, sum g*a} from pass 1 of
+// the BatchNorm backward) to ONE pair, publishes it in its exchange slot (peer memory), passes a cross-rank barrier and
+// gathers every replica's pair in rank order into out[world][2][C] -- which the BatchNorm kernels then merge exactly
+// like per-CTA partials (fixed order => every replica computes bit-identical statistics).
+struct BnPeers {
+    float* slot[DP_MAX_WORLD];               // every rank's exchange slot (>= 2*C floats, peer mapped)
+    unsigned int* flags[DP_MAX_WORLD];       // every rank's flag pad (layout as DpPeers)
+};
+
+__global__ void __launch_bounds__(512)
+dp_bn_sync_kernel(const __grid_constant__ BnPeers Q, const float* __restrict__ local_part, int nparts, int C,
+                  float* __restrict__ out, int rank, int world) {
+    unsigned int* myflags = Q.flags[rank];
+    const unsigned int epoch = myflags[2 * world + 1] + 1u;
+    const int i = threadIdx.x;                       // i < 2*C: (which, channel)
+    if (i < 2 * C) {
+        const int which = i / C, c = i - which * C;
+        double s = 0.0;
+        for (int j = 0; j < nparts; ++j) s += (double)__ldg(local_part + ((size_t)j * 2 + which) * C + c);
+        Q.slot[rank][i] = (float)s;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < world) {
+        dp_st_release_sys(Q.flags[threadIdx.x] + rank, epoch);
+        dp_wait_flag(myflags + threadIdx.x, epoch);
+    }
+    __syncthreads();
+    if (i < 2 * C) {
+        const int which = i / C, c = i - which * C;
+        for (int r = 0; r < world; ++r)
+            out[((size_t)r * 2 + which) * C + c] = __ldcv(Q.slot[r] + i);          // peer load, not cached
+    }
+    if (threadIdx.x == 0) myflags[2 * world + 1] = epoch;
+}
+
+// slots / flags: HOST arrays of `world` peer-mapped pointers; a slot holds >= 2*C floats and must not be reused by
+// another exchange before every rank has passed a later cross-rank barrier (the engine gives every (block, direction)
+// its own slot; the optimizer exchange at the end of the step is that barrier).  flags: one pad
+// (ecgb200_dp_flag_words) shared by all BatchNorm exchanges of the step.  C <= 256.
+extern "C" int ecgb200_dp_bn_sync_f32(const float* local_part, int nparts, int C, float* const* slots,
+                                      unsigned int* const* flags, float* out, int rank, int world, void* stream) {
+    if (!local_part || nparts <= 0 || C <= 0 || !slots || !flags || !out) return ECGB200_EINVAL;
+    if (C > 256 || world < 1 || world > DP_MAX_WORLD || rank < 0 || rank >= world) return ECGB200_EUNSUPPORTED;
+    BnPeers Q;
+    for (int r = 0; r < DP_MAX_WORLD; ++r) {
+        Q.slot[r] = r < world ? slots[r] : nullptr;
+        Q.flags[r] = r < world ? flags[r] : nullptr;
+        if (r < world && (!Q.slot[r] || !Q.flags[r])) return ECGB200_EINVAL;
+    }
+    dp_bn_sync_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(Q, local_part, nparts, C, out, rank, world);
     return ecg_launch_status();
 }

@@ -275,3 +275,96 @@ extern "C" int ecgb200_wfdb16_zscore_f32(const void* dat, const float* gain, con
     wfdb16_zscore_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const short*)dat, gain, baseline, out, n_leads, T, normalize);
     return ecg_launch_status();
 }
+
+// ---------------------------------------------------------------- raw frames -> the conv stack's input (N1 + N2 fused)
+// The same decode + per-lead z-score, but the result goes straight to what the first tcgen05 conv reads: blocked
+// channels-last bf16 xb[b][lead/8][t][8] with the leads zero-padded to a multiple of 16 -- the fp32 (B, leads, T) tensor
+// of the reference's Dataset (src/datasets/ptbxl.py:122-127, 136-141) never exists.  One block per record: the raw frames
+// are staged in shared memory once (coalesced 4-byte loads), every thread keeps the running sums of ALL leads of its
+// frames (two passes in double: mean, then centred M2, as the oracle's numpy), one block reduction per pass.
+#include <cuda_bf16.h>
+__global__ void __launch_bounds__(256)
+wfdb16_zscore_pack_kernel(const short* __restrict__ dat, const float* __restrict__ gain, const int* __restrict__ baseline,
+                          uint4* __restrict__ xb, int n_leads, int Cp, int T) {
+    extern __shared__ __align__(16) unsigned char wf_smem[];
+    short* fr = reinterpret_cast<short*>(wf_smem);                       // [T][n_leads]
+    __shared__ double red[8][WF_MAXL];
+    __shared__ float mean_s[WF_MAXL], inv_s[WF_MAXL];
+    __shared__ double meand_s[WF_MAXL];
+    const short* rec = dat + (size_t)blockIdx.x * T * n_leads;
+    const int nwords = (T * n_leads) >> 1;                               // host guarantees T * n_leads even
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x)
+        reinterpret_cast<int*>(fr)[i] = __ldg(reinterpret_cast<const int*>(rec) + i);
+    double g[WF_MAXL];
+    int bl[WF_MAXL];
+#pragma unroll
+    for (int l = 0; l < WF_MAXL; ++l) { g[l] = l < n_leads ? (double)gain[l] : 1.0; bl[l] = l < n_leads ? baseline[l] : 0; }
+    __syncthreads();
+    auto phys = [&](int t, int l) -> float {
+        const int d = (int)fr[t * n_leads + l];
+        return d == -32768 ? __int_as_float(0x7fc00000) : (float)((double)(d - bl[l]) / g[l]);
+    };
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double acc[WF_MAXL];
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+        for (int l = 0; l < WF_MAXL; ++l) acc[l] = 0.0;
+        for (int t = threadIdx.x; t < T; t += blockDim.x) {
+#pragma unroll
+            for (int l = 0; l < WF_MAXL; ++l)
+                if (l < n_leads) {
+                    const double v = (double)phys(t, l);
+                    if (pass == 0) acc[l] += v;
+                    else { const double d = v - meand_s[l]; acc[l] += d * d; }
+                }
+        }
+#pragma unroll
+        for (int l = 0; l < WF_MAXL; ++l) {
+            if (l < n_leads) {
+                const double r = warp_sum_d(acc[l]);
+                if (lane == 0) red[w][l] = r;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < n_leads) {
+            double s = 0.0;
+            for (int j = 0; j < 8; ++j) s += red[j][threadIdx.x];
+            if (pass == 0) { meand_s[threadIdx.x] = s / (double)T; mean_s[threadIdx.x] = (float)(s / (double)T); }
+            else inv_s[threadIdx.x] = 1.0f / ((float)sqrt(s / (double)T) + 1e-6f);
+        }
+        __syncthreads();
+    }
+    const int nchunk = Cp / 8;
+    uint4* out = xb + (size_t)blockIdx.x * nchunk * T;
+    for (int i = threadIdx.x; i < nchunk * T; i += blockDim.x) {
+        const int cc = i / T, t = i - cc * T;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int l = cc * 8 + j;
+            v[j] = l < n_leads ? (phys(t, l) - mean_s[l]) * inv_s[l] : 0.f;
+        }
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]),
+                       h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+        out[i] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                            *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+    }
+}
+
+// dat (B, T, n_leads) int16 frames; xb [B][Cp/8][T][8] bf16 with Cp = n_leads rounded up to 16.
+extern "C" int ecgb200_wfdb16_zscore_pack_bf16(const void* dat, const float* gain, const int* baseline, void* xb,
+                                               int B, int n_leads, int T, void* stream) {
+    if (!dat || !gain || !baseline || !xb || B <= 0 || T <= 0) return ECGB200_EINVAL;
+    if (n_leads <= 0 || n_leads > WF_MAXL || ((T * n_leads) & 1) || (((uintptr_t)dat) & 3)) return ECGB200_EUNSUPPORTED;
+    const size_t smem = (size_t)T * n_leads * sizeof(short);
+    if (smem > 200 * 1024) return ECGB200_EUNSUPPORTED;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(wfdb16_zscore_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    const int Cp = (n_leads + 15) / 16 * 16;
+    wfdb16_zscore_pack_kernel<<<B, 256, smem, (cudaStream_t)stream>>>((const short*)dat, gain, baseline, (uint4*)xb,
+                                                                     n_leads, Cp, T);
+    return ecg_launch_status();
+}
+

@@ -30,6 +30,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // Bounded wait: a protocol bug must abort the kernel (trap) instead of hanging the GPU.  If a diagnostic
 // buffer was registered (ecgb200_debug_set_diag: pinned host memory), the stuck barrier is recorded first.
 static __device__ unsigned long long* g_mbar_diag = nullptr;   // per translation unit
+// deadlock limit of mbar_wait in ns (0 = wait for ever); set by ecgb200_set_spin_timeout_ms.  The default is long
+// enough for time-slicing / preemption / a debugger to pause the CTA without a spurious trap.
+static __device__ unsigned long long g_mbar_timeout_ns = 30000000000ull;
 __device__ __forceinline__ uint64_t globaltimer_ns() {
     uint64_t t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -50,8 +53,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (done) return;
         if ((it & 1023u) == 1023u) {
             const uint64_t now = globaltimer_ns();
+            const uint64_t limit = g_mbar_timeout_ns;
             if (t0 == 0) t0 = now;
-            else if (now - t0 > 2000000000ull) {                  // 2 s: deadlock
+            else if (limit == 0) continue;
+            else if (now - t0 > limit) {                          // deadlock
                 unsigned long long* d = g_mbar_diag;
                 if (d != nullptr) {
                     d[1] = ((unsigned long long)blockIdx.x << 32) | threadIdx.x;
@@ -60,7 +65,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
                     __threadfence_system();
                 }
                 __trap();
-            } else if (now - t0 > 1000000000ull) {                // 1 s: every stuck waiter leaves a note
+            } else if (now - t0 > limit / 2) {                    // half way: every stuck waiter leaves a note
                 unsigned long long* d = g_mbar_diag;
                 if (d != nullptr && (threadIdx.x & 31) == (threadIdx.x >> 5) % 32 * 0 + ((threadIdx.x & 31))) {
                     const unsigned w = threadIdx.x >> 5;

@@ -20,7 +20,7 @@ from typing import Optional
 
 import torch
 
-from ._lib import lib, check, EcgB200Error
+from ._lib import lib, check, EcgB200Error, configure_timeouts
 from .ecg_cnn import ECGCNN
 from .ecg_multimodal import ECGMultimodal
 
@@ -48,6 +48,7 @@ class InferStep:
         self.use_graph = use_graph
         self.graphs = None
         self.launches_per_batch = 6
+        configure_timeouts()
         self._alloc()
         self.refresh()
 

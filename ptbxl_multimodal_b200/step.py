@@ -9,10 +9,14 @@ buffers (the nn.Module's parameters are re-pointed to views of the flat paramete
 ``torch.cuda.CUDAGraph`` and replayed per step, so a step costs one launch from the host and
 no host<->device synchronisation (the loss stays on the device until the caller reads it).
 
-Data parallel (one process per GPU): gradients are summed with NCCL all-reduce in two buckets
--- the 4th conv block (65 % of the bytes, ready first) on a side stream while blocks 3..1
-still run backward, the rest at the end -- and the 1/world_size average is folded into the
-AdamW kernel (``gscale``).  BatchNorm statistics are per rank (torch DDP semantics)."""
+Data parallel (one process per GPU): the gradient mean and the optimizer are ONE exchange, in two buckets --
+the 4th conv block (65 % of the bytes, final as soon as its weight gradient is) while blocks 3..1 still run
+backward, the rest at the end.  bf16 engine: reduce-scatter + AdamW on the owned shard + all-gather as one
+kernel per bucket over NVLink peer memory (csrc/dp_fused.cu, ``dp_mode="fused"``); ``dp_mode="nccl"`` keeps NCCL
+all-reduce + a replicated AdamW (the 1/world_size average folded into the AdamW kernel) for A/B runs and for the
+fp32 engine.  BatchNorm statistics are per rank (torch DDP semantics) unless ``sync_bn=True``: then every
+BatchNorm pass exchanges its partial sums over peer memory and all ranks normalise with the statistics of the
+GLOBAL batch -- the single-device reference's result on the concatenated batch."""
 from __future__ import annotations
 
 import ctypes as C
@@ -20,7 +24,7 @@ from typing import List, Optional
 
 import torch
 
-from ._lib import lib, check, EcgB200Error
+from ._lib import lib, check, EcgB200Error, configure_timeouts
 from .ecg_cnn import ECGCNN
 from .ecg_multimodal import ECGMultimodal
 from .optim import FusedAdamW
@@ -43,7 +47,8 @@ class _Seg:
 
 class TrainStep:
     def __init__(self, model, optimizer: FusedAdamW, batch_size: int, seq_len: int,
-                 process_group=None, use_graph: bool = True, precision: str = "fp32", dp_mode: str = "auto"):
+                 process_group=None, use_graph: bool = True, precision: str = "fp32", dp_mode: str = "auto",
+                 raw_input: bool = False, sync_bn: bool = False):
         if not isinstance(model, (ECGCNN, ECGMultimodal)):
             raise EcgB200Error("TrainStep drives ecgb200 ECGCNN / ECGMultimodal models")
         if not isinstance(optimizer, FusedAdamW) or len(optimizer.param_groups) != 1:
@@ -72,11 +77,21 @@ class TrainStep:
         self.dp_fused = self.world > 1 and (dp_mode == "fused" or (dp_mode == "auto" and self.bf16))
         if self.dp_fused and not self.bf16:
             raise EcgB200Error("dp_mode='fused' is implemented for precision='bf16'")
+        # raw_input: the step starts from raw WFDB format-16 frames (B, T, leads) int16 (load_frames) -- decode, per-lead
+        # z-score and the bf16 pack are one kernel at the head of the graph (SURVEY 8f N1 + N2)
+        self.raw_input = bool(raw_input)
+        if self.raw_input and not self.bf16:
+            raise EcgB200Error("raw_input=True is implemented for precision='bf16'")
+        self.sync_bn = bool(sync_bn) and self.world > 1
+        if self.sync_bn and not self.dp_fused:
+            raise EcgB200Error("sync_bn=True needs the peer-memory exchange (precision='bf16', dp_mode 'auto' or 'fused')")
         self.use_graph = use_graph
         self.graph = None
         self.launches_per_step = 0
         self._prof = None
         self._prof_tag = ""
+        self._stamps = None
+        configure_timeouts()
         self._flatten()
         self._alloc()
 
@@ -91,8 +106,11 @@ class TrainStep:
                 [(n, p) for n, p in named if n.startswith(last)]
         total = sum(p.numel() for _, p in order)
         dev = self.dev
-        # padded so that the space splits into 16-byte aligned shards for any world size <= 8
-        self.total_pad = padded_size(total)
+        # Two buckets, each padded so that it splits into 16-byte aligned shards for any world size <= 8:
+        # B = [0, bucket_a_off) everything but conv block 4, A = [bucket_a_off, total_pad) block 4 (the tail)
+        n_rest = sum(p.numel() for n, p in order if not n.startswith(last))
+        self.bucket_a_off = padded_size(n_rest)
+        self.total_pad = self.bucket_a_off + padded_size(total - n_rest)
         if self.dp_fused:
             self._alloc_symmetric(self.total_pad)
         else:
@@ -106,6 +124,8 @@ class TrainStep:
             for n, p in order:
                 if p.dtype != F32:
                     raise EcgB200Error("parameters must be float32")
+                if n.startswith(last) and off < self.bucket_a_off:
+                    off = self.bucket_a_off                  # block 4 starts on its own bucket
                 s = _Seg(n, p, off)
                 self.P[off:off + s.n].copy_(p.detach().reshape(-1))
                 st = self.opt.state[p]
@@ -119,11 +139,12 @@ class TrainStep:
                 self.seg[n] = s
                 off += s.n
         self.total = total
+        self._probe = next(iter(self.seg.values()))
         if self.world > 1:
             # replicas must start identical (DDP broadcasts too); cheap, once
             torch.distributed.broadcast(self.P, src=torch.distributed.get_global_rank(self.pg, 0) if self.pg is not None else 0,
                                         group=self.pg)
-        self.bucket_a_off = self.seg[last + "net.0.weight"].off     # block 4 = tail of the buffers
+        assert self.seg[last + "net.0.weight"].off == self.bucket_a_off
         self.hyper, self.step_dev = self.opt.device_state(group, dev)
         if self.world > 1:
             self.opt.grad_scale = 1.0 / self.world
@@ -137,28 +158,40 @@ class TrainStep:
         group = self.pg if self.pg is not None else dist.group.WORLD
         self.rank = dist.get_rank(group)
         nflag = lib.ecgb200_dp_flag_words(self.world)
+        self.flag_stride = max(nflag, 64)                    # words between flag pads (256-byte aligned)
         self.P = symm.empty(n, dtype=F32, device=self.dev)
         self.G = symm.empty(n, dtype=F32, device=self.dev)
-        self.flags = symm.empty(max(nflag, 64), dtype=torch.int32, device=self.dev)
-        self.P.zero_(); self.G.zero_(); self.flags.zero_()
+        # three flag pads (bucket A, bucket B, BatchNorm exchanges) + 8 BatchNorm exchange slots of 2 * 256 floats
+        self.flags = symm.empty(3 * self.flag_stride, dtype=torch.int32, device=self.dev)
+        self.bnx = symm.empty(8 * 512, dtype=F32, device=self.dev)
+        self.P.zero_(); self.G.zero_(); self.flags.zero_(); self.bnx.zero_()
         torch.cuda.synchronize(self.dev)
-        hp, hg, hf = (symm.rendezvous(t, group) for t in (self.P, self.G, self.flags))
-        self._symm_handles = (hp, hg, hf)                    # keep the mappings alive
+        hp, hg, hf, hb = (symm.rendezvous(t, group) for t in (self.P, self.G, self.flags, self.bnx))
+        self._symm_handles = (hp, hg, hf, hb)                # keep the mappings alive
         ptrs = lambda h: [int(h.buffer_ptrs[r]) for r in range(self.world)]      # noqa: E731
-        self.peer_p, self.peer_g, self.peer_f = ptrs(hp), ptrs(hg), ptrs(hf)
+        self.peer_p, self.peer_g, self.peer_f, self.peer_bnx = ptrs(hp), ptrs(hg), ptrs(hf), ptrs(hb)
         if self.peer_p[self.rank] != self.P.data_ptr() or self.peer_g[self.rank] != self.G.data_ptr():
             raise EcgB200Error("symmetric-memory rendezvous returned unexpected local pointers")
         dist.barrier(group)
+
+    def _flag_pad(self, which: int):
+        """Peer pointers of flag pad `which` (0: bucket A, 1: bucket B, 2: BatchNorm exchanges)."""
+        return [p + 4 * which * self.flag_stride for p in self.peer_f]
+
+    def _buckets(self):
+        """(offset, length, flag pad) of the exchange buckets, in launch order."""
+        return [(self.bucket_a_off, self.total_pad - self.bucket_a_off, 0), (0, self.bucket_a_off, 1)]
 
     def gather_optimizer_state(self):
         """dp_mode='fused' shards the Adam moments (each rank updates 1/world of them).  Before saving an
         optimizer checkpoint, call this on every rank: all-gathers the shards so that opt.state is complete."""
         if not self.dp_fused:
             return
-        lo, hi = shard_bounds(self.total_pad, self.world)[self.rank]
-        for buf in (self.M, self.V):
-            shard = buf[lo:hi].clone()
-            torch.distributed.all_gather_into_tensor(buf, shard, group=self.pg)
+        for off, n, _ in self._buckets():
+            lo, hi = shard_bounds(n, self.world)[self.rank]
+            for buf in (self.M, self.V):
+                shard = buf[off + lo:off + hi].clone()
+                torch.distributed.all_gather_into_tensor(buf[off:off + n], shard, group=self.pg)
 
     def _refresh_views(self):
         """Re-point parameters at the flat buffers if something (e.g. load_state_dict keeps
@@ -169,6 +202,21 @@ class TrainStep:
                     self.P[s.off:s.off + s.n].copy_(s.param.detach().reshape(-1))
                     s.param.data = self.P[s.off:s.off + s.n].view(s.param.shape)
                 s.param.grad = self.G[s.off:s.off + s.n].view(s.param.shape)
+                # optimizer.load_state_dict() replaces the moment tensors: adopt the new values and re-alias, so that
+                # the captured graphs (which update M / V) and opt.state_dict() stay one and the same
+                st = self.opt.state[s.param]
+                for key, flat in (("exp_avg", self.M), ("exp_avg_sq", self.V)):
+                    t = st.get(key)
+                    if t is None or t.data_ptr() != flat.data_ptr() + 4 * s.off:
+                        if t is not None:
+                            flat[s.off:s.off + s.n].copy_(t.detach().reshape(-1).to(flat.device, F32))
+                        st[key] = flat[s.off:s.off + s.n].view(s.param.shape)
+        group = self.opt.param_groups[0]
+        sd = group.get("_step_dev")
+        if sd is None or sd.data_ptr() != self.step_dev.data_ptr():
+            # the step counter the graphs increment must be the optimizer's: re-adopt the host-side step count
+            self.step_dev.fill_(int(group.get("step", 0)))
+            group["_step_dev"] = self.step_dev
 
     # ------------------------------------------------------------------ static buffers
     def _alloc(self):
@@ -208,27 +256,9 @@ class TrainStep:
             self.ybuf = [eb(B, self.chan[l + 1] // 8, self.L[l], 8) for l in range(4)]
             self.wt = [eb(15, self.cip[l] // 8, self.chan[l + 1], 8) for l in range(4)]
             self.wd = [None] + [eb(15, self.chan[l + 1] // 8, self.cip[l], 8) for l in range(1, 4)]
-            # BN backward: reduce + apply as two launches.  The single cooperative launch
-            # (ecgb200_bn_relu_pool_bwd_fused_bf16) measured SLOWER inside the step (466 vs 447 us at B=256): its
-            # 2-blocks-per-SM shared-memory slices lower occupancy and, needing the whole GPU at once, it stops
-            # overlapping with the weight-gradient branch.  Kept behind ECGB200_BN_FUSED=1 for experiments.
-            import os
-            use = os.environ.get("ECGB200_BN_FUSED") == "1"
-            self.bn_fused = [lib.ecgb200_bn_bwd_fused_nsplit(B, self.chan[l + 1], self.L[l], 1 if l < 3 else 0) if use else 0
-                             for l in range(4)]
-            self.ndb = [self.bn_fused[l] or lib.ecgb200_bn_nsplit(B, self.chan[l + 1]) for l in range(4)]
+            # BN backward = reduce + apply launches (the apply pass is launched programmatically dependent)
+            self.ndb = [lib.ecgb200_bn_nsplit(B, self.chan[l + 1]) for l in range(4)]
             self.dbpart = [e(self.chan[l + 1], self.ndb[l]) for l in range(4)]
-            # Option (off): dgrad of block l+1 also produces block l's BatchNorm-backward sums in its epilogue
-            # (conv_tc_kernel<4>), so that the separate reduce launch disappears.  Measured SLOWER at batch 256 (0.462 vs
-            # 0.431 ms/step): each dgrad grows by 10.5 us -- as much as the reduce kernel it replaces -- and that time is
-            # spent in the exposed, SM-exclusive epilogue of a tensor kernel, while the reduce kernel could share the SMs
-            # with the weight-gradient branch.  ECGB200_BN_DGRAD_FUSE=1 enables it.
-            self.bn_dgrad_fuse = os.environ.get("ECGB200_BN_DGRAD_FUSE", "0") == "1" and not use
-            self.nbw = [lib.ecgb200_conv1d_stat_parts_bf16(B, self.chan[l + 2], self.chan[l + 1], self.L[l + 1])
-                        if self.bn_dgrad_fuse else 0 for l in range(3)]
-            if self.bn_dgrad_fuse and min(self.nbw) <= 0:
-                self.bn_dgrad_fuse = False
-            self.bwpart = [e(self.nbw[l], 2, self.chan[l + 1]) if self.bn_dgrad_fuse else None for l in range(3)]
             self.stat = [None] * 4
             # per-CTA {sum, sumsq} partials written by the conv epilogue
             self.nstat = [lib.ecgb200_conv1d_stat_parts_bf16(B, self.cip[l], self.chan[l + 1], self.L[l]) for l in range(4)]
@@ -237,6 +267,15 @@ class TrainStep:
             self.statp = [e(self.nstat[l], 2, self.chan[l + 1]) for l in range(4)]
             self.wpT = e(self.chan[4], self.bb.proj.out_features)
             self.loss_part = e(lib.ecgb200_head_loss_parts(B))
+            if self.raw_input:
+                # raw WFDB format-16 frames per input slot + per-lead calibration (.hea gain / baseline)
+                nlead = self.chan[0]
+                self.frames = [torch.zeros(B, T, nlead, dtype=torch.int16, device=dev) for _ in range(2)]
+                self.gain = torch.full((nlead,), 200.0, dtype=F32, device=dev)
+                self.baseline = torch.zeros(nlead, dtype=torch.int32, device=dev)
+            if self.sync_bn:
+                # exchanged statistics: one {sum, sum of squares} / {sum g, sum g*a} pair per replica
+                self.bnsync = [e(self.world, 2, self.chan[l + 1]) for l in range(4)]
         c4 = self.chan[4]
         self.gap = e(B, c4)
         self.dgap = e(B, c4)
@@ -270,12 +309,21 @@ class TrainStep:
         del big
         self.side = torch.cuda.Stream(device=dev) if (self.world > 1 or self.bf16) else None
         self.linear = False
-        self.comm = torch.cuda.Stream(device=dev) if (self.world > 1 and self.bf16 and not self.dp_fused) else None
+        self.comm = torch.cuda.Stream(device=dev) if (self.world > 1 and self.bf16) else None
 
     # ------------------------------------------------------------------ the kernel sequence
     def _k(self, name, fn, *args):
         """One C-ABI call; with self._prof set, bracket it with CUDA events on the launch stream."""
         prof = self._prof
+        if self._stamps is not None:
+            # schedule trace: %globaltimer stamps in stream order before / after the call (args[-1] is its stream)
+            buf, names = self._stamps
+            i = len(names)
+            names.append((name + self._prof_tag, args[-1]))
+            check(lib.ecgb200_debug_stamp(buf.data_ptr(), 2 * i, args[-1]), "stamp")
+            check(fn(*args), name)
+            check(lib.ecgb200_debug_stamp(buf.data_ptr(), 2 * i + 1, args[-1]), "stamp")
+            return
         if prof is None:
             check(fn(*args), name)
             return
@@ -321,31 +369,28 @@ class TrainStep:
         main = torch.cuda.current_stream(self.dev)
         # critical path: pack the input + block-1 weights (+ step counter); blocks 2-4 and the proj transpose
         # are re-laid beside the first conv on the side stream
-        self._k("prep", lib.ecgb200_step_prep_bf16, _p(self.x), _p(self.acts[0]), B, self.chan[0], self.T, 1,
-                PV(Pp(wkeys[0]), None, None, None), PV(_p(self.wt[0]), None, None, None), PV(None, None, None, None),
+        if self.raw_input:
+            self._k("decode", lib.ecgb200_wfdb16_zscore_pack_bf16, _p(self.frames[self.cur]), _p(self.gain),
+                    _p(self.baseline), _p(self.acts[0]), B, self.chan[0], self.T, st)
+            n += 1
+        self._k("prep", lib.ecgb200_step_prep_bf16, None if self.raw_input else _p(self.x), _p(self.acts[0]), B, self.chan[0],
+                self.T, 1, PV(Pp(wkeys[0]), None, None, None), PV(_p(self.wt[0]), None, None, None), PV(None, None, None, None),
                 I4(self.chan[1], 0, 0, 0), I4(self.chan[0], 0, 0, 0), None, None, 0, 0, self.step_dev.data_ptr(), st)
         ev_prep = torch.cuda.Event()
         ev_prep.record(main)
-
-        def prep_rest():
-            # released by `prep`, but enqueued AFTER conv 1 so that the critical node is created (and launched) first
-            if self.linear:
-                self.side = main
-            else:
-                self.side.wait_event(ev_prep)
-            with torch.cuda.stream(self.side):
-                self._k("prep_w", lib.ecgb200_step_prep_bf16, None, None, 0, 0, 0, 3,
-                        PV(*[Pp(k) for k in wkeys[1:]], None), PV(*[_p(w) for w in self.wt[1:]], None),
-                        PV(*[_p(w) for w in self.wd[1:]], None), I4(*self.chan[2:5], 0), I4(*self.chan[1:4], 0),
-                        Pp(pre + "proj.weight"), _p(self.wpT),
-                        self.feat, self.chan[4], None, self.side.cuda_stream)
-                done = torch.cuda.Event()
-                done.record(self.side)
-            return done
-        import os
-        # creating prep_w's node after conv 1's measured slower (462 vs 448 us): conv 2 then waits for it
-        prep_late = os.environ.get("ECGB200_PREPW_LATE", "0") == "1"
-        prep_done = None if prep_late else prep_rest()
+        # released by `prep`; its node is created before conv 1's (created after it measured slower: conv 2 then waits)
+        if self.linear:
+            self.side = main
+        else:
+            self.side.wait_event(ev_prep)
+        with torch.cuda.stream(self.side):
+            self._k("prep_w", lib.ecgb200_step_prep_bf16, None, None, 0, 0, 0, 3,
+                    PV(*[Pp(k) for k in wkeys[1:]], None), PV(*[_p(w) for w in self.wt[1:]], None),
+                    PV(*[_p(w) for w in self.wd[1:]], None), I4(*self.chan[2:5], 0), I4(*self.chan[1:4], 0),
+                    Pp(pre + "proj.weight"), _p(self.wpT),
+                    self.feat, self.chan[4], None, self.side.cuda_stream)
+            prep_done = torch.cuda.Event()
+            prep_done.record(self.side)
         n += 2
         for l in range(4):
             cip, co, L = self.cip[l], self.chan[l + 1], self.L[l]
@@ -356,17 +401,26 @@ class TrainStep:
                 main.wait_event(prep_done)
             self._k("conv_fwd", lib.ecgb200_conv1d_fwd_stats_bf16, _p(self.acts[l]), _p(self.wt[l]), Pp(k + "0.bias"),
                     _p(self.ybuf[l]), _p(self.statp[l]), B, cip, co, L, st)
-            if l == 0 and prep_late:
-                self._prof_tag = ""
-                prep_done = prep_rest()
-                self._prof_tag = "_L1"
-            self._k("bn_relu_pool", lib.ecgb200_bn_relu_pool_fwd_train_bf16, _p(self.ybuf[l]), _p(self.statp[l]),
-                    self.nstat[l], Pp(k + "1.weight"), Pp(k + "1.bias"), bn.running_mean.data_ptr(),
+            stat, nparts, nrep = self.statp[l], self.nstat[l], 1
+            if self.sync_bn:
+                stat, nparts, nrep = self._bn_exchange(l, 0, self.statp[l], self.nstat[l], st), self.world, self.world
+                n += 1
+            self._k("bn_relu_pool", lib.ecgb200_bn_relu_pool_fwd_train_bf16, _p(self.ybuf[l]), _p(stat),
+                    nparts, Pp(k + "1.weight"), Pp(k + "1.bias"), bn.running_mean.data_ptr(),
                     bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(), _p(self.bnst[l]),
                     _p(self.acts[l + 1]) if l < 3 else None, _p(self.gap) if l == 3 else None, B, co, L,
-                    float(bn.momentum), float(bn.eps), st)
+                    float(bn.momentum), float(bn.eps), nrep, st)
             n += 2
         return n
+
+    def _bn_exchange(self, l, direction, part, nparts, st):
+        """SyncBN: all replicas' partial pairs of block l (direction 0 forward statistics, 1 backward sums) gathered
+        into bnsync[l] (world, 2, C) over peer memory."""
+        W = C.c_void_p * self.world
+        slot = 512 * 4 * (2 * l + direction)                    # byte offset of this exchange's slot
+        self._k("bn_sync", lib.ecgb200_dp_bn_sync_f32, _p(part), nparts, self.chan[l + 1],
+                W(*[p + slot for p in self.peer_bnx]), W(*self._flag_pad(2)), _p(self.bnsync[l]), self.rank, self.world, st)
+        return self.bnsync[l]
 
     def _fork_side(self, main):
         if self.linear:                      # single-stream schedule: "side" work is enqueued in line
@@ -393,65 +447,65 @@ class TrainStep:
             dy = dys[l & 1]
             if wg_done[l & 1] is not None:
                 main.wait_event(wg_done[l & 1])                # wgrad of block l+2 has finished reading this dy
-            if self.bn_dgrad_fuse and l < 3:
-                # the sums came out of dgrad_{l+1}'s epilogue: second pass only
-                self._k("bn_bwd", lib.ecgb200_bn_relu_pool_bwd_apply_bf16, _p(self.ybuf[l]), _p(self.bnst[l]), _p(self.dp),
-                        _p(self.bwpart[l]), self.nbw[l], _p(dy), Gp(k + "1.weight"), Gp(k + "1.bias"), _p(self.dbpart[l]),
-                        B, co, L, 1, st)
-                n += 1
+            dpb, dgap = (_p(self.dp), None) if l < 3 else (None, _p(self.dgap))
+            if self.sync_bn:
+                # reduce -> exchange over peer memory -> apply with the sums of the GLOBAL batch
+                self._k("bn_bwd", lib.ecgb200_bn_relu_pool_bwd_reduce_bf16, _p(self.ybuf[l]), _p(self.bnst[l]), dpb, dgap,
+                        _p(self.ws2), B, co, L, st)
+                merged = self._bn_exchange(l, 1, self.ws2, self.ndb[l], st)
+                self._k("bn_bwd_apply", lib.ecgb200_bn_relu_pool_bwd_apply_bf16, _p(self.ybuf[l]), _p(self.bnst[l]), dpb, dgap,
+                        _p(merged), self.world, self.rank, self.world, _p(dy), Gp(k + "1.weight"), Gp(k + "1.bias"),
+                        _p(self.dbpart[l]), B, co, L, 1, st)
+                n += 3
             else:
-                self._k("bn_bwd", lib.ecgb200_bn_relu_pool_bwd_fused_bf16 if self.bn_fused[l] else lib.ecgb200_bn_relu_pool_bwd_bf16,
-                        _p(self.ybuf[l]), _p(self.bnst[l]),
-                        _p(self.dp) if l < 3 else None, _p(self.dgap) if l == 3 else None, _p(dy),
+                self._k("bn_bwd", lib.ecgb200_bn_relu_pool_bwd_bf16, _p(self.ybuf[l]), _p(self.bnst[l]), dpb, dgap, _p(dy),
                         Gp(k + "1.weight"), Gp(k + "1.bias"), _p(self.dbpart[l]), _p(self.ws2), B, co, L, 1, st)
-                n += 1 if self.bn_fused[l] else 2
-            # Order matters: the tensor kernels cannot share an SM (TMEM + shared memory), so whichever of dgrad_l
-            # (critical path) and wgrad_l (side) the graph launches first takes the GPU, and ready nodes are launched in
-            # creation order.  Measured (same box, us/step): wgrad node created first ("early") 476 -- or 456 when a
-            # slower head_wgrad happened to delay it; wgrad released only after dgrad completes ("after") 466;
-            # both released by bn_bwd_l with dgrad's node created first ("both", the default) 453.
-            import os
-            mode = os.environ.get("ECGB200_WGRAD_ORDER", "both")
-            early = mode == "early"
-            ev_bn = None
-            if mode == "both":                       # both released by bn_bwd_l, but dgrad's node is created first
-                ev_bn = torch.cuda.Event()
-                ev_bn.record(main)
-            if l > 0 and not early:
-                self._dgrad(l, dy, st)
+                n += 2
+            # Order matters: the tensor kernels of the two branches share the SMs one CTA at a time (TMEM + shared
+            # memory), and ready graph nodes are launched in creation order.  Both dgrad_l (critical path) and wgrad_l
+            # (side) are released by bn_bwd_l, with dgrad's node created first (measured, us/step: wgrad first 476,
+            # wgrad released only after dgrad completes 466, this order 453).
+            ev_bn = torch.cuda.Event()
+            ev_bn.record(main)
+            if l > 0:
+                self._k("dgrad", lib.ecgb200_conv1d_fwd_bf16, _p(dy), _p(self.wd[l]), None, _p(self.dp), B, co, ci, L, st)
                 n += 1
-            if ev_bn is not None and not self.linear:
-                self.side.wait_event(ev_bn)
+            if self.linear:
+                self.side = main
             else:
-                self._fork_side(main)
+                self.side.wait_event(ev_bn)
             with torch.cuda.stream(self.side):
                 self._k("wgrad", lib.ecgb200_conv1d_wgrad_bf16, _p(dy), _p(self.acts[l]), Gp(k + "0.weight"),
                         Gp(k + "0.bias"), _p(self.dbpart[l]), self.ndb[l], _p(self.ws), B, ci, co, L,
                         self.side.cuda_stream)
                 wg_done[l & 1] = torch.cuda.Event()
                 wg_done[l & 1].record(self.side)
-                if l == 3 and self.world > 1 and not self.dp_fused:
-                    # bucket A (block 4, the tail of G) is final: all-reduce it while blocks 3..1 run
-                    self.comm.wait_event(wg_done[l & 1])
-                    with torch.cuda.stream(self.comm):
-                        torch.distributed.all_reduce(self.G[self.bucket_a_off:], group=self.pg)
             n += 2
-            if l > 0 and early:
-                self._dgrad(l, dy, st)
-                n += 1
+            if l == 3 and self.world > 1:
+                # bucket A (block 4 = the tail of the flat buffers; bn_bwd_4 already left its BatchNorm gradients there) is
+                # final: exchange it on the communication stream while blocks 3..1 run backward
+                self.comm.wait_event(wg_done[l & 1])
+                with torch.cuda.stream(self.comm):
+                    if self.dp_fused:
+                        self._dp_exchange(0, self.comm.cuda_stream)
+                        n += 1
+                    else:
+                        torch.distributed.all_reduce(self.G[self.bucket_a_off:], group=self.pg)
         return n
 
-    def _dgrad(self, l, dy, st):
-        """Input gradient of block l (= dp of block l-1); with bn_dgrad_fuse its epilogue also leaves block l-1's
-        BatchNorm-backward sums in bwpart[l-1]."""
-        B, ci, co, L = self.B, self.chan[l], self.chan[l + 1], self.L[l]
-        if self.bn_dgrad_fuse:
-            self._k("dgrad", lib.ecgb200_conv1d_dgrad_bnstats_bf16, _p(dy), _p(self.wd[l]), _p(self.dp), _p(self.ybuf[l - 1]),
-                    _p(self.bnst[l - 1]), _p(self.bwpart[l - 1]), B, co, ci, L, self.L[l - 1], st)
-        else:
-            self._k("dgrad", lib.ecgb200_conv1d_fwd_bf16, _p(dy), _p(self.wd[l]), None, _p(self.dp), B, co, ci, L, st)
+    def _dp_exchange(self, which, st):
+        """Bucket `which` (0 = block 4, 1 = the rest): reduce-scatter + AdamW on the owned shard + all-gather, one
+        kernel over NVLink peer memory."""
+        off, cnt, pad = self._buckets()[which]
+        W = C.c_void_p * self.world
+        self._prof_tag = "_A" if which == 0 else "_B"
+        self._k("dp_adamw_fused", lib.ecgb200_dp_adamw_fused_range_f32, W(*self.peer_p), W(*self.peer_g),
+                W(*self._flag_pad(pad)), self.M.data_ptr(), self.V.data_ptr(), off, cnt, self.rank, self.world,
+                self.hyper.data_ptr(), self.step_dev.data_ptr(), st)
+        self._prof_tag = ""
 
     def _bwd_blocks(self, st, pre, Pp, Gp):
+        """fp32 engine: BN/ReLU/pool backward -> wgrad -> dgrad, block 4 down to 1, on one stream."""
         B = self.B
         n = 0
         main = torch.cuda.current_stream(self.dev)
@@ -459,18 +513,11 @@ class TrainStep:
             ci, co, L = self.chan[l], self.chan[l + 1], self.L[l]
             k = f"{pre}backbone.{l}.net."
             self._prof_tag = f"_L{l + 1}"
-            if self.bf16:
-                self._k("bn_bwd", lib.ecgb200_bn_relu_pool_bwd_bf16, _p(self.ybuf[l]), _p(self.bnst[l]),
-                        _p(self.dp) if l < 3 else None, _p(self.dgap) if l == 3 else None, _p(self.dy),
-                        Gp(k + "1.weight"), Gp(k + "1.bias"), _p(self.dbpart[l]), _p(self.ws2), B, co, L, 1, st)
-                self._k("wgrad", lib.ecgb200_conv1d_wgrad_bf16, _p(self.dy), _p(self.acts[l]), Gp(k + "0.weight"),
-                        Gp(k + "0.bias"), _p(self.dbpart[l]), self.ndb[l], _p(self.ws), B, ci, co, L, st)
-            else:
-                self._k("bn_bwd", lib.ecgb200_bn_relu_pool_bwd_f32, _p(self.ybuf[l]), _p(self.bnst[l]), Pp(k + "1.weight"),
-                        _p(self.dp) if l < 3 else None, _p(self.dgap) if l == 3 else None,
-                        _p(self.dy), Gp(k + "1.weight"), Gp(k + "1.bias"), _p(self.ws), B, co, L, 1, st)
-                self._k("wgrad", lib.ecgb200_conv1d_wgrad_f32, _p(self.dy), _p(self.acts[l]), Gp(k + "0.weight"),
-                        Gp(k + "0.bias"), _p(self.ws), B, ci, co, L, st)
+            self._k("bn_bwd", lib.ecgb200_bn_relu_pool_bwd_f32, _p(self.ybuf[l]), _p(self.bnst[l]), Pp(k + "1.weight"),
+                    _p(self.dp) if l < 3 else None, _p(self.dgap) if l == 3 else None,
+                    _p(self.dy), Gp(k + "1.weight"), Gp(k + "1.bias"), _p(self.ws), B, co, L, 1, st)
+            self._k("wgrad", lib.ecgb200_conv1d_wgrad_f32, _p(self.dy), _p(self.acts[l]), Gp(k + "0.weight"),
+                    Gp(k + "0.bias"), _p(self.ws), B, ci, co, L, st)
             n += 5
             if l == 3 and self.world > 1:
                 # bucket A (block 4, the tail of G) is final: all-reduce it while blocks 3..1 run
@@ -480,12 +527,8 @@ class TrainStep:
                 with torch.cuda.stream(self.side):
                     torch.distributed.all_reduce(self.G[self.bucket_a_off:], group=self.pg)
             if l > 0:
-                if self.bf16:
-                    self._k("dgrad", lib.ecgb200_conv1d_fwd_bf16, _p(self.dy), _p(self.wd[l]), None, _p(self.dp),
-                            B, co, ci, L, st)
-                else:
-                    self._k("dgrad", lib.ecgb200_conv1d_fwd_f32, _p(self.dy), _p(self.wd[l]), None, _p(self.dp), None,
-                            B, co, ci, L, st)
+                self._k("dgrad", lib.ecgb200_conv1d_fwd_f32, _p(self.dy), _p(self.wd[l]), None, _p(self.dp), None,
+                        B, co, ci, L, st)
                 n += 1
         return n
 
@@ -507,17 +550,7 @@ class TrainStep:
         blocks = list(self.bb.backbone)
         # ---- forward
         if self.bf16:
-            # ECGB200_PDL=fwd: programmatic dependent launch for the forward chain only (no weight-gradient branch
-            # competes for SM slots there)
-            import os
-            fwd_pdl = self.use_graph and os.environ.get("ECGB200_PDL", "0") == "fwd"
-            if fwd_pdl:
-                old_pdl = lib.ecgb200_set_pdl(1)
-            try:
-                n += self._fwd_blocks_bf16(st, pre, Pp, blocks)
-            finally:
-                if fwd_pdl:
-                    lib.ecgb200_set_pdl(old_pdl)
+            n += self._fwd_blocks_bf16(st, pre, Pp, blocks)
         else:
             n += self._fwd_blocks_fp32(st, pre, Pp, blocks)
         self._prof_tag = ""
@@ -588,18 +621,18 @@ class TrainStep:
             ev3.record(self.side)
             main.wait_event(ev3)                                # join the weight-gradient branch
             if self.dp_fused:
-                # reduce-scatter + AdamW on the owned shard + all-gather, one kernel over NVLink peer memory
-                W = C.c_void_p * self.world
-                self._k("dp_adamw_fused", lib.ecgb200_dp_adamw_fused_f32, W(*self.peer_p), W(*self.peer_g),
-                        W(*self.peer_f), self.M.data_ptr(), self.V.data_ptr(), self.total_pad, self.rank, self.world,
-                        self.hyper.data_ptr(), self.step_dev.data_ptr(), st)
+                # bucket B (everything but block 4); bucket A went out under the backward of blocks 3..1
+                self._dp_exchange(1, st)
+                ev4 = torch.cuda.Event()
+                ev4.record(self.comm)
+                main.wait_event(ev4)                            # join the bucket-A exchange
             else:
                 self._k("adamw", lib.ecgb200_adamw_flat_f32, self.P.data_ptr(), self.G.data_ptr(), self.M.data_ptr(),
                         self.V.data_ptr(), self.total_pad, self.hyper.data_ptr(), self.step_dev.data_ptr(), st)
             n += 1
         else:
             one = C.c_void_p * 1
-            num = (C.c_int64 * 1)(self.total)
+            num = (C.c_int64 * 1)(self.total_pad)        # pads hold p = g = 0 and stay 0
             self._k("adamw", lib.ecgb200_adamw_f32, 1, one(self.P.data_ptr()), one(self.G.data_ptr()), one(self.M.data_ptr()),
                     one(self.V.data_ptr()), num, self.hyper.data_ptr(), self.step_dev.data_ptr(), st)
             n += 2
@@ -667,16 +700,7 @@ class TrainStep:
             return
         # warm-up outside capture would advance the optimizer; capture directly instead
         torch.cuda.synchronize(self.dev)
-        import os
-        # programmatic dependent launch of the conv / BN-forward chain measured slower in the step (460 vs 449 us:
-        # early-scheduled dependents take SM slots from the weight-gradient branch), so it is opt-in
-        old = lib.ecgb200_set_pdl(1 if (self.bf16 and os.environ.get("ECGB200_PDL", "0") == "1") else 0)
-        # Capturing the critical path on a higher-priority stream than the weight-gradient branch (so that dgrad
-        # wins the SMs over wgrad when both become ready) measured slightly SLOWER (460 vs 451 us): the step is
-        # bound by the sum of the tensor kernels, which cannot share an SM (TMEM / shared memory), not by their
-        # order.  Equal priorities by default.
-        prio = os.environ.get("ECGB200_MAIN_PRIORITY", "0")
-        self.capture_stream = torch.cuda.Stream(device=self.dev, priority=int(prio)) if self.bf16 else None
+        self.capture_stream = torch.cuda.Stream(device=self.dev) if self.bf16 else None
         keep = self.cur
         graphs = []
         try:
@@ -687,7 +711,6 @@ class TrainStep:
                     self._enqueue()
                 graphs.append(g)
         finally:
-            lib.ecgb200_set_pdl(old)
             self._select(keep)
         self.graphs = graphs
         self.graph = graphs[0]
@@ -710,6 +733,36 @@ class TrainStep:
             self._prof = None
             self.opt.param_groups[0]["step"] = self.opt.param_groups[0].get("step", 0) + 1
         return [(n, acc[n] / iters) for n in order]
+
+    def trace_schedule(self, replays: int = 5):
+        """The schedule the captured two-stream step REALLY runs (no nsys on the box): the step is captured once more with
+        a one-thread %globaltimer stamp kernel before and after every C-ABI call on that call's stream, replayed, and the
+        last replay's stamps are returned as [(name, stream id, start us, end us)] relative to the first stamp.  Every stamp
+        costs ~1.5 us of its stream, so the traced step is slower than the real one: read overlaps and gaps, not totals.
+        Advances training by `replays` steps."""
+        self._refresh_views()
+        buf = torch.zeros(512, dtype=torch.int64, device=self.dev)
+        names = []
+        self._stamps = (buf, names)
+        try:
+            torch.cuda.synchronize(self.dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=torch.cuda.Stream(device=self.dev)):
+                self._enqueue()
+        finally:
+            self._stamps = None
+        for _ in range(replays):
+            g.replay()
+        torch.cuda.synchronize(self.dev)
+        self.opt.param_groups[0]["step"] = self.opt.param_groups[0].get("step", 0) + replays
+        t = buf.cpu().tolist()
+        t0 = min(v for v in t[:2 * len(names)] if v)
+        streams = {}
+        out = []
+        for i, (n, st) in enumerate(names):
+            sid = streams.setdefault(st, len(streams))
+            out.append((n, sid, (t[2 * i] - t0) / 1000.0, (t[2 * i + 1] - t0) / 1000.0))
+        return out
 
     def time_kernels(self, iters: int = 10):
         """Device time of every C-ABI call of the step, free of host launch overhead: each call is captured
@@ -768,12 +821,46 @@ class TrainStep:
         if slot is None:
             self._select(s)
 
+    def load_frames(self, frames, y, demo=None, slot=None):
+        """raw_input engines: copy a batch of raw WFDB format-16 frames (B, T, leads) int16 (pinned host or device) into an
+        input slot; the graph decodes, z-scores and packs them on the device (set_calibration for gain / baseline)."""
+        if not self.raw_input:
+            raise EcgB200Error("load_frames() needs TrainStep(..., raw_input=True)")
+        s = (self.cur ^ 1) if slot is None else int(slot)
+        if tuple(frames.shape) != tuple(self.frames[s].shape) or frames.dtype != torch.int16:
+            raise EcgB200Error(f"expected int16 frames {tuple(self.frames[s].shape)}, got {frames.dtype} {tuple(frames.shape)}")
+        self.frames[s].copy_(frames, non_blocking=True)
+        self.ys[s].copy_(y, non_blocking=True)
+        if self.mm:
+            if demo is None:
+                raise EcgB200Error("ECGMultimodal step needs x_demo")
+            self.demos[s].copy_(demo, non_blocking=True)
+        if slot is None:
+            self._select(s)
+
+    def set_calibration(self, gain, baseline):
+        """Per-lead ADC gain (units per mV) and baseline of the .hea header for raw_input engines."""
+        self.gain.copy_(torch.as_tensor(gain, dtype=F32).reshape(-1))
+        self.baseline.copy_(torch.as_tensor(baseline, dtype=torch.int32).reshape(-1))
+
+    def close(self):
+        """Drop the captured graphs and the NVLink peer mappings (call before destroy_process_group())."""
+        self.graph = None
+        self.graphs = None
+        torch.cuda.synchronize(self.dev)
+        for name in ("_symm_handles", "peer_p", "peer_g", "peer_f", "peer_bnx"):
+            if hasattr(self, name):
+                delattr(self, name)
+
     def run(self, slot=None):
         """One optimizer step on whatever input slot `slot` (default: the current one) holds.  Returns the loss
         buffer (device scalar, overwritten by the next step)."""
         if slot is not None and int(slot) != self.cur:
             self._select(int(slot))
         group = self.opt.param_groups[0]
+        if group.get("_step_dev") is not self.step_dev or \
+                self.opt.state[self._probe.param].get("exp_avg", self.M).data_ptr() != self.M.data_ptr() + 4 * self._probe.off:
+            self._refresh_views()                               # optimizer.load_state_dict() after the engine was built
         hyper, _ = self.opt.device_state(group, self.dev)
         if hyper.data_ptr() != self.hyper.data_ptr():          # lr / betas changed on the host
             self.hyper.copy_(hyper)

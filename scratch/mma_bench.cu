@@ -7,7 +7,7 @@
 
 __global__ void __launch_bounds__(320, 1)
 mma_bench(int N, int nmma, int shift16, int nacc, int lbo, int sbo, int amn, int bmn, int a_stride, int b_stride,
-          long long* out, int mode, int M) {
+          long long* out, int mode, int M, int blbo, int bsbo) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
     uint32_t* slot = reinterpret_cast<uint32_t*>(smem + 64);
@@ -134,11 +134,15 @@ mma_bench(int N, int nmma, int shift16, int nacc, int lbo, int sbo, int amn, int
                     uint32_t dd[4], al[4], bl[4], fl[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) { dd[e] = tmem + vz; al[e] = alo + (uint32_t)e * astep + vz; bl[e] = blo + (uint32_t)e * bstep; fl[e] = 1u; }
-                    if (leader) tc::mma_bf16_x4(dd, al, bl, fl, ahi, bhi, idesc);
+                    uint64_t a64[4], b64[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { a64[e] = ((uint64_t)ahi << 32) | al[e]; b64[e] = ((uint64_t)bhi << 32) | bl[e]; }
+                    (void)fl;
+                    if (leader) tc::mma_bf16_x4<0xF>(dd, a64, b64, idesc);
                     if (mode == 12) {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) { al[e] += 4 * astep; bl[e] += 4 * bstep; }
-                        if (leader) tc::mma_bf16_x4(dd, al, bl, fl, ahi, bhi, idesc);
+                        for (int e = 0; e < 4; ++e) { a64[e] += 4 * astep; b64[e] += 4 * bstep; }
+                        if (leader) tc::mma_bf16_x4<0xF>(dd, a64, b64, idesc);
                     }
                     alo += 4 * astep; blo += 4 * bstep;
                     if ((i & 15) == 12) { alo -= 16 * astep; blo -= 16 * bstep; }
@@ -191,7 +195,7 @@ mma_bench(int N, int nmma, int shift16, int nacc, int lbo, int sbo, int amn, int
         const long long t0 = clock64();
         for (int i = 0; i < nmma; ++i) {
             const uint64_t ad = tc::make_desc(a0 + (uint32_t)((i % 15) * shift16 * 16) + (uint32_t)((i & 3) * a_stride), lbo, sbo);
-            const uint64_t bd = tc::make_desc(b0 + (uint32_t)((i & 3) * b_stride), (uint32_t)(bmn ? 128 : N * 16), bmn ? 16 : 128);
+            const uint64_t bd = tc::make_desc(b0 + (uint32_t)((i & 3) * b_stride), (uint32_t)(blbo ? blbo : (bmn ? 128 : N * 16)), (uint32_t)(bsbo ? bsbo : (bmn ? 16 : 128)));
             tc::mma_bf16(tmem + (uint32_t)((i % nacc) * N), ad, bd, idesc, i >= nacc ? 1u : 0u);
         }
         const long long t1 = clock64();
@@ -211,7 +215,7 @@ int main() {
     const int smem = 1024 + 200 * 1024;
     cudaFuncSetAttribute(mma_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     const int nmma = 240;
-    struct Case { const char* name; int N, shift, nacc, lbo, sbo, amn, bmn, astr, bstr; int mode = 0, M = 128; };
+    struct Case { const char* name; int N, shift, nacc, lbo, sbo, amn, bmn, astr, bstr; int mode = 0, M = 128, blbo = 0, bsbo = 0; };
     const Case cases[] = {
         {"fwd K-major N=256 aligned 1acc", 256, 0, 1, 144 * 16, 128, 0, 0, 2 * 144 * 16, 2 * 256 * 16},
         {"fwd K-major N=256 shifted 1acc", 256, 1, 1, 144 * 16, 128, 0, 0, 2 * 144 * 16, 2 * 256 * 16},
@@ -247,10 +251,8 @@ int main() {
         {"uniform-warp lean N=128 shift 2acc", 128, 1, 2, 144 * 16, 128, 0, 0, 36864, 4096, 5, 128},
         {"uniform add per MMA N=32", 32, 1, 1, 144 * 16, 128, 0, 0, 0, 1024, 10, 128},
         {"uniform batch4 N=32", 32, 1, 1, 144 * 16, 128, 0, 0, 0, 1024, 11, 128},
-        {"uniform batch8 N=32", 32, 1, 1, 144 * 16, 128, 0, 0, 0, 1024, 12, 128},
         {"vector batch4 N=32", 32, 1, 1, 144 * 16, 128, 0, 0, 0, 1024, 13, 128},
         {"uniform batch4 N=128", 128, 1, 1, 144 * 16, 128, 0, 0, 0, 4096, 11, 128},
-        {"uniform batch8 N=128", 128, 1, 1, 144 * 16, 128, 0, 0, 0, 4096, 12, 128},
         {"alt A (tile stride 5120) N=32", 32, 0, 1, 144 * 16, 128, 0, 0, 5120, 1024, 6, 128},
         {"alt A (+16 B) N=32", 32, 0, 1, 144 * 16, 128, 0, 0, 16, 1024, 6, 128},
         {"alt A (+128 B) N=32", 32, 0, 1, 144 * 16, 128, 0, 0, 128, 1024, 6, 128},
@@ -259,12 +261,24 @@ int main() {
         {"alt A+B N=32", 32, 0, 1, 144 * 16, 128, 0, 0, 5120, 1024, 9, 128},
         {"alt A+B N=128", 128, 0, 1, 144 * 16, 128, 0, 0, 5120, 4096, 9, 128},
         {"alt A+B N=256", 256, 0, 1, 144 * 16, 128, 0, 0, 5120, 8192, 9, 128},
-        {"wgrad MN-major N=128 taps-as-N 1acc", 128, 0, 1, 128, 128 * 16, 1, 1, 256, 256},
-        {"wgrad MN-major N=128 taps-as-N 4acc", 128, 0, 4, 128, 128 * 16, 1, 1, 256, 256},
+        // round 2 (mode 1 = invariant descriptors: pure tensor-pipe rate of the operand geometry)
+        {"wgrad both MN-major, B taps-as-N N=128", 128, 0, 1, 128, 128 * 16, 1, 1, 256, 256, 1, 128, 0, 0},
+        {"wgrad A K-major / B taps-as-N N=128", 128, 0, 1, 128 * 16, 128, 0, 1, 256, 256, 1, 128, 0, 0},
+        {"taps-as-M A(sbo16) / B MN-major N=32", 32, 0, 1, 128, 16, 1, 1, 256, 256, 1, 128, 128, 2048},
+        {"taps-as-M A(sbo16) / B MN-major N=64", 64, 0, 1, 128, 16, 1, 1, 256, 256, 1, 128, 128, 2048},
+        {"taps-as-M A(sbo16) / B MN-major N=128", 128, 0, 1, 128, 16, 1, 1, 256, 256, 1, 128, 128, 2048},
+        {"taps-as-M A(sbo16) / B MN-major N=256", 256, 0, 1, 128, 16, 1, 1, 256, 256, 1, 128, 128, 2048},
+        {"MN-major A(sbo 2K) / MN-major B(sbo 2K) N=128", 128, 0, 1, 128, 128 * 16, 1, 1, 256, 256, 1, 128, 128, 2048},
+        {"MN-major A(sbo 2K) / MN-major B(sbo 2K) N=32", 32, 0, 1, 128, 128 * 16, 1, 1, 256, 256, 1, 128, 128, 2048},
+        {"K-major A / MN-major B(sbo 2K) N=128", 128, 0, 1, 128 * 16, 128, 0, 1, 256, 256, 1, 128, 128, 2048},
+        {"MN-major A(sbo 2K) / K-major B N=128", 128, 0, 1, 128, 128 * 16, 1, 0, 256, 256, 1, 128, 0, 0},
+        {"taps-as-M A(sbo16) / K-major B N=32", 32, 0, 1, 128, 16, 1, 0, 256, 256, 1, 128, 0, 0},
+        {"taps-as-M A(sbo16) / K-major B N=64", 64, 0, 1, 128, 16, 1, 0, 256, 256, 1, 128, 0, 0},
+        {"taps-as-M A(sbo16) / K-major B N=128", 128, 0, 1, 128, 16, 1, 0, 256, 256, 1, 128, 0, 0},
     };
     for (const Case& c : cases) {
         for (int rep = 0; rep < 2; ++rep)
-            mma_bench<<<148, c.mode >= 3 ? 320 : 128, smem>>>(c.N, nmma, c.shift, c.nacc, c.lbo, c.sbo, c.amn, c.bmn, c.astr, c.bstr, out, c.mode, c.M);
+            mma_bench<<<148, c.mode >= 3 ? 320 : 128, smem>>>(c.N, nmma, c.shift, c.nacc, c.lbo, c.sbo, c.amn, c.bmn, c.astr, c.bstr, out, c.mode, c.M, c.blbo, c.bsbo);
         cudaError_t e = cudaDeviceSynchronize();
         long long h[2];
         cudaMemcpy(h, out, 16, cudaMemcpyDeviceToHost);

@@ -6,7 +6,7 @@ BF = torch.bfloat16
 names = {0: 'start', 32: 'all issued', 33: 'acc full', 34: 'epi done'}
 for n in range(8):
     names[8 + n] = f'ld{n} issued'; names[16 + n] = f'ld{n} landed'; names[24 + n] = f'mma{n} issued'
-for (B, Ci, Co, L) in [(256, 128, 256, 125), (256, 64, 128, 250), (256, 12, 32, 1000)]:
+for (B, Ci, Co, L) in [(256, 128, 256, 125), (256, 64, 128, 250), (256, 32, 64, 500), (256, 12, 32, 1000)]:
     Cip = (Ci + 15) // 16 * 16
     xb = torch.randn(B, Cip // 8, L, 8, device='cuda').to(BF)
     dyb = torch.randn(B, Co // 8, L, 8, device='cuda').to(BF)

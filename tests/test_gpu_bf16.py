@@ -191,7 +191,7 @@ def test_conv_stats_and_fused_bn_forward(B, Ci, Co, L):
         gap = torch.empty(B, Co, device=DEV) if use_gap else None
         check(lib.ecgb200_bn_relu_pool_fwd_train_bf16(ptr(yb), ptr(part), nparts, ptr(gg), ptr(btg), ptr(rmg), ptr(rvg),
                                                       ptr(nbt), ptr(st), ptr(pb), ptr(gap), B, Co, L, 0.1, 1e-5,
-                                                      stream()), "bn_fwd_train")
+                                                      1, stream()), "bn_fwd_train")
         torch.cuda.synchronize()
         # reference statistics from the values the GPU actually stored (y differs from yref by bf16 ties)
         rm2, rv2 = torch.zeros(Co), torch.ones(Co)
@@ -288,12 +288,14 @@ def test_step_prep_and_flat_adamw():
     assert torch.equal(pa, pb_) and torch.equal(ma, mb) and torch.equal(va, vb)
 
 
-@pytest.mark.parametrize("B,C,L", [(4, 32, 1000), (3, 64, 250), (5, 256, 125), (2, 128, 31), (256, 64, 500), (64, 256, 125)])
+@pytest.mark.parametrize("B,C,L", [(4, 32, 1000), (6, 64, 250), (4, 256, 125), (2, 128, 31), (256, 64, 500), (64, 256, 125)])
 @pytest.mark.parametrize("use_gap", [False, True])
-def test_bn_backward_fused_equals_two_kernel_path(B, C, L, use_gap):
-    """One cooperative launch (reduce -> grid barrier -> apply from shared memory) == the reduce + apply pair."""
-    ns = lib.ecgb200_bn_bwd_fused_nsplit(B, C, L, 0 if use_gap else 1)
-    assert ns > 0
+def test_bn_backward_split_passes_and_syncbn_on_one_gpu(B, C, L, use_gap):
+    """(a) The reduce and apply passes as separate C-ABI calls == the combined call, bit for bit.
+    (b) SyncBN arithmetic emulated on one GPU: the batch is cut into two "replicas"; each runs pass 1 on its half,
+    the per-replica pairs are gathered in rank order (what ecgb200_dp_bn_sync_f32 does over peer memory) and pass 2 runs
+    per half with nrep = 2 -- the halves' dy equal the single-device result on the whole batch, and the per-replica
+    dgamma / dbeta add up to the whole batch's (the gradient exchange sums them)."""
     y = (gen(B, C, L, seed=5) * 1.7 + 0.3)
     gamma, beta = (1 + 0.2 * gen(C, seed=6)).to(DEV), (0.1 * gen(C, seed=7)).to(DEV)
     yb = to_blocked(y).to(DEV)
@@ -307,22 +309,55 @@ def test_bn_backward_fused_equals_two_kernel_path(B, C, L, use_gap):
     dout = gen(B, C, seed=11) if use_gap else gen(B, C, Lp, seed=11)
     dpb = None if use_gap else to_blocked(dout).to(DEV)
     dgap = dout.to(DEV) if use_gap else None
-    res = []
-    for fused in (False, True):
-        dyb = torch.full((B, C // 8, L, 8), float("nan"), dtype=BF, device=DEV)
+
+    def combined(yb_, dpb_, dgap_, b):
+        dyb = torch.full((b, C // 8, L, 8), float("nan"), dtype=BF, device=DEV)
         dgm, dbt = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
-        nsp = ns if fused else lib.ecgb200_bn_nsplit(B, C)
-        dbp = torch.empty(C, nsp, device=DEV)
-        fn = lib.ecgb200_bn_relu_pool_bwd_fused_bf16 if fused else lib.ecgb200_bn_relu_pool_bwd_bf16
-        check(fn(ptr(yb), ptr(st), ptr(dpb), ptr(dgap), ptr(dyb), ptr(dgm), ptr(dbt), ptr(dbp), ptr(ws), B, C, L, 1,
-                 stream()), "bn_bwd")
+        dbp = torch.empty(C, lib.ecgb200_bn_nsplit(b, C), device=DEV)
+        check(lib.ecgb200_bn_relu_pool_bwd_bf16(ptr(yb_), ptr(st), ptr(dpb_), ptr(dgap_), ptr(dyb), ptr(dgm), ptr(dbt), ptr(dbp),
+                                                ptr(ws), b, C, L, 1, stream()), "bn_bwd")
         torch.cuda.synchronize()
-        res.append((dyb.float().cpu(), dgm.cpu(), dbt.cpu(), dbp.sum(dim=1).cpu()))
-    (dy0, g0, b0, s0), (dy1, g1, b1, s1) = res
-    assert torch.isfinite(dy1).all()
-    assert rel_inf(g1, g0) < 1e-5 and rel_inf(b1, b0) < 1e-5
-    assert rel_inf(dy1, dy0) < 8e-3                      # same math, different partial-sum grouping: bf16 ties
-    assert float((s1 - s0).abs().max()) <= 1e-3 * float(s0.abs().max()) + 1e-2
+        return dyb, dgm, dbt, dbp
+
+    def reduce(yb_, dpb_, dgap_, b):
+        ns = lib.ecgb200_bn_nsplit(b, C)
+        part = torch.full((ns, 2, C), float("nan"), device=DEV)
+        check(lib.ecgb200_bn_relu_pool_bwd_reduce_bf16(ptr(yb_), ptr(st), ptr(dpb_), ptr(dgap_), ptr(part), b, C, L, stream()),
+              "bn_bwd_reduce")
+        return part
+
+    def apply(yb_, dpb_, dgap_, b, part, local_idx, nrep):
+        dyb = torch.full((b, C // 8, L, 8), float("nan"), dtype=BF, device=DEV)
+        dgm, dbt = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+        dbp = torch.empty(C, lib.ecgb200_bn_nsplit(b, C), device=DEV)
+        check(lib.ecgb200_bn_relu_pool_bwd_apply_bf16(ptr(yb_), ptr(st), ptr(dpb_), ptr(dgap_), ptr(part), part.shape[0],
+                                                      local_idx, nrep, ptr(dyb), ptr(dgm), ptr(dbt), ptr(dbp), b, C, L, 1,
+                                                      stream()), "bn_bwd_apply")
+        torch.cuda.synchronize()
+        return dyb, dgm, dbt, dbp
+
+    dy0, g0, b0, s0 = combined(yb, dpb, dgap, B)
+    # (a) split passes
+    part = reduce(yb, dpb, dgap, B)
+    dy1, g1, b1, s1 = apply(yb, dpb, dgap, B, part, -1, 1)
+    assert torch.equal(dy0, dy1) and torch.equal(g0, g1) and torch.equal(b0, b1) and torch.equal(s0, s1)
+    # (b) two replicas of B/2 windows each, statistics (bn_state) of the whole batch
+    h = B // 2
+    halves = []
+    for r in range(2):
+        sl = slice(r * h, (r + 1) * h)
+        halves.append((yb[sl].contiguous(), None if use_gap else dpb[sl].contiguous(), dgap[sl].contiguous() if use_gap else None))
+    pairs = torch.stack([reduce(*hv, h).double().sum(dim=0).float() for hv in halves])      # (2, 2, C): one pair per replica
+    # the whole batch's upstream gradient is what each replica sees (same loss scaling): compare directly
+    gsum, bsum = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+    for r, hv in enumerate(halves):
+        dyr, gr, br, _ = apply(*hv, h, pairs, r, 2)
+        ref = dy0[r * h:(r + 1) * h].float()
+        assert torch.isfinite(dyr.float()).all()
+        assert rel_inf(dyr.float().cpu(), ref.cpu()) < 8e-3                 # same math, another summation order: bf16 ties
+        assert float((dyr.float() != ref).float().mean()) < 2e-3
+        gsum += gr; bsum += br
+    assert rel_inf(gsum, g0) < 2e-5 and rel_inf(bsum, b0) < 2e-5
 
 
 @pytest.mark.parametrize("B", [256, 7])
@@ -378,63 +413,3 @@ def test_fused_multimodal_head(B):
     for (w, b), (kw, kb) in zip(zip(dw, db), (("wp", "bp"), ("wh", "bh"), ("wf", "bf"), ("w2", "b2"), ("w0", "b0"))):
         assert rel_inf(w, L[kw].grad) < tol, kw
         assert rel_inf(b, L[kb].grad) < tol, kb
-
-
-@pytest.mark.parametrize("B,Cn,C,Lprev", [(3, 64, 32, 1000), (2, 128, 64, 500), (3, 256, 128, 250), (2, 256, 128, 251),
-                                          (1, 64, 32, 41), (256, 64, 32, 1000), (200, 256, 128, 250)])
-def test_dgrad_with_bn_backward_sums_equals_separate_reduce(B, Cn, C, Lprev):
-    """conv_tc_kernel<4>: dgrad of block l+1 whose epilogue also produces block l's {sum g, sum g*a} == plain dgrad
-    (bit-exact dp) followed by bn_bwd_reduce (sums to fp32 round-off), and the apply pass fed with those partials
-    gives the reduce + apply pair's dy / dgamma / dbeta."""
-    L = Lprev // 2
-    y = gen(B, C, Lprev, seed=5) * 1.7 + 0.3
-    gamma, beta = (1 + 0.2 * gen(C, seed=6)).to(DEV), (0.1 * gen(C, seed=7)).to(DEV)
-    gamma[::5] *= -1.0
-    yb = to_blocked(y).to(DEV)
-    rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
-    nbt = torch.zeros((), dtype=torch.int64, device=DEV)
-    st = torch.empty(4, C, device=DEV)
-    ws = torch.zeros(lib.ecgb200_bn_bwd_ws_bytes(B, C), dtype=torch.uint8, device=DEV)
-    check(lib.ecgb200_bn_train_stats_bf16(ptr(yb), ptr(gamma), ptr(beta), ptr(rm), ptr(rv), ptr(nbt), ptr(st), ptr(ws),
-                                          B, C, Lprev, 0.1, 1e-5, stream()), "stats")
-    # dgrad of the block above: dy (B, Cn, L) with weights (Cn, C, 15)
-    w = gen(Cn, C, 15, seed=3, scale=0.05).to(DEV)
-    wf = torch.empty(15, C // 8, Cn, 8, dtype=BF, device=DEV)
-    wd = torch.empty(15, Cn // 8, C, 8, dtype=BF, device=DEV)
-    check(lib.ecgb200_conv1d_prep_weights_bf16(ptr(w), ptr(wf), ptr(wd), Cn, C, stream()), "prep")
-    dyn = to_blocked(gen(B, Cn, L, seed=8)).to(DEV)
-    dp0 = torch.full((B, C // 8, L, 8), float("nan"), dtype=BF, device=DEV)
-    check(lib.ecgb200_conv1d_fwd_bf16(ptr(dyn), ptr(wd), None, ptr(dp0), B, Cn, C, L, stream()), "dgrad")
-    nparts = lib.ecgb200_conv1d_stat_parts_bf16(B, Cn, C, L)
-    assert nparts > 0
-    part = torch.full((nparts, 2, C), float("nan"), device=DEV)
-    dp1 = torch.full((B, C // 8, L, 8), float("nan"), dtype=BF, device=DEV)
-    check(lib.ecgb200_conv1d_dgrad_bnstats_bf16(ptr(dyn), ptr(wd), ptr(dp1), ptr(yb), ptr(st), ptr(part), B, Cn, C, L,
-                                                Lprev, stream()), "dgrad_bnstats")
-    torch.cuda.synchronize()
-    assert torch.equal(dp0, dp1)
-    assert torch.isfinite(part).all()
-    # reference path: reduce + apply on the same dp
-    nsp = lib.ecgb200_bn_nsplit(B, C)
-    outs = []
-    for fused in (False, True):
-        dyb = torch.full((B, C // 8, Lprev, 8), float("nan"), dtype=BF, device=DEV)
-        dgm, dbt = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
-        dbp = torch.empty(C, nsp, device=DEV)
-        if fused:
-            check(lib.ecgb200_bn_relu_pool_bwd_apply_bf16(ptr(yb), ptr(st), ptr(dp1), ptr(part), nparts, ptr(dyb), ptr(dgm),
-                                                          ptr(dbt), ptr(dbp), B, C, Lprev, 1, stream()), "apply")
-        else:
-            check(lib.ecgb200_bn_relu_pool_bwd_bf16(ptr(yb), ptr(st), ptr(dp0), None, ptr(dyb), ptr(dgm), ptr(dbt),
-                                                    ptr(dbp), ptr(ws), B, C, Lprev, 1, stream()), "bn_bwd")
-        torch.cuda.synchronize()
-        outs.append((dyb.float().cpu(), dgm.cpu(), dbt.cpu(), dbp.sum(dim=1).cpu()))
-    ref_part = ws.view(torch.float32)[:nsp * 2 * C].view(nsp, 2, C).sum(dim=0).cpu()
-    got_part = part.sum(dim=0).cpu()
-    assert rel_inf(got_part[0], ref_part[0]) < 1e-5 and rel_inf(got_part[1], ref_part[1]) < 1e-5
-    (dy0, g0, b0, s0), (dy1, g1, b1, s1) = outs
-    assert torch.isfinite(dy1).all()
-    assert rel_inf(g1, g0) < 1e-5 and rel_inf(b1, b0) < 1e-5
-    assert rel_inf(dy1, dy0) < 8e-3                      # same math, different partial-sum grouping: bf16 ties
-    assert float((dy1 != dy0).float().mean()) < 1e-3
-    assert float((s1 - s0).abs().max()) <= 1e-3 * float(s0.abs().max()) + 1e-2

@@ -61,3 +61,49 @@ def test_device_decode_matches_oracle(B, T):
     frames[0, 5, 2] = -32768
     out2 = decode_batch(torch.from_numpy(frames.astype(np.int16)).cuda(), h.gains, h.baselines).cpu().numpy()
     assert np.isnan(out2[0, 2]).all() and np.isfinite(out2[0, 1]).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T", [(3, 5000), (4, 1000), (1, 38)])
+def test_fused_decode_zscore_pack_matches_oracle_and_feeds_the_engine(B, T):
+    """N1 + N2 fused (ecgb200_wfdb16_zscore_pack_bf16): raw frames -> z-scored bf16 in the first conv's blocked layout ==
+    the numpy oracle rounded to bf16 (<= 1 bf16 ulp on a vanishing fraction: the mean / std sums are fp64 in another
+    order), padding leads exactly zero; and a raw_input TrainStep fed the frames takes the same step as the fp32-input
+    engine fed the decoded windows."""
+    from ptbxl_multimodal_b200._lib import lib, check, ptr, stream
+    from ptbxl_multimodal_b200.wfdb16 import parse_header, decode_batch
+    h = parse_header(HEA)
+    rng = np.random.default_rng(1)
+    frames = (rng.standard_normal((B, T, 12)) * 300 + rng.integers(-200, 200, size=(1, 1, 12))).astype("<i2")
+    ft = torch.from_numpy(frames.astype(np.int16)).cuda()
+    gain = torch.tensor(h.gains, dtype=torch.float32, device="cuda")
+    base = torch.tensor(h.baselines, dtype=torch.int32, device="cuda")
+    xb = torch.full((B, 2, T, 8), float("nan"), dtype=torch.bfloat16, device="cuda")
+    check(lib.ecgb200_wfdb16_zscore_pack_bf16(ptr(ft), ptr(gain), ptr(base), ptr(xb), B, 12, T, stream()), "decode_pack")
+    torch.cuda.synchronize()
+    got = xb.float().permute(0, 1, 3, 2).reshape(B, 16, T).cpu()
+    assert (got[:, 12:] == 0).all()
+    ref = torch.from_numpy(np.stack([W.load_and_normalize(frames[b].tobytes(), h.gains, h.baselines) for b in range(B)]))
+    refb = ref.to(torch.bfloat16).float()
+    diff = (got[:, :12] - refb).abs()
+    assert float(diff.max()) <= 2.0 ** -7 * float(refb.abs().max())              # at most one bf16 ulp
+    assert float((diff > 0).float().mean()) < 1e-3
+    if T < 1000:
+        return
+    import ptbxl_multimodal_b200 as P
+    from ptbxl_multimodal_b200.step import TrainStep
+    y = (torch.rand(B, 5, generator=torch.Generator().manual_seed(2)) < 0.3).float().cuda()
+    res = []
+    for raw in (False, True):
+        torch.manual_seed(42)
+        m = P.ECGCNN(12, 256, 5).cuda().train()
+        eng = TrainStep(m, P.FusedAdamW(m.parameters(), lr=1e-3, weight_decay=1e-4), B, T, precision="bf16", raw_input=raw)
+        if raw:
+            eng.set_calibration(h.gains, h.baselines)
+            eng.load_frames(ft, y)
+            loss = float(eng.run())
+        else:
+            loss = float(eng(decode_batch(ft, h.gains, h.baselines), y))
+        res.append((loss, eng.P.clone()))
+    assert abs(res[0][0] - res[1][0]) < 1e-3 * abs(res[0][0])
+    assert float((res[0][1] - res[1][1]).abs().max()) < 5e-3                     # a handful of 1-ulp input differences
