@@ -195,16 +195,24 @@ def oracle_check(rank, world, dev, kind, sync_bn):
         gmean = {k: sum(o[k] for o in objs) / world for k in keys}
         sd1 = O.clone_sd(sd)
         O.adamw_step(sd1, gmean, O.AdamWState(sd1, lr, wd))
-        wu = 0.0
+        # AdamW's first update is -lr * g / (|g| + eps): sign-like, so elements whose gradient is ~0 are ill-conditioned
+        # (a 1e-9 difference flips the update by 2 * lr).  The update is therefore compared on the well-conditioned half
+        # (|mean oracle gradient| above the tensor's median); the exchanged gradient itself on all elements.
+        wu = wg = 0.0
         for k in keys:
             if k.endswith("net.0.bias"):
                 continue
-            du_e = (model.get_parameter(k).detach().cpu() - p0[k].cpu())
-            du_o = sd1[k] - sd[k]
-            wu = max(wu, 1 - cos(du_e, du_o))
-        ok = ok and wu < 5e-2
+            ge = gl[k].clone()
+            dist.all_reduce(ge)
+            wg = max(wg, 1 - cos(ge / world, gmean[k]))
+            du_e = (model.get_parameter(k).detach().cpu() - p0[k].cpu()).flatten()
+            du_o = (sd1[k] - sd[k]).flatten()
+            big = gmean[k].abs().flatten() >= gmean[k].abs().flatten().median()
+            wu = max(wu, 1 - cos(du_e[big], du_o[big]))
+        ok = ok and wu < 2e-2 and wg < 3e-3
         say(rank, f"3. oracle, local BN ({kind}): logits rel_inf {rel_inf(eng.logits, ref['logits']):.2e}, worst local-gradient 1-cos "
-                  f"{worst:.2e} (<3e-3), worst 1-cos of the applied update vs AdamW(mean of oracle gradients) {wu:.2e} (<5e-2)")
+                  f"{worst:.2e} (<3e-3), mean of rank gradients vs mean of per-shard oracle gradients 1-cos {wg:.2e} (<3e-3), applied "
+                  f"update vs AdamW(mean of oracle gradients) on the well-conditioned half 1-cos {wu:.2e} (<2e-2)")
     else:
         xa = torch.cat([s[0] for s in shards]); ya = torch.cat([s[-1] for s in shards])
         da = torch.cat([s[1] for s in shards]) if kind == "mm" else None
@@ -266,15 +274,21 @@ def ddp_check(rank, world, dev):
     model = P.ECGCNN(12, 256, nl).to(dev).train()
     eng = TrainStep(model, P.FusedAdamW(model.parameters(), lr=lr, weight_decay=wd), B, T, precision="bf16", use_graph=False)
     loss = float(eng(x.to(dev), y.to(dev)))
-    worst = 0.0
+    worst = wu = 0.0
     for k, p in stock.named_parameters():
         if k.endswith("net.0.bias"):
             continue
-        du_e = model.get_parameter(k).detach().cpu() - sd[k]
-        du_d = p.detach().cpu() - sd[k]
-        worst = max(worst, 1 - cos(du_e, du_d))
-    ok = abs(loss - loss_ddp) < 2e-2 * loss_ddp and worst < 8e-2
-    say(rank, f"3b. torch DDP (stock fp32 modules, NCCL): loss {loss:.5f} vs {loss_ddp:.5f}; worst 1-cos of the applied update {worst:.2e} (<8e-2)")
+        ge = model.get_parameter(k).grad.detach().clone()
+        dist.all_reduce(ge)
+        gd = p.grad.detach()                                   # DDP has averaged it over the ranks
+        worst = max(worst, 1 - cos(ge / world, gd))
+        big = (gd.abs().flatten() >= gd.abs().flatten().median()).cpu()
+        du_e = (model.get_parameter(k).detach().cpu() - sd[k]).flatten()
+        du_d = (p.detach().cpu() - sd[k]).flatten()
+        wu = max(wu, 1 - cos(du_e[big], du_d[big]))
+    ok = abs(loss - loss_ddp) < 2e-2 * loss_ddp and worst < 3e-2 and wu < 8e-2
+    say(rank, f"3b. torch DDP (stock fp32 modules, NCCL): loss {loss:.5f} vs {loss_ddp:.5f}; mean of rank gradients vs DDP's averaged "
+              f"gradient worst 1-cos {worst:.2e} (<3e-2, bf16 vs fp32); applied update on the well-conditioned half 1-cos {wu:.2e} (<8e-2)")
     eng.close()
     return all_ok(ok, dev)
 
