@@ -61,8 +61,9 @@ def parse():
     ap.add_argument("--repeats", type=int, default=5, help="timed regions of K steps each; the median is reported")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true")
-    ap.add_argument("--input", default="fp32", choices=["fp32", "int16"],
-                    help="e2e leg: what crosses PCIe per step (fp32 windows, or raw int16 WFDB frames decoded on the device)")
+    ap.add_argument("--input", default="int16", choices=["fp32", "int16"],
+                    help="what a step starts from: raw int16 WFDB format-16 frames (decoded + z-scored + packed on the device; "
+                         "half the H2D bytes of the e2e leg) or fp32 windows as the reference's Dataset returns them")
     return ap.parse_args()
 
 
@@ -456,7 +457,7 @@ def run_train(args, w, world, rank, local, dev, dist):
     # (~1 MB per window, i.e. > 126 MB for every benchmarked batch).
     for s in (0, 1):
         if raw:
-            eng.load_frames(hraw[s].to(dev), dy[s], slot=s)
+            eng.load_frames(hraw[s].to(dev), dy[s], dd[s], slot=s)
         else:
             eng.load_batch(dx[s], dy[s], dd[s], slot=s)
 
@@ -485,7 +486,7 @@ def run_train(args, w, world, rank, local, dev, dist):
         copy_stream.wait_event(freed[s])                  # the graph that read slot s has finished
         with torch.cuda.stream(copy_stream):
             if raw:
-                eng.load_frames(hraw[i % NB], hy[i % NB], slot=s)
+                eng.load_frames(hraw[i % NB], hy[i % NB], hd[i % NB], slot=s)
             else:
                 eng.load_batch(hx[i % NB], hy[i % NB], hd[i % NB], slot=s)
             staged[s].record(copy_stream)

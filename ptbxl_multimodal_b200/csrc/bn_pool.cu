@@ -371,7 +371,8 @@ __host__ __device__ inline int bnb_tile_b(int B, int C, int blocks_per_sm = 4) {
     if (ns < 1) ns = 1;
     return (B + ns - 1) / ns;
 }
-// backward kernels hold ~90 registers: 3 blocks of 256 threads per SM
+// backward kernels hold ~80 registers: 3 blocks of 256 threads per SM (held to 64 registers / 4 blocks they measured
+// SLOWER, alone 18.5 -> 21.3 us per block and in the step 0.422 -> 0.441 ms: spills in the reduce pass, more partials)
 extern "C" int ecgb200_bn_nsplit(int B, int C) { const int tb = bnb_tile_b(B, C, 3); return (B + tb - 1) / tb; }
 
 // Merge `nparts` partial pairs laid out part[i][2][C] for the 8 channels of chunk cc with all 256
@@ -661,7 +662,7 @@ extern "C" int ecgb200_bn_relu_pool_fwd_train_bf16(const void* yb, const float* 
         (C & 7) || L < 2 || nrep < 1)
         return ECGB200_EINVAL;
     const int Lp = L / 2;
-    const int tile_b = bnb_tile_b(B, C, 4), NS = (B + tile_b - 1) / tile_b;
+    const int tile_b = bnb_tile_b(B, C, 3), NS = (B + tile_b - 1) / tile_b;
     cudaStream_t st = (cudaStream_t)stream;
     if (gap != nullptr)
         return ecg_launch_pdl(bn_fwd_train_bf16_kernel<true>, dim3(C / 8, NS), dim3(256), 0, st, (const uint4*)yb,
@@ -700,6 +701,7 @@ bn_bwd_reduce_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__
                           float* __restrict__ part, int B, int C, int L, int Lp, int tile_b) {
     __shared__ float sh[8 * 16];
     ecg_pdl_launch_dependents();            // the apply kernel may be scheduled (and run its prologue) under this one
+    ecg_pdl_wait();                         // dp / dgap come from the kernel launched just before (no-op without PDL)
     const int cc = blockIdx.x, NS = gridDim.y;
     const int b0 = blockIdx.y * tile_b, nb = min(tile_b, B - b0);
     const float inv_lp = 1.0f / (float)Lp;
@@ -858,9 +860,8 @@ extern "C" int ecgb200_bn_relu_pool_bwd_bf16(const void* yb, const float* bn_sta
     const int Lp = L / 2;
     const int tile_b = bnb_tile_b(B, C, 3), NS = (B + tile_b - 1) / tile_b;
     float* part = (float*)ws;
-    bn_bwd_reduce_bf16_kernel<<<dim3(C / 8, NS), 256, 0, st>>>((const uint4*)yb, bn_state, (const uint4*)dpb,
-                                                              dgap, part, B, C, L, Lp, tile_b);
-    int rc = ecg_launch_status();
+    int rc = ecg_launch_pdl(bn_bwd_reduce_bf16_kernel, dim3(C / 8, NS), dim3(256), 0, st, (const uint4*)yb, bn_state,
+                            (const uint4*)dpb, dgap, part, B, C, L, Lp, tile_b);
     if (rc) return rc;
     const float inv_n = 1.0f / ((float)B * (float)L);
     // programmatic dependent launch of the apply pass: its blocks are scheduled while the reduce pass drains and

@@ -45,6 +45,20 @@ int ecg_make_act_tmap(CUtensorMap* m, const void* base, int B, int C, int L, int
     return r == CUDA_SUCCESS ? 0 : ECGB200_EINVAL;
 }
 
+int ecg_make_act_tmap64(CUtensorMap* m, const void* base, int B, int C, int L, int box_rows, int box_chunks) {
+    ecg_tmap_encode_fn enc = ecg_get_tmap_encode();
+    if (enc == nullptr) return ECGB200_EUNSUPPORTED;
+    if (box_rows <= 0 || box_rows > 128) return ECGB200_EINVAL;
+    const cuuint64_t dims[3] = {(cuuint64_t)L * 2, (cuuint64_t)(C / 8), (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)L * 16, (cuuint64_t)(C / 8) * L * 16};         // bytes, dims 1..2
+    const cuuint32_t box[3] = {(cuuint32_t)box_rows * 2, (cuuint32_t)box_chunks, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : ECGB200_EINVAL;
+}
+
 // ---------------------------------------------------------------- layout conversion kernels
 // x fp32 (B, Ci, T)  ->  xb bf16 [B][Cp/8][T][8], channels Ci..Cp-1 zero.   One thread per (b, chunk, t).
 __global__ void pack_input_bf16_kernel(const float* __restrict__ x, uint4* __restrict__ xb,
@@ -165,6 +179,7 @@ struct Conv2Cfg {
     int NST;                         // weight ring depth; 0 = whole weight tensor resident in shared memory
     int total_tiles, tiles_t, ngroups;
     uint32_t tmem_cols, xbytes_al;
+    int wide;                        // input tiles through the 8-byte-element maps (per chunk: 2 KB + 256 B boxes)
 };
 
 // All MMAs of one weight stage: RC tiles x NJ K-steps, fully unrolled so that every descriptor is
@@ -253,7 +268,8 @@ __device__ __forceinline__ void conv_issue_group_stream(uint32_t acc0, uint64_t 
 constexpr int C2_THREADS = 320;
 template <int MODE>
 __global__ void __launch_bounds__(C2_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __nv_bfloat16* __restrict__ wprep,
+conv_tc_kernel(const __grid_constant__ CUtensorMap xmapA, const __grid_constant__ CUtensorMap xmapB,
+               const __nv_bfloat16* __restrict__ wprep,
                const float* __restrict__ bias, const float* __restrict__ shift, __nv_bfloat16* __restrict__ y,
                float* __restrict__ stat_part, const Conv2Cfg P) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -277,7 +293,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __nv_bfloat16* __
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);     // provably warp-uniform
     const int lane = threadIdx.x & 31;
     const int ngl = ((int)blockIdx.x < P.ngroups) ? (P.ngroups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    ecg_pdl_launch_dependents();
     long long* const trace = g_conv_trace;
     if (threadIdx.x == 0) { CTR(0); CTA_SPAN(0); }
 
@@ -289,7 +304,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __nv_bfloat16* __
         }
         tc::fence_barrier_init();
         tc::fence_proxy_async();
-        tc::prefetch_tmap(&xmap);
+        tc::prefetch_tmap(&xmapA);
+        tc::prefetch_tmap(&xmapB);
     }
     if (warp == 2) tc::tmem_alloc(tmem_slot, P.tmem_cols);
     tc::fence_before_sync();
@@ -310,7 +326,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __nv_bfloat16* __
                 for (int r = 0; r < rcount; ++r) {
                     const int tile = tile0 + r;
                     const int b = tile / P.tiles_t, t0 = (tile - b * P.tiles_t) * TC_TILE_M;
-                    tc::tma_load_4d(xs + (size_t)(xb * R + r) * P.xbytes_al, &xmap, xfull + xb, 0, t0 - ECG_PAD, 0, b);
+                    uint8_t* dst = xs + (size_t)(xb * R + r) * P.xbytes_al;
+                    if (P.wide) {
+                        // per 8-channel chunk: rows [t0-7, t0+121) as one 2 KB box, rows [t0+121, t0+137) as a 256 B box
+                        for (int c = 0; c < Ci / 8; ++c, dst += TC_ROWS * 16) {
+                            tc::tma_load_3d(dst, &xmapA, xfull + xb, 2 * (t0 - ECG_PAD), c, b);
+                            tc::tma_load_3d(dst + 128 * 16, &xmapB, xfull + xb, 2 * (t0 - ECG_PAD + 128), c, b);
+                        }
+                    } else {
+                        tc::tma_load_4d(dst, &xmapA, xfull + xb, 0, t0 - ECG_PAD, 0, b);       // one box {8, 144, Ci/8, 1}
+                    }
                 }
                 if (gi < 4) CTR(8 + gi);                         // x load of group gi issued
             };
@@ -398,6 +423,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __nv_bfloat16* __
             tc::mma_commit(accfull + as);              // accumulators of this group are complete
             if (gi < 4) CTR(32 + gi);                  // all MMAs of group gi issued
         }
+        // programmatic dependent launch, triggered LATE: only this CTA's last epilogue is still to run, so the next
+        // kernel's launch latency and prologue hide under the tail without its CTAs squatting on SM slots earlier
+        // (triggering at the top of the kernel measured slower: the early dependents compete with the weight-gradient branch)
+        ecg_pdl_launch_dependents();
         }
         __syncwarp();
     } else {
@@ -655,18 +684,25 @@ template <int MODE>
 static int conv_tc_launch(const void* xb, const void* wprep, const float* bias, const float* shift, void* yb,
                           float* stat_part, int B, int Ci, int Co, int L, void* stream) {
     if (Ci <= 0 || (Ci & 15) || Ci > 256 || (Ci > 64 && (Ci & 63)) || Co <= 0 || (Co & 31) || Co > 256) return ECGB200_EUNSUPPORTED;
-    CUtensorMap xmap;
-    int rc = ecg_make_act_tmap(&xmap, xb, B, Ci, L, TC_ROWS, Ci / 8);
+    // Input tiles: one 4-D box of 16-byte rows per tile for the thin layers; from 128 input channels on, two wide-row
+    // boxes per 8-channel chunk (measured, CTA time at B=256: 128->256 32.5 -> 31.8 us, 256->128 31.7 -> 30.6 us,
+    // 128->64 26.5 -> 25.6 us; for <= 64 input channels the 2 x Ci/8 instructions per tile cost more than they save)
+    const int wide = Ci >= 128;
+    CUtensorMap xmapA, xmapB;
+    int rc = wide ? ecg_make_act_tmap64(&xmapA, xb, B, Ci, L, 128, 1) : ecg_make_act_tmap(&xmapA, xb, B, Ci, L, TC_ROWS, Ci / 8);
+    if (rc) return rc;
+    rc = ecg_make_act_tmap64(&xmapB, xb, B, Ci, L, TC_ROWS - 128, 1);
     if (rc) return rc;
     Conv2Cfg P;
     size_t smem;
     const int grid = conv2_cfg(B, Ci, Co, L, &P, &smem);
     if (grid <= 0) return ECGB200_EUNSUPPORTED;
+    P.wide = wide;
     {   // the attribute is per device: set it on every call (cheap, legal during stream capture)
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
         if (e != cudaSuccess) return (int)e;
     }
-    return ecg_launch_pdl(conv_tc_kernel<MODE>, dim3(grid), dim3(C2_THREADS), smem, (cudaStream_t)stream, xmap,
+    return ecg_launch_pdl(conv_tc_kernel<MODE>, dim3(grid), dim3(C2_THREADS), smem, (cudaStream_t)stream, xmapA, xmapB,
                           (const __nv_bfloat16*)wprep, bias, shift, (__nv_bfloat16*)yb, stat_part, P);
 }
 
@@ -739,7 +775,8 @@ __device__ __forceinline__ void wgrad_issue_item(uint32_t tmem_base, uint64_t al
 }
 
 __global__ void __launch_bounds__(192, 1)
-wgrad_tc_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant__ CUtensorMap xmap,
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant__ CUtensorMap xmapA,
+                const __grid_constant__ CUtensorMap xmapB,
                 float* __restrict__ part, int Co, int Cip, int L, int B, int ncc, int ochunks, int nst) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
@@ -765,7 +802,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant
         tc::fence_barrier_init();
         tc::fence_proxy_async();
         tc::prefetch_tmap(&dymap);
-        tc::prefetch_tmap(&xmap);
+        tc::prefetch_tmap(&xmapA);
+        tc::prefetch_tmap(&xmapB);
     }
     if (warp == 2) tc::tmem_alloc(tmem_slot, 512);
     tc::fence_before_sync();
@@ -783,8 +821,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant
                 tc::mbar_wait(empty + slot, ephase);
                 uint8_t* st = stages + (size_t)slot * stage_bytes;
                 tc::mbar_arrive_expect_tx(full + slot, dybytes + xbytes);
-                tc::tma_load_4d(st, &dymap, full + slot, 0, tt * TC_TILE_M, ob * 16, b);
-                tc::tma_load_4d(st + dybytes, &xmap, full + slot, 0, tt * TC_TILE_M - ECG_PAD, cb * ncc, b);
+                tc::tma_load_3d(st, &dymap, full + slot, 2 * tt * TC_TILE_M, ob * 16, b);
+                for (int c = 0; c < ncc; ++c) {
+                    uint8_t* dst = st + dybytes + (size_t)c * (TC_ROWS * 16);
+                    tc::tma_load_3d(dst, &xmapA, full + slot, 2 * (tt * TC_TILE_M - ECG_PAD), cb * ncc + c, b);
+                    tc::tma_load_3d(dst + 128 * 16, &xmapB, full + slot, 2 * (tt * TC_TILE_M - ECG_PAD + 128), cb * ncc + c, b);
+                }
                 if (n < 8) CTR(8 + n);                           // loads of item n issued
                 if (++slot == nst) { slot = 0; ephase ^= 1; }
                 b += db; tt += dt;
@@ -865,6 +907,138 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant
     }
 }
 
+// ---------------------------------------------------------------- thin layers: "taps as M"
+// Stem layers (Co <= 64): with dY^T as the A operand only Co of the 128 MMA rows are real.  Swap the roles:
+//   D[(k, c8)][o] += X[t + k][c8]^T * dY[t][o]
+// A = one 8-channel chunk of the X tile, MN-major with an M-chunk stride of ONE ROW (16 B): M-chunk m = the chunk shifted
+//     by m rows = tap m, so M = 16 taps x 8 channels = 128 rows, all real (tap 15 is computed and dropped);
+// B = the dY tile [Co/8][128 rows][8], MN-major, N = Co (32 / 64): the 47-cycle instruction instead of the 64-cycle N = 128.
+// Per (sample, 128-step tile) item: Cip/8 chunks x 8 K-steps MMAs, half the tensor time of the taps-as-N form, and the whole
+// dY tile is read once per item (all chunks live in one CTA: Cip/8 * Co <= 256 TMEM columns).  The accumulator of chunk i
+// sits in columns [i * Co, (i + 1) * Co): TMEM lane = (tap, c8), column = o, i.e. for a fixed o the 128 lanes are 512
+// CONTIGUOUS bytes of the partial layout part[z][o][c/8][16][8] -- every store instruction of the epilogue is coalesced as is.
+template <int NCC>
+__device__ __forceinline__ void wgrad_thin_issue_item(uint32_t tmem_base, uint32_t co, uint64_t alo, uint64_t blo,
+                                                      uint32_t idesc, bool accum) {
+#pragma unroll
+    for (int i = 0; i < NCC; ++i) {
+#pragma unroll
+        for (int jb = 0; jb < TC_TILE_M / 16; jb += 4) {
+            uint32_t dd[4];
+            uint64_t al[4], bl[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                dd[e] = tmem_base + (uint32_t)i * co;
+                al[e] = alo + (uint64_t)(i * TC_ROWS + (jb + e) * 16);       // X chunk i, K-step = 16 time rows
+                bl[e] = blo + (uint64_t)((jb + e) * 16);                      // dY tile, same K-step
+            }
+            if (jb > 0 || accum) tc::mma_bf16_x4<0xF>(dd, al, bl, idesc);
+            else tc::mma_bf16_x4<0xE>(dd, al, bl, idesc);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(192, 1)
+wgrad_thin_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_constant__ CUtensorMap xmap,
+                  float* __restrict__ part, int Co, int Cip, int L, int B, int nst, uint32_t tmem_cols) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty = full + WT_MAXST;
+    uint64_t* accfull = empty + WT_MAXST;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfull + 1);
+    uint8_t* stages = smem + TC_HDR;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int z = blockIdx.x, S = gridDim.x, ncc = Cip / 8;
+    if (threadIdx.x == 0) CTA_SPAN(0);
+    const int tiles_t = (L + TC_TILE_M - 1) / TC_TILE_M;
+    const int items = B * tiles_t;
+    const int nloc = (items - z + S - 1) / S;            // items z, z+S, ...   (host guarantees >= 1)
+    const uint32_t dybytes = (uint32_t)Co * 128 * 2;     // [Co/8][128 rows][8] bf16
+    const uint32_t xbytes = (uint32_t)ncc * TC_ROWS * 16;
+    const uint32_t stage_bytes = dybytes + xbytes;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < WT_MAXST; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(empty + i, 1); }
+        tc::mbar_init(accfull, 1);
+        tc::fence_barrier_init();
+        tc::fence_proxy_async();
+        tc::prefetch_tmap(&dymap);
+        tc::prefetch_tmap(&xmap);
+    }
+    if (warp == 2) tc::tmem_alloc(tmem_slot, tmem_cols);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int slot = 0;
+            uint32_t ephase = 1;                                 // fresh barriers: the first pass does not block
+            int b = z / tiles_t, tt = z - b * tiles_t;           // item -> (sample, time tile), advanced by S per step
+            const int db = S / tiles_t, dt = S - db * tiles_t;
+            for (int n = 0; n < nloc; ++n) {
+                tc::mbar_wait(empty + slot, ephase);
+                uint8_t* st = stages + (size_t)slot * stage_bytes;
+                tc::mbar_arrive_expect_tx(full + slot, stage_bytes);
+                tc::tma_load_3d(st, &dymap, full + slot, 2 * tt * TC_TILE_M, 0, b);          // one box: 128 rows x Co/8 chunks
+                tc::tma_load_4d(st + dybytes, &xmap, full + slot, 0, tt * TC_TILE_M - ECG_PAD, 0, b);   // {8, 144, Cip/8, 1}
+                if (++slot == nst) { slot = 0; ephase ^= 1; }
+                b += db; tt += dt;
+                if (tt >= tiles_t) { tt -= tiles_t; ++b; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = tc::make_idesc_bf16(128, Co, 1, 1);
+            // A = X chunk: M chunk m = tap m = the chunk shifted by m rows (SBO = 16 B), K 8-row groups 128 B apart
+            const uint64_t adesc0 = tc::make_desc(0, 128, 16);
+            // B = dY: N (o) chunks 128 rows * 16 B apart, K (t) 8-row groups 128 B apart
+            const uint64_t bdesc0 = tc::make_desc(0, 128, 128 * 16);
+            const uint64_t alo0 = adesc0 + (uint64_t)((tc::smem_u32(stages) + dybytes) >> 4);
+            const uint64_t blo0 = bdesc0 + (uint64_t)(tc::smem_u32(stages) >> 4);
+            int slot = 0;
+            uint32_t fphase = 0, accum = 0;
+            for (int n = 0; n < nloc; ++n) {
+                tc::mbar_wait(full + slot, fphase);
+                tc::fence_after_sync();
+                const uint64_t alo = alo0 + (uint64_t)((uint32_t)slot * (stage_bytes >> 4));
+                const uint64_t blo = blo0 + (uint64_t)((uint32_t)slot * (stage_bytes >> 4));
+                if (ncc == 4) wgrad_thin_issue_item<4>(tmem_base, (uint32_t)Co, alo, blo, idesc, accum != 0);
+                else if (ncc == 2) wgrad_thin_issue_item<2>(tmem_base, (uint32_t)Co, alo, blo, idesc, accum != 0);
+                else wgrad_thin_issue_item<1>(tmem_base, (uint32_t)Co, alo, blo, idesc, accum != 0);
+                accum = 1;
+                tc::mma_commit(empty + slot);
+                if (++slot == nst) { slot = 0; fphase ^= 1; }
+            }
+            tc::mma_commit(accfull);
+        }
+    } else {
+        const int q = warp & 3;
+        tc::mbar_wait(accfull, 0);
+        tc::fence_after_sync();
+        const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16);
+        for (int i = 0; i < ncc; ++i) {
+            for (int c0 = 0; c0 < Co; c0 += 32) {
+                float v[32];
+                tc::tmem_ld32(taddr + (uint32_t)(i * Co + c0), v);
+                tc::tmem_ld_wait();
+                // lane (tap, c8) of output channel o = 512 contiguous bytes over the 128 lanes: coalesced as is
+                float* dst = part + (((size_t)z * Co + c0) * ncc + i) * 128 + 32 * q + lane;
+#pragma unroll
+                for (int e = 0; e < 32; ++e) dst[(size_t)e * ncc * 128] = v[e];
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 2) {
+        tc::tmem_dealloc(tmem_base, tmem_cols);
+        if (lane == 0) CTA_SPAN(1);
+    }
+}
+
 // dW[o][c][k] = sum_z part[z][o][c/8][k][c%8]  (c < Ci, k < 15);  db[o] = sum_j db_part[o][j]
 // Block = RC x 32 float4 columns of the partial layout x ZL z-lanes (ZL * RC = 32): every load is a coalesced
 // 512-byte row; few splits (S <= 24) -> 8 z-lanes x 4 column sets per thread (independent loads in flight, one wave
@@ -927,12 +1101,33 @@ wgrad_tc_reduce_kernel(const float4* __restrict__ part, const float* __restrict_
     }
 }
 
+// thin layers: taps-as-M kernel (all chunks of the input in one CTA: Cip/8 * Co TMEM columns)
+static bool wgrad_is_thin(int Cip, int Co) {
+    return Co <= 64 && (Co & 31) == 0 && Cip <= 32 && Cip / 8 * Co <= 256;
+}
+
+static int wgrad_launch_reduce(const float4* pw, const float* db_part, float* dw, float* db, int S, int Co, int Ci, int Cip,
+                               int ndb, cudaStream_t st) {
+    if (S <= 24) {
+        const int nblk_w = ecg_cdiv(Co * Cip * 4, 128);
+        wgrad_tc_reduce_kernel<8><<<nblk_w + ecg_cdiv(Co, 256), 256, 0, st>>>(pw, db_part, dw, db, S, Co, Ci, Cip, ndb, nblk_w);
+    } else if (S <= 80) {
+        const int nblk_w = ecg_cdiv(Co * Cip * 4, 64);
+        wgrad_tc_reduce_kernel<16><<<nblk_w + ecg_cdiv(Co, 512), 512, 0, st>>>(pw, db_part, dw, db, S, Co, Ci, Cip, ndb, nblk_w);
+    } else {
+        const int nblk_w = ecg_cdiv(Co * Cip * 4, 32);
+        wgrad_tc_reduce_kernel<32><<<nblk_w + ecg_cdiv(Co, 1024), 1024, 0, st>>>(pw, db_part, dw, db, S, Co, Ci, Cip, ndb, nblk_w);
+    }
+    return ecg_launch_status();
+}
+
 static void wgrad_tc_cfg(int B, int Cip, int Co, int L, int* ncc, int* S) {
     *ncc = Cip / 8 < 4 ? Cip / 8 : 4;
-    // thin layers (<= 64 output channels): two chunks per CTA -- half the split-K partial bytes for the same MMA count
-    // (measured at B=256: block 2 26.7 -> 23.4 us); wide layers are bound by re-reading the dY tile per chunk group and
-    // stay at four (two chunks: block 4 41.5 -> 51.1 us, block 3 27.9 -> 30.0 us)
-    if (Co <= 64 && *ncc > 2) *ncc = 2;
+    if (wgrad_is_thin(Cip, Co)) *ncc = Cip / 8;
+    // <= 64 output channels without the thin kernel: two chunks per CTA -- half the split-K partial bytes for the same MMA
+    // count (measured at B=256: block 2 26.7 -> 23.4 us); wide layers are bound by re-reading the dY tile per chunk group
+    // and stay at four (two chunks: block 4 41.5 -> 51.1 us, block 3 27.9 -> 30.0 us)
+    else if (Co <= 64 && *ncc > 2) *ncc = 2;
     const int blocks_oc = (Cip / 8 / *ncc) * ecg_cdiv(Co, 128);
     const int items = B * ecg_cdiv(L, TC_TILE_M);
     int s = 148 / blocks_oc;
@@ -958,11 +1153,32 @@ extern "C" int ecgb200_conv1d_wgrad_bf16(const void* dyb, const void* xb, float*
     if (Co <= 0 || (Co & 7) || Co > 256 || Cip > 256 || (Cip > 16 && (Cip & 31))) return ECGB200_EUNSUPPORTED;
     int ncc, S;
     wgrad_tc_cfg(B, Cip, Co, L, &ncc, &S);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (wgrad_is_thin(Cip, Co)) {
+        // taps as M: one CTA holds all Cip/8 chunks, the batch is split S ways over the SMs
+        CUtensorMap dymap, xmap;
+        int rc = ecg_make_act_tmap64(&dymap, dyb, B, Co, L, TC_TILE_M, Co / 8);
+        if (rc) return rc;
+        rc = ecg_make_act_tmap(&xmap, xb, B, Cip, L, TC_ROWS, Cip / 8);
+        if (rc) return rc;
+        const size_t stage = (size_t)Co * 256 + (size_t)(Cip / 8) * TC_ROWS * 16;
+        int nst = (int)(WT_SMEM_BUDGET / stage);
+        if (nst > WT_MAXST) nst = WT_MAXST;
+        const size_t smem = TC_HDR + (size_t)nst * stage;
+        cudaError_t e = cudaFuncSetAttribute(wgrad_thin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        wgrad_thin_kernel<<<S, 192, smem, st>>>(dymap, xmap, (float*)ws, Co, Cip, L, B, nst, tmem_cols_for(Cip / 8 * Co));
+        rc = ecg_launch_status();
+        if (rc) return rc;
+        return wgrad_launch_reduce((const float4*)ws, db_part, dw, db, S, Co, Ci, Cip, ndb, st);
+    }
     const int ochunks = Co >= 128 ? 16 : Co / 8;
-    CUtensorMap dymap, xmap;
-    int rc = ecg_make_act_tmap(&dymap, dyb, B, Co, L, TC_TILE_M, ochunks);
+    CUtensorMap dymap, xmapA, xmapB;
+    int rc = ecg_make_act_tmap64(&dymap, dyb, B, Co, L, TC_TILE_M, ochunks);
     if (rc) return rc;
-    rc = ecg_make_act_tmap(&xmap, xb, B, Cip, L, TC_ROWS, ncc);
+    rc = ecg_make_act_tmap64(&xmapA, xb, B, Cip, L, 128, 1);
+    if (rc) return rc;
+    rc = ecg_make_act_tmap64(&xmapB, xb, B, Cip, L, TC_ROWS - 128, 1);
     if (rc) return rc;
     const size_t stage = (size_t)ochunks * 128 * 16 + (size_t)ncc * TC_ROWS * 16;
     // the A operand is always described as M = 128 rows = 16 chunks (rows >= Co are computed and discarded), so a
@@ -976,21 +1192,9 @@ extern "C" int ecgb200_conv1d_wgrad_bf16(const void* dyb, const void* xb, float*
         cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
         if (e != cudaSuccess) return (int)e;
     }
-    cudaStream_t st = (cudaStream_t)stream;
     dim3 grid(Cip / 8 / ncc, ecg_cdiv(Co, 128), S);
-    wgrad_tc_kernel<<<grid, 192, smem, st>>>(dymap, xmap, (float*)ws, Co, Cip, L, B, ncc, ochunks, nst);
+    wgrad_tc_kernel<<<grid, 192, smem, st>>>(dymap, xmapA, xmapB, (float*)ws, Co, Cip, L, B, ncc, ochunks, nst);
     rc = ecg_launch_status();
     if (rc) return rc;
-    const float4* pw = (const float4*)ws;
-    if (S <= 24) {
-        const int nblk_w = ecg_cdiv(Co * Cip * 4, 128);
-        wgrad_tc_reduce_kernel<8><<<nblk_w + ecg_cdiv(Co, 256), 256, 0, st>>>(pw, db_part, dw, db, S, Co, Ci, Cip, ndb, nblk_w);
-    } else if (S <= 80) {
-        const int nblk_w = ecg_cdiv(Co * Cip * 4, 64);
-        wgrad_tc_reduce_kernel<16><<<nblk_w + ecg_cdiv(Co, 512), 512, 0, st>>>(pw, db_part, dw, db, S, Co, Ci, Cip, ndb, nblk_w);
-    } else {
-        const int nblk_w = ecg_cdiv(Co * Cip * 4, 32);
-        wgrad_tc_reduce_kernel<32><<<nblk_w + ecg_cdiv(Co, 1024), 1024, 0, st>>>(pw, db_part, dw, db, S, Co, Ci, Cip, ndb, nblk_w);
-    }
-    return ecg_launch_status();
+    return wgrad_launch_reduce((const float4*)ws, db_part, dw, db, S, Co, Ci, Cip, ndb, st);
 }

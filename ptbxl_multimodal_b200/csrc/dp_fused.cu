@@ -54,7 +54,10 @@ __device__ __forceinline__ void dp_wait_flag(const unsigned int* f, unsigned int
     }
 }
 
-__global__ void __launch_bounds__(256)
+// 128 threads per block: the bucket-A exchange runs beside the tensor kernels of blocks 3..1, and 256 threads x 48
+// registers did not fit next to a conv CTA (320 x 168) in the register file -- its blocks then took whole SMs away from
+// the persistent dgrad grid while they spun on the entry barrier (dgrad_3: 29.6 -> 47.9 us in the traced schedule).
+__global__ void __launch_bounds__(128)
 dp_adamw_fused_kernel(const __grid_constant__ DpPeers Q, float* __restrict__ m, float* __restrict__ v, long long off,
                       long long n, int rank, int world, const float* __restrict__ hyper,
                       const int* __restrict__ step_now) {
@@ -138,8 +141,8 @@ extern "C" int ecgb200_dp_flag_words(int world) { return 2 * world + 2; }
 // fixed grid per (bucket size, world): the exit barrier counts epoch * gridDim.x block arrivals, so a flag pad must
 // always be used with the same bucket
 static int dp_grid(long long n, int world) {
-    long long b = (n / 4 / world + 255) / 256;
-    return (int)(b < 8 ? 8 : (b > 96 ? 96 : b));
+    long long b = (n / 4 / world + 255) / 256;             // ~2 float4 per thread
+    return (int)(b < 8 ? 8 : (b > 120 ? 120 : b));
 }
 
 // p / g / flags: HOST arrays of `world` peer-mapped device pointers (this rank's own buffers at index `rank`).
@@ -164,7 +167,7 @@ extern "C" int ecgb200_dp_adamw_fused_range_f32(float* const* p, const float* co
         if (r < world && ((((uintptr_t)Q.p[r] | (uintptr_t)Q.g[r]) & 15) != 0)) return ECGB200_EINVAL;
     }
     if ((((uintptr_t)m | (uintptr_t)v) & 15) != 0) return ECGB200_EINVAL;
-    dp_adamw_fused_kernel<<<dp_grid(n, world), 256, 0, (cudaStream_t)stream>>>(Q, m, v, (long long)off, (long long)n, rank,
+    dp_adamw_fused_kernel<<<dp_grid(n, world), 128, 0, (cudaStream_t)stream>>>(Q, m, v, (long long)off, (long long)n, rank,
                                                                              world, hyper, step_now);
     return ecg_launch_status();
 }
@@ -188,17 +191,30 @@ struct BnPeers {
     unsigned int* flags[DP_MAX_WORLD];       // every rank's flag pad (layout as DpPeers)
 };
 
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(1024)
 dp_bn_sync_kernel(const __grid_constant__ BnPeers Q, const float* __restrict__ local_part, int nparts, int C,
                   float* __restrict__ out, int rank, int world) {
     unsigned int* myflags = Q.flags[rank];
     const unsigned int epoch = myflags[2 * world + 1] + 1u;
     const int i = threadIdx.x;                       // i < 2*C: (which, channel)
-    if (i < 2 * C) {
-        const int which = i / C, c = i - which * C;
+    // local reduce: 1024 threads = up to 512 (which, channel) columns x >= 2 partial groups, independent loads in flight
+    // (one thread per column walking 148 partials serially took 22 us); groups combined in a fixed order
+    __shared__ double acc[1024];
+    {
+        const int ncol = 2 * C, ngrp = 1024 / ncol;               // C <= 256, power-of-two widths: ngrp >= 2
+        const int col = threadIdx.x % ncol, grp = threadIdx.x / ncol;
         double s = 0.0;
-        for (int j = 0; j < nparts; ++j) s += (double)__ldg(local_part + ((size_t)j * 2 + which) * C + c);
-        Q.slot[rank][i] = (float)s;
+        if (grp < ngrp) {
+            const int which = col / C, c = col - which * C;
+            for (int j = grp; j < nparts; j += ngrp) s += (double)__ldg(local_part + ((size_t)j * 2 + which) * C + c);
+        }
+        acc[threadIdx.x] = s;
+        __syncthreads();
+        if (i < ncol) {
+            double t = 0.0;
+            for (int g = 0; g < ngrp; ++g) t += acc[g * ncol + i];
+            Q.slot[rank][i] = (float)t;
+        }
     }
     __threadfence_system();
     __syncthreads();
@@ -222,13 +238,13 @@ dp_bn_sync_kernel(const __grid_constant__ BnPeers Q, const float* __restrict__ l
 extern "C" int ecgb200_dp_bn_sync_f32(const float* local_part, int nparts, int C, float* const* slots,
                                       unsigned int* const* flags, float* out, int rank, int world, void* stream) {
     if (!local_part || nparts <= 0 || C <= 0 || !slots || !flags || !out) return ECGB200_EINVAL;
-    if (C > 256 || world < 1 || world > DP_MAX_WORLD || rank < 0 || rank >= world) return ECGB200_EUNSUPPORTED;
+    if (C > 256 || (C & 7) || world < 1 || world > DP_MAX_WORLD || rank < 0 || rank >= world) return ECGB200_EUNSUPPORTED;
     BnPeers Q;
     for (int r = 0; r < DP_MAX_WORLD; ++r) {
         Q.slot[r] = r < world ? slots[r] : nullptr;
         Q.flags[r] = r < world ? flags[r] : nullptr;
         if (r < world && (!Q.slot[r] || !Q.flags[r])) return ECGB200_EINVAL;
     }
-    dp_bn_sync_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(Q, local_part, nparts, C, out, rank, world);
+    dp_bn_sync_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(Q, local_part, nparts, C, out, rank, world);
     return ecg_launch_status();
 }

@@ -158,6 +158,8 @@ head_fwd_bwd_kernel(const float* __restrict__ gap, const float* __restrict__ wpT
     const int b0 = blockIdx.x * HB, nb = min(HB, B - b0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int o = tid & 255;
+    ecg_pdl_launch_dependents();
+    ecg_pdl_wait();                                  // gap comes from the BatchNorm kernel launched just before
     for (int i = tid; i < HB * Cin; i += HT) {
         const int s = i / Cin, c = i - s * Cin;
         reinterpret_cast<float*>(gs4)[c * HB + s] = s < nb ? __ldg(gap + (size_t)(b0 + s) * Cin + c) : 0.f;
@@ -241,7 +243,7 @@ extern "C" int ecgb200_head_fwd_bwd_f32(const float* gap, const float* wpT, cons
         !loss_part || B <= 0)
         return ECGB200_EINVAL;
     if (Cin <= 0 || Cin > HMAXF || F <= 0 || F > HMAXF || NL <= 0 || NL > HMAXL) return ECGB200_EUNSUPPORTED;
-    head_fwd_bwd_kernel<<<(B + HB - 1) / HB, HT, 0, (cudaStream_t)stream>>>(
+    return ecg_launch_pdl(head_fwd_bwd_kernel, dim3((B + HB - 1) / HB), dim3(HT), 0, (cudaStream_t)stream,
         gap, wpT, wp, bp, wh, bh, target, z, logits, dlogits, dz, dgap, loss_part, B, Cin, F, NL, gscale);
     return ecg_launch_status();
 }

@@ -48,7 +48,7 @@ class _Seg:
 class TrainStep:
     def __init__(self, model, optimizer: FusedAdamW, batch_size: int, seq_len: int,
                  process_group=None, use_graph: bool = True, precision: str = "fp32", dp_mode: str = "auto",
-                 raw_input: bool = False, sync_bn: bool = False):
+                 raw_input: bool = False, sync_bn: bool = False, pdl: bool = False):
         if not isinstance(model, (ECGCNN, ECGMultimodal)):
             raise EcgB200Error("TrainStep drives ecgb200 ECGCNN / ECGMultimodal models")
         if not isinstance(optimizer, FusedAdamW) or len(optimizer.param_groups) != 1:
@@ -82,6 +82,9 @@ class TrainStep:
         self.raw_input = bool(raw_input)
         if self.raw_input and not self.bf16:
             raise EcgB200Error("raw_input=True is implemented for precision='bf16'")
+        # pdl: programmatic dependent launch along the main-stream chain (conv -> BatchNorm -> conv ..., head, BatchNorm
+        # backward -> dgrad): a kernel's launch latency and prologue overlap the tail of the one before
+        self.pdl = bool(pdl) and self.bf16
         self.sync_bn = bool(sync_bn) and self.world > 1
         if self.sync_bn and not self.dp_fused:
             raise EcgB200Error("sync_bn=True needs the peer-memory exchange (precision='bf16', dp_mode 'auto' or 'fused')")
@@ -540,6 +543,13 @@ class TrainStep:
             self.acts[0] = self.x                      # fp32 mode convolves the input buffer directly
 
     def _enqueue(self):
+        old = lib.ecgb200_set_pdl(1 if self.pdl else 0)
+        try:
+            self._enqueue_step()
+        finally:
+            lib.ecgb200_set_pdl(old)
+
+    def _enqueue_step(self):
         main = torch.cuda.current_stream(self.dev)
         st = main.cuda_stream
         B = self.B
