@@ -273,6 +273,22 @@ int ecgb200_dp_flag_words(int world);
 int ecgb200_dp_adamw_fused_range_f32(float* const* p, const float* const* g, unsigned int* const* flags, float* m,
                                      float* v, int64_t off, int64_t n, int rank, int world, const float* hyper,
                                      const int* step_now, void* stream);
+/* One-hop ("LL") form of the bucket exchange: every 4-byte payload travels with its flag in one 8-byte word
+ * {value, epoch}, so there are no barriers and no fences -- every rank pushes its gradients into the shard owners'
+ * inboxes, the owners sum in rank order, apply AdamW and push the new parameters into every rank's inbox, every rank
+ * unpacks its inbox into its replica.  Same arithmetic and summation order, i.e. the same bits, as
+ * ecgb200_dp_adamw_fused_range_f32, at about half its latency (one NVLink hop per phase instead of fence + flag + poll).
+ * p, g, m, v: this rank's flat buffers (need not be peer mapped); inbox: HOST array of `world` peer-mapped pointers to
+ * every rank's inbox of ecgb200_dp_ll_inbox_words(n) zero-initialised 8-byte words, one inbox per bucket; ctr: 2 zeroed
+ * uint32 of this rank per bucket (epoch, blocks finished). */
+int ecgb200_dp_adamw_ll_f32(float* p, const float* g, float* m, float* v, void* const* inbox, unsigned int* ctr,
+                            int64_t off, int64_t n, int rank, int world, const float* hyper, const int* step_now,
+                            void* stream);
+size_t ecgb200_dp_ll_inbox_words(int64_t n);
+/* SyncBN exchange in the same one-hop form: inbox = HOST array of peer-mapped pointers to every rank's
+ * [2][world][512] 8-byte words for THIS (block, direction) slot; ctr: 1 zeroed uint32 of this rank per slot. */
+int ecgb200_dp_bn_sync_ll_f32(const float* local_part, int nparts, int C, void* const* inbox, unsigned int* ctr,
+                              float* out, int rank, int world, void* stream);
 /* SyncBN statistics exchange over NVLink peer memory (one tiny launch per BatchNorm pass): reduces this replica's
  * local_part[nparts][2][C] to one pair, publishes it in slots[rank] (>= 2*C floats of peer-mapped memory), passes a
  * cross-rank barrier and gathers all replicas' pairs in rank order into out[world][2][C] (device memory of this

@@ -67,6 +67,9 @@ _SIGS = {
     "ecgb200_dp_flag_words": (_I, [_I]),
     "ecgb200_dp_adamw_fused_range_f32": (_I, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, _I, _I, _P, _P, _P]),
     "ecgb200_dp_bn_sync_f32": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _P]),
+    "ecgb200_dp_adamw_ll_f32": (_I, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, _I, _I, _P, _P, _P]),
+    "ecgb200_dp_ll_inbox_words": (_Z, [C.c_int64]),
+    "ecgb200_dp_bn_sync_ll_f32": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _P]),
     "ecgb200_set_pdl": (_I, [_I]),
     "ecgb200_debug_set_trace": (_I, [_P]),
     "ecgb200_debug_set_diag": (_I, [_P]),

@@ -45,6 +45,18 @@ static inline int ecg_launch_pdl(void (*kernel)(KP...), dim3 grid, dim3 block, s
     return ecg_launch_pdl_if(g_ecg_pdl != 0, kernel, grid, block, smem, st, args...);
 }
 
+// One AdamW element update (torch.optim.AdamW order of operations, src/training/loop.py:34) with EVERY rounding pinned by
+// intrinsics -- nothing is left to the compiler's FMA contraction, which may differ from kernel to kernel -- so that the
+// multi-tensor, flat, barrier-exchange and one-hop-exchange kernels all produce the same bits from the same inputs.
+struct AdamK { float decay, one_m_b1, b2, one_m_b2, bc2, eps, ss; };
+__device__ __forceinline__ void adamw_update(float& p, float& m, float& v, float g, const AdamK& K) {
+    const float pi = __fmul_rn(p, K.decay);                                          // decoupled weight decay
+    m = __fadd_rn(m, __fmul_rn(K.one_m_b1, __fsub_rn(g, m)));                         // lerp
+    v = __fadd_rn(__fmul_rn(v, K.b2), __fmul_rn(__fmul_rn(K.one_m_b2, g), g));        // mul + addcmul
+    const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), K.bc2), K.eps);
+    p = __fsub_rn(pi, __fmul_rn(K.ss, __fdiv_rn(m, denom)));                          // addcdiv
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -307,12 +307,9 @@ adamw_kernel(const __grid_constant__ AdamTensors T, const float* __restrict__ hy
     float* __restrict__ v = T.v[t];
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (long long)gridDim.x * blockDim.x) {
-        const float gi = g[i] * S.gscale;
-        float pi = p[i] * S.decay;
-        const float mi = m[i] + S.one_m_b1 * (gi - m[i]);              // lerp
-        const float vi = v[i] * S.b2 + S.one_m_b2 * gi * gi;           // mul + addcmul
-        const float denom = sqrtf(vi) / S.bc2_sqrt + S.eps;
-        pi = pi - S.step_size * (mi / denom);                          // addcdiv
+        const AdamK K = {S.decay, S.one_m_b1, S.b2, S.one_m_b2, S.bc2_sqrt, S.eps, S.step_size};
+        float pi = p[i], mi = m[i], vi = v[i];
+        adamw_update(pi, mi, vi, __fmul_rn(g[i], S.gscale), K);
         p[i] = pi; m[i] = mi; v[i] = vi;
     }
 }

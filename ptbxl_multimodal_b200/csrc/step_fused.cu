@@ -360,28 +360,20 @@ adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __r
         const float4 g4 = __ldg(reinterpret_cast<const float4*>(g) + i);
         float4 p4 = reinterpret_cast<float4*>(p)[i], m4 = reinterpret_cast<float4*>(m)[i],
                v4 = reinterpret_cast<float4*>(v)[i];
-        const float gg[4] = {g4.x * gscale, g4.y * gscale, g4.z * gscale, g4.w * gscale};
+        const float gg[4] = {__fmul_rn(g4.x, gscale), __fmul_rn(g4.y, gscale), __fmul_rn(g4.z, gscale), __fmul_rn(g4.w, gscale)};
         float pp[4] = {p4.x, p4.y, p4.z, p4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+        const AdamK K = {decay, one_m_b1, b2, one_m_b2, bc2, eps, ss};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            float pi = pp[e] * decay;
-            mm[e] = mm[e] + one_m_b1 * (gg[e] - mm[e]);
-            vv[e] = vv[e] * b2 + one_m_b2 * gg[e] * gg[e];
-            const float denom = sqrtf(vv[e]) / bc2 + eps;
-            pp[e] = pi - ss * (mm[e] / denom);
-        }
+        for (int e = 0; e < 4; ++e) adamw_update(pp[e], mm[e], vv[e], gg[e], K);
         reinterpret_cast<float4*>(p)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
         reinterpret_cast<float4*>(m)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
         reinterpret_cast<float4*>(v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
     }
     for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const float gi = g[i] * gscale;
-        float pi = p[i] * decay;
-        const float mi = m[i] + one_m_b1 * (gi - m[i]);
-        const float vi = v[i] * b2 + one_m_b2 * gi * gi;
-        const float denom = sqrtf(vi) / bc2 + eps;
-        p[i] = pi - ss * (mi / denom);
-        m[i] = mi; v[i] = vi;
+        const AdamK K = {decay, one_m_b1, b2, one_m_b2, bc2, eps, ss};
+        float pi = p[i], mi = m[i], vi = v[i];
+        adamw_update(pi, mi, vi, __fmul_rn(g[i], gscale), K);
+        p[i] = pi; m[i] = mi; v[i] = vi;
     }
 }
 

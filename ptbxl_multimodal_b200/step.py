@@ -70,11 +70,13 @@ class TrainStep:
         self.dev = next(model.parameters()).device
         if self.dev.type != "cuda":
             raise EcgB200Error("TrainStep needs the model on a CUDA device (no CPU fallback)")
-        if dp_mode not in ("auto", "fused", "nccl"):
-            raise EcgB200Error("dp_mode must be 'auto', 'fused' (peer-memory reduce-scatter + AdamW + all-gather "
-                               "kernel) or 'nccl' (all-reduce, then a replicated AdamW)")
-        # gradient exchange: the fused NVLink kernel needs the flat-buffer optimizer of the bf16 engine
-        self.dp_fused = self.world > 1 and (dp_mode == "fused" or (dp_mode == "auto" and self.bf16))
+        if dp_mode not in ("auto", "fused", "barrier", "nccl"):
+            raise EcgB200Error("dp_mode must be 'auto', 'fused' (peer-memory reduce-scatter + AdamW + all-gather kernel, "
+                               "one-hop {value, epoch} words), 'barrier' (the same with flag barriers) or 'nccl' (all-reduce, "
+                               "then a replicated AdamW)")
+        # gradient exchange: the fused NVLink kernels need the flat-buffer optimizer of the bf16 engine
+        self.dp_fused = self.world > 1 and (dp_mode in ("fused", "barrier") or (dp_mode == "auto" and self.bf16))
+        self.dp_ll = self.dp_fused and dp_mode != "barrier"        # one-hop words instead of barriers
         if self.dp_fused and not self.bf16:
             raise EcgB200Error("dp_mode='fused' is implemented for precision='bf16'")
         # raw_input: the step starts from raw WFDB format-16 frames (B, T, leads) int16 (load_frames) -- decode, per-lead
@@ -167,12 +169,19 @@ class TrainStep:
         # three flag pads (bucket A, bucket B, BatchNorm exchanges) + 8 BatchNorm exchange slots of 2 * 256 floats
         self.flags = symm.empty(3 * self.flag_stride, dtype=torch.int32, device=self.dev)
         self.bnx = symm.empty(8 * 512, dtype=F32, device=self.dev)
-        self.P.zero_(); self.G.zero_(); self.flags.zero_(); self.bnx.zero_()
+        # one-hop exchange: per bucket an inbox of {value, epoch} words (gradients for the owned shard from every rank +
+        # the new parameters of the whole bucket, both double-buffered by epoch parity), per BatchNorm exchange slot
+        # [2][world][512] words; epoch counters are plain local memory
+        self.ll_words = [int(lib.ecgb200_dp_ll_inbox_words(cnt)) for _, cnt, _ in self._buckets()]
+        self.bn_ll_words = 2 * self.world * 512
+        self.inbox = symm.empty(sum(self.ll_words) + 8 * self.bn_ll_words, dtype=torch.int64, device=self.dev)
+        self.ll_ctr = torch.zeros(2 * 2 + 8, dtype=torch.int32, device=self.dev)
+        self.P.zero_(); self.G.zero_(); self.flags.zero_(); self.bnx.zero_(); self.inbox.zero_()
         torch.cuda.synchronize(self.dev)
-        hp, hg, hf, hb = (symm.rendezvous(t, group) for t in (self.P, self.G, self.flags, self.bnx))
-        self._symm_handles = (hp, hg, hf, hb)                # keep the mappings alive
+        hp, hg, hf, hb, hi = (symm.rendezvous(t, group) for t in (self.P, self.G, self.flags, self.bnx, self.inbox))
+        self._symm_handles = (hp, hg, hf, hb, hi)            # keep the mappings alive
         ptrs = lambda h: [int(h.buffer_ptrs[r]) for r in range(self.world)]      # noqa: E731
-        self.peer_p, self.peer_g, self.peer_f, self.peer_bnx = ptrs(hp), ptrs(hg), ptrs(hf), ptrs(hb)
+        self.peer_p, self.peer_g, self.peer_f, self.peer_bnx, self.peer_inbox = ptrs(hp), ptrs(hg), ptrs(hf), ptrs(hb), ptrs(hi)
         if self.peer_p[self.rank] != self.P.data_ptr() or self.peer_g[self.rank] != self.G.data_ptr():
             raise EcgB200Error("symmetric-memory rendezvous returned unexpected local pointers")
         dist.barrier(group)
@@ -420,7 +429,14 @@ class TrainStep:
         """SyncBN: all replicas' partial pairs of block l (direction 0 forward statistics, 1 backward sums) gathered
         into bnsync[l] (world, 2, C) over peer memory."""
         W = C.c_void_p * self.world
-        slot = 512 * 4 * (2 * l + direction)                    # byte offset of this exchange's slot
+        k = 2 * l + direction
+        if self.dp_ll:
+            off = 8 * (sum(self.ll_words) + k * self.bn_ll_words)        # byte offset of this exchange's inbox
+            self._k("bn_sync", lib.ecgb200_dp_bn_sync_ll_f32, _p(part), nparts, self.chan[l + 1],
+                    W(*[p + off for p in self.peer_inbox]), self.ll_ctr.data_ptr() + 4 * (4 + k), _p(self.bnsync[l]),
+                    self.rank, self.world, st)
+            return self.bnsync[l]
+        slot = 512 * 4 * k                                      # byte offset of this exchange's slot
         self._k("bn_sync", lib.ecgb200_dp_bn_sync_f32, _p(part), nparts, self.chan[l + 1],
                 W(*[p + slot for p in self.peer_bnx]), W(*self._flag_pad(2)), _p(self.bnsync[l]), self.rank, self.world, st)
         return self.bnsync[l]
@@ -473,6 +489,23 @@ class TrainStep:
             if l > 0:
                 self._k("dgrad", lib.ecgb200_conv1d_fwd_bf16, _p(dy), _p(self.wd[l]), None, _p(self.dp), B, co, ci, L, st)
                 n += 1
+            if l == 2 and self.world > 1:
+                # Bucket A (block 4 = the tail of the flat buffers; bn_bwd_4 left its BatchNorm gradients there, wgrad_4 the
+                # rest) goes out on the communication stream under the backward of blocks 2..1.  It is released only once
+                # dgrad_3 has COMPLETED: released together with dgrad_3 / wgrad_3 (right after wgrad_4) the extra ready node
+                # flipped the launch order of those two, wgrad_3's CTAs took the SMs first and dgrad_3 -- the critical path --
+                # ran 24 us late (traced schedule, 2 GPUs).
+                ev_d3 = torch.cuda.Event()
+                ev_d3.record(main)
+                self.comm.wait_event(ev_wg4)
+                self.comm.wait_event(ev_d3)
+                with torch.cuda.stream(self.comm):
+                    if self.dp_fused:
+                        self._dp_exchange(0, self.comm.cuda_stream)
+                        self._prof_tag = f"_L{l + 1}"
+                        n += 1
+                    else:
+                        torch.distributed.all_reduce(self.G[self.bucket_a_off:], group=self.pg)
             if self.linear:
                 self.side = main
             else:
@@ -484,16 +517,8 @@ class TrainStep:
                 wg_done[l & 1] = torch.cuda.Event()
                 wg_done[l & 1].record(self.side)
             n += 2
-            if l == 3 and self.world > 1:
-                # bucket A (block 4 = the tail of the flat buffers; bn_bwd_4 already left its BatchNorm gradients there) is
-                # final: exchange it on the communication stream while blocks 3..1 run backward
-                self.comm.wait_event(wg_done[l & 1])
-                with torch.cuda.stream(self.comm):
-                    if self.dp_fused:
-                        self._dp_exchange(0, self.comm.cuda_stream)
-                        n += 1
-                    else:
-                        torch.distributed.all_reduce(self.G[self.bucket_a_off:], group=self.pg)
+            if l == 3:
+                ev_wg4 = wg_done[l & 1]
         return n
 
     def _dp_exchange(self, which, st):
@@ -502,9 +527,15 @@ class TrainStep:
         off, cnt, pad = self._buckets()[which]
         W = C.c_void_p * self.world
         self._prof_tag = "_A" if which == 0 else "_B"
-        self._k("dp_adamw_fused", lib.ecgb200_dp_adamw_fused_range_f32, W(*self.peer_p), W(*self.peer_g),
-                W(*self._flag_pad(pad)), self.M.data_ptr(), self.V.data_ptr(), off, cnt, self.rank, self.world,
-                self.hyper.data_ptr(), self.step_dev.data_ptr(), st)
+        if self.dp_ll:
+            boff = 8 * sum(self.ll_words[:which])
+            self._k("dp_adamw_fused", lib.ecgb200_dp_adamw_ll_f32, self.P.data_ptr(), self.G.data_ptr(), self.M.data_ptr(),
+                    self.V.data_ptr(), W(*[p + boff for p in self.peer_inbox]), self.ll_ctr.data_ptr() + 8 * which, off, cnt,
+                    self.rank, self.world, self.hyper.data_ptr(), self.step_dev.data_ptr(), st)
+        else:
+            self._k("dp_adamw_fused", lib.ecgb200_dp_adamw_fused_range_f32, W(*self.peer_p), W(*self.peer_g),
+                    W(*self._flag_pad(pad)), self.M.data_ptr(), self.V.data_ptr(), off, cnt, self.rank, self.world,
+                    self.hyper.data_ptr(), self.step_dev.data_ptr(), st)
         self._prof_tag = ""
 
     def _bwd_blocks(self, st, pre, Pp, Gp):
@@ -858,7 +889,7 @@ class TrainStep:
         self.graph = None
         self.graphs = None
         torch.cuda.synchronize(self.dev)
-        for name in ("_symm_handles", "peer_p", "peer_g", "peer_f", "peer_bnx"):
+        for name in ("_symm_handles", "peer_p", "peer_g", "peer_f", "peer_bnx", "peer_inbox"):
             if hasattr(self, name):
                 delattr(self, name)
 

@@ -38,10 +38,19 @@ timeit('bn_sync C=256 nparts=148', lambda st: check(lib.ecgb200_dp_bn_sync_f32(p
 timeit('bn_sync C=256 nparts=1', lambda st: check(lib.ecgb200_dp_bn_sync_f32(part.data_ptr(), 1, 256, ptrs(hx), ptrs(hf, 4 * 64 * 2), out.data_ptr(), rank, world, st), 'x'))
 for cnt, pad in ((3360, 0), (3360 * 80, 1), (3360 * 150, 3)):
     timeit(f'dp_adamw_fused_range n={cnt}', lambda st: check(lib.ecgb200_dp_adamw_fused_range_f32(ptrs(hp), ptrs(hg), ptrs(hf, 4 * 64 * pad), M.data_ptr(), V.data_ptr(), 0, cnt, rank, world, hyper.data_ptr(), step.data_ptr(), st), 'x'))
+I_ = symm.empty(4 * 3360 * 150 + 2 * world * 512, dtype=torch.int64, device=dev); I_.zero_(); torch.cuda.synchronize()
+hi = symm.rendezvous(I_, dist.group.WORLD)
+ctr = torch.zeros(8, dtype=torch.int32, device=dev)
+for cnt in (3360, 3360 * 80, 3360 * 150):
+    I_.zero_(); ctr.zero_(); torch.cuda.synchronize(); dist.barrier()
+    timeit(f'dp_adamw_ll n={cnt}', lambda st: check(lib.ecgb200_dp_adamw_ll_f32(P_.data_ptr(), G_.data_ptr(), M.data_ptr(), V.data_ptr(), ptrs(hi), ctr.data_ptr(), 0, cnt, rank, world, hyper.data_ptr(), step.data_ptr(), st), 'x'))
+I_.zero_(); ctr.zero_(); torch.cuda.synchronize(); dist.barrier()
+timeit('bn_sync_ll C=256 nparts=148', lambda st: check(lib.ecgb200_dp_bn_sync_ll_f32(part.data_ptr(), 148, 256, ptrs(hi, 8 * 4 * 3360 * 150), ctr.data_ptr() + 16, out.data_ptr(), rank, world, st), 'x'))
+timeit('bn_sync_ll C=32 nparts=148', lambda st: check(lib.ecgb200_dp_bn_sync_ll_f32(part.data_ptr(), 148, 32, ptrs(hi, 8 * 4 * 3360 * 150), ctr.data_ptr() + 16, out.data_ptr(), rank, world, st), 'x'))
 x = torch.zeros(1024, device=dev)
 timeit('nccl all_reduce 4 KB (for scale)', lambda st: dist.all_reduce(x), iters=20)
 dist.barrier(); torch.cuda.synchronize()
 import threading, time
 threading.Thread(target=lambda: (time.sleep(20), os._exit(0)), daemon=True).start()
-del hp, hg, hf, hx
+del hp, hg, hf, hx, hi
 dist.destroy_process_group()

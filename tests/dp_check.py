@@ -92,7 +92,12 @@ def kernel_level_check(rank, world, dev):
     hyper = torch.tensor([1.5e-3, 0.9, 0.999, 1e-8, 1e-4, 1.0 / world], device=dev)
     st = torch.cuda.current_stream().cuda_stream
     ok = True
-    for variant in ("one bucket", "two buckets"):
+    I_ = symm.empty(int(lib.ecgb200_dp_ll_inbox_words(n_a)) + int(lib.ecgb200_dp_ll_inbox_words(n_b)), dtype=torch.int64, device=dev)
+    I_.zero_()
+    torch.cuda.synchronize(dev)
+    hinb = symm.rendezvous(I_, dist.group.WORLD)
+    ctr = torch.zeros(4, dtype=torch.int32, device=dev)
+    for variant in ("one bucket", "two buckets", "two buckets, one-hop words"):
         P_.copy_(torch.randn(n, generator=torch.Generator().manual_seed(5)))
         M, V = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
         Pr, Mr, Vr = P_.clone(), M.clone(), V.clone()
@@ -107,6 +112,15 @@ def kernel_level_check(rank, world, dev):
                 check(lib.ecgb200_dp_adamw_fused_f32(ptrs(hp), ptrs(hg), ptrs(hf), M.data_ptr(), V.data_ptr(), n, rank, world,
                                                      hyper.data_ptr(), step.data_ptr(), st), "dp_adamw_fused")
                 owned = [(rank * (n // world), (rank + 1) * (n // world))]
+            elif variant == "two buckets, one-hop words":
+                owned = []
+                boff = 0
+                for k, (off, cnt) in enumerate(((n_b, n_a), (0, n_b))):
+                    check(lib.ecgb200_dp_adamw_ll_f32(P_.data_ptr(), G_.data_ptr(), M.data_ptr(), V.data_ptr(), ptrs(hinb, boff),
+                                                      ctr.data_ptr() + 8 * k, off, cnt, rank, world, hyper.data_ptr(),
+                                                      step.data_ptr(), st), "dp_adamw_ll")
+                    boff += 8 * int(lib.ecgb200_dp_ll_inbox_words(cnt))
+                    owned.append((off + rank * (cnt // world), off + (rank + 1) * (cnt // world)))
             else:
                 owned = []
                 for off, cnt, pad in ((n_b, n_a, 1), (0, n_b, 2)):
@@ -129,7 +143,7 @@ def kernel_level_check(rank, world, dev):
             ok = ok and good
         ok = all_ok(ok, dev)
         say(rank, f"1. kernel level ({variant}): fused exchange == rank-ordered sum + AdamW, bit-exact on all {world} ranks: {ok}")
-    del hp, hg, hf
+    del hp, hg, hf, hinb
     return ok
 
 
@@ -138,6 +152,10 @@ def mode_level_check(rank, world, dev):
     for kind, B in (("cnn", 16), ("mm", 8), ("cnn", 128)):
         ef, lf, tf = run("fused", B, 1000, 3, rank, dev, kind)
         pf = ef.P.clone()
+        eb, lb, tb = run("barrier", B, 1000, 3, rank, dev, kind)
+        same_b = bool(torch.equal(eb.P, pf))                  # one-hop words == flag barriers, bit for bit, any world size
+        eb.close()
+        del eb
         en, ln, tn = run("nccl", B, 1000, 3, rank, dev, kind)
         pn = en.P.clone()
         diff = float((pf - pn).abs().max() / pn.abs().max())
@@ -148,13 +166,14 @@ def mode_level_check(rank, world, dev):
         # different order, fp32 rounding differs in the last bit and 53 Adam steps through bf16 activations amplify
         # it, so only the first steps' losses are required to agree there (the kernel-level check above is exact).
         lim = 0.0 if world == 2 else float("inf")
-        good = diff <= lim and same and all(abs(a - b) <= 2e-4 * max(1.0, abs(b)) for a, b in zip(lf, ln))
+        good = diff <= lim and same and same_b and all(abs(a - b) <= 2e-4 * max(1.0, abs(b)) for a, b in zip(lf, ln))
         ef.gather_optimizer_state()
         mdiff = float((ef.M - en.M).abs().max() / en.M.abs().max().clamp_min(1e-30))
         good = good and mdiff <= lim
         ok = ok and good
         say(rank, f"2. {kind} B/rank={B} world={world}: fused vs nccl params rel diff {diff:.2e}, moments {mdiff:.2e}, ranks identical "
-                  f"{same}, losses {['%.5f' % v for v in lf]} | step fused {tf:.1f} us, nccl {tn:.1f} us -> {'OK' if good else 'MISMATCH'}")
+                  f"{same}, one-hop == barrier form {same_b}, losses {['%.5f' % v for v in lf]} | step fused {tf:.1f} us, barrier {tb:.1f} us, "
+                  f"nccl {tn:.1f} us -> {'OK' if good else 'MISMATCH'}")
         ef.close(); en.close()
         del ef, en
     return all_ok(ok, dev)

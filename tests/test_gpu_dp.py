@@ -24,6 +24,6 @@ def test_data_parallel_step_against_oracle_ddp_and_nccl():
     print(res.stderr[-3000:])
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "dp_check passed" in res.stdout
-    for tag in ("1. kernel level (one bucket)", "1. kernel level (two buckets)", "3. oracle, local BN (cnn)",
+    for tag in ("1. kernel level (one bucket)", "1. kernel level (two buckets)", "1. kernel level (two buckets, one-hop words)", "3. oracle, local BN (cnn)",
                 "3. oracle, local BN (mm)", "3b. torch DDP", "4. oracle, SyncBN (cnn)", "4. oracle, SyncBN (mm)"):
         assert tag in res.stdout, tag
