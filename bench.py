@@ -436,7 +436,8 @@ def run_train(args, w, world, rank, local, dev, dist):
     model = (P.ECGCNN(12, 256, w["nl"]) if w["kind"] == "cnn" else P.ECGMultimodal(num_labels=w["nl"])).to(dev).train()
     opt = P.FusedAdamW(model.parameters(), lr=w["lr"], weight_decay=w["wd"])
     raw = args.input == "int16" and precision == "bf16"
-    eng = TrainStep(model, opt, B, T, precision=precision, raw_input=raw)
+    NS = 2 if world == 1 else 4                 # input slots = prefetch depth + 1 (see TrainStep: jitter under data parallel)
+    eng = TrainStep(model, opt, B, T, precision=precision, raw_input=raw, input_slots=NS)
 
     # synthetic data: NB distinct batches, resident on device and in pinned host memory
     NB = 8 if B * T <= 256 * 1000 else 4
@@ -476,13 +477,13 @@ def run_train(args, w, world, rank, local, dev, dist):
     # ---- end-to-end arm: every step its own pinned-host batch in (H2D on a copy stream, straight into the idle
     # input slot while the other slot's graph runs) and the loss out (D2H)
     copy_stream = torch.cuda.Stream(device=dev)
-    staged = [torch.cuda.Event() for _ in range(2)]
-    freed = [torch.cuda.Event() for _ in range(2)]
+    staged = [torch.cuda.Event() for _ in range(NS)]
+    freed = [torch.cuda.Event() for _ in range(NS)]
     host_loss = torch.zeros(64, dtype=torch.float32).pin_memory()
     main_stream = torch.cuda.current_stream(dev)
 
     def prefetch(i):
-        s = i & 1
+        s = i % NS
         copy_stream.wait_event(freed[s])                  # the graph that read slot s has finished
         with torch.cuda.stream(copy_stream):
             if raw:
@@ -492,10 +493,11 @@ def run_train(args, w, world, rank, local, dev, dist):
             staged[s].record(copy_stream)
 
     def step_e2e(i):
-        s = i & 1
+        s = i % NS
         if i == 0:
-            prefetch(0)
-        prefetch(i + 1)                                   # next batch streams in under this step's compute
+            for j in range(NS - 1):
+                prefetch(j)
+        prefetch(i + NS - 1)                              # batches i+1 .. i+NS-1 stream in under this step's compute
         main_stream.wait_event(staged[s])
         loss = eng.run(slot=s)
         freed[s].record(main_stream)
@@ -503,7 +505,7 @@ def run_train(args, w, world, rank, local, dev, dist):
 
     def reset_e2e():
         torch.cuda.synchronize(dev)
-        for s in range(2):
+        for s in range(NS):
             freed[s].record(main_stream)
 
     reset_e2e()
@@ -619,6 +621,7 @@ def run_train(args, w, world, rank, local, dev, dist):
             "l2": "step working set (~1 MB per window) > 126 MB L2; inputs alternate between the engine's two resident input slots",
             "repeats": R, "timing": f"median of {R} timed regions of {K} steps each (CUDA events, max over ranks)",
             "e2e_input": "int16 WFDB frames, decoded + z-scored + packed on the device" if raw else "fp32 windows",
+            "input_slots": NS,
             "grad_exchange": ("fused peer-memory reduce-scatter + AdamW + all-gather kernels (block-4 bucket under backward)" if eng.dp_fused
                               else ("nccl all-reduce" if world > 1 else "none"))}),
         "clocks": clocks,

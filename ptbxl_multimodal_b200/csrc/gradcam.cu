@@ -253,19 +253,25 @@ __device__ __forceinline__ void wf_block_stats(LoadFrame load, int n_leads, int 
                                                long long (*red)[2 * WF_MAXL + 1] /* [8][2*WF_MAXL+1] */) {
     long long s1[WF_MAXL], s2[WF_MAXL];
     int bad = 0;
+    {
+        int a1[WF_MAXL];                                 // |sum| <= 32768 * frames per thread: int32 up to 65535 frames
+        unsigned long long a2[WF_MAXL];
 #pragma unroll
-    for (int l = 0; l < WF_MAXL; ++l) { s1[l] = 0; s2[l] = 0; }
-    for (int t = threadIdx.x; t < T; t += blockDim.x) {
-        short v[WF_MAXL];
-        load(t, v);
+        for (int l = 0; l < WF_MAXL; ++l) { a1[l] = 0; a2[l] = 0ull; }
+        for (int t = threadIdx.x; t < T; t += blockDim.x) {
+            short v[WF_MAXL];
+            load(t, v);
 #pragma unroll
-        for (int l = 0; l < WF_MAXL; ++l)
-            if (l < n_leads) {
-                const int d = (int)v[l];
-                bad |= (d == -32768) ? (1 << l) : 0;
-                s1[l] += d;
-                s2[l] += (long long)(d * d);
-            }
+            for (int l = 0; l < WF_MAXL; ++l)
+                if (l < n_leads) {
+                    const int d = (int)v[l];
+                    bad |= (d == -32768) ? (1 << l) : 0;
+                    a1[l] += d;
+                    a2[l] += (unsigned)(d * d);
+                }
+        }
+#pragma unroll
+        for (int l = 0; l < WF_MAXL; ++l) { s1[l] = a1[l]; s2[l] = (long long)a2[l]; }
     }
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
@@ -350,43 +356,71 @@ extern "C" int ecgb200_wfdb16_zscore_f32(const void* dat, const float* gain, con
 // are staged in shared memory once (coalesced 4-byte loads), every thread keeps the running sums of ALL leads of its
 // frames (two passes in double: mean, then centred M2, as the oracle's numpy), one block reduction per pass.
 #include <cuda_bf16.h>
+// NL = compile-time lead count (12 for PTB-XL: the per-frame loops then carry no predicates), 0 = run-time n_leads.
+template <int NL>
 __global__ void __launch_bounds__(256)
 wfdb16_zscore_pack_kernel(const short* __restrict__ dat, const float* __restrict__ gain, const int* __restrict__ baseline,
-                          uint4* __restrict__ xb, int n_leads, int Cp, int T) {
+                          uint4* __restrict__ xb, int n_leads_rt, int Cp, int T) {
     extern __shared__ __align__(16) unsigned char wf_smem[];
     short* fr = reinterpret_cast<short*>(wf_smem);                       // [T][n_leads]
     __shared__ long long red[8][2 * WF_MAXL + 1];
     __shared__ WfStats S;
+    const int n_leads = NL > 0 ? NL : n_leads_rt;
     const short* rec = dat + (size_t)blockIdx.x * T * n_leads;
-    const int nwords = (T * n_leads) >> 1;                               // host guarantees T * n_leads even
-    for (int i = threadIdx.x; i < nwords; i += blockDim.x)
-        reinterpret_cast<int*>(fr)[i] = __ldg(reinterpret_cast<const int*>(rec) + i);
+    const int nbytes = T * n_leads * 2;
+    if ((nbytes & 15) == 0 && ((reinterpret_cast<uintptr_t>(rec) & 15) == 0)) {
+        for (int i = threadIdx.x; i < (nbytes >> 4); i += blockDim.x)
+            reinterpret_cast<uint4*>(fr)[i] = __ldg(reinterpret_cast<const uint4*>(rec) + i);
+    } else {
+        for (int i = threadIdx.x; i < (nbytes >> 2); i += blockDim.x)        // host guarantees T * n_leads even
+            reinterpret_cast<int*>(fr)[i] = __ldg(reinterpret_cast<const int*>(rec) + i);
+    }
     __syncthreads();
     wf_block_stats([&](int t, short* v) {
+        if (NL == 12) {                                                      // one frame = 24 bytes = three 8-byte words
+            const uint2* f2 = reinterpret_cast<const uint2*>(fr + t * 12);
+            const uint2 a = f2[0], b = f2[1], c = f2[2];
+            const unsigned w[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
 #pragma unroll
-        for (int l = 0; l < WF_MAXL; ++l) v[l] = l < n_leads ? fr[t * n_leads + l] : (short)0;
+            for (int l = 0; l < 6; ++l) { v[2 * l] = (short)(w[l] & 0xffffu); v[2 * l + 1] = (short)(w[l] >> 16); }
+#pragma unroll
+            for (int l = 12; l < WF_MAXL; ++l) v[l] = 0;
+        } else {
+#pragma unroll
+            for (int l = 0; l < WF_MAXL; ++l) v[l] = l < n_leads ? fr[t * n_leads + l] : (short)0;
+        }
     }, n_leads, T, gain, baseline, &S, red);
     // z = ((d - baseline) / gain - mean) / (std + 1e-6) = (d - mean_d) / (gain * (std + 1e-6)); d - mean_d is formed
     // exactly (integer part) + a small fraction, so fp32 keeps its full precision for large DC offsets
     const int nchunk = Cp / 8;
     uint4* out = xb + (size_t)blockIdx.x * nchunk * T;
-    for (int i = threadIdx.x; i < nchunk * T; i += blockDim.x) {
-        const int cc = i / T, t = i - cc * T;
-        float v[8];
+    int mi[WF_MAXL];
+    float mf[WF_MAXL], sc[WF_MAXL];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int l = cc * 8 + j;
+    for (int l = 0; l < WF_MAXL; ++l) {
+        const bool on = l < n_leads;
+        mi[l] = on ? S.mi[l] : 0; mf[l] = on ? S.mf[l] : 0.f; sc[l] = on ? S.sc[l] : 0.f;
+    }
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        float v[WF_MAXL];
+#pragma unroll
+        for (int l = 0; l < WF_MAXL; ++l) {
             if (l < n_leads) {
                 const int d = (int)fr[t * n_leads + l];
-                v[j] = d == -32768 ? __int_as_float(0x7fc00000) : ((float)(d - S.mi[l]) - S.mf[l]) * S.sc[l];
+                v[l] = d == -32768 ? __int_as_float(0x7fc00000) : ((float)(d - mi[l]) - mf[l]) * sc[l];
             } else {
-                v[j] = 0.f;
+                v[l] = 0.f;
             }
         }
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]),
-                       h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
-        out[i] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
-                            *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+#pragma unroll
+        for (int cc = 0; cc < WF_MAXL / 8; ++cc) {
+            if (cc < nchunk) {
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * cc], v[8 * cc + 1]), h1 = __floats2bfloat162_rn(v[8 * cc + 2], v[8 * cc + 3]),
+                               h2 = __floats2bfloat162_rn(v[8 * cc + 4], v[8 * cc + 5]), h3 = __floats2bfloat162_rn(v[8 * cc + 6], v[8 * cc + 7]);
+                out[(size_t)cc * T + t] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                                     *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+            }
+        }
     }
 }
 
@@ -397,13 +431,22 @@ extern "C" int ecgb200_wfdb16_zscore_pack_bf16(const void* dat, const float* gai
     if (n_leads <= 0 || n_leads > WF_MAXL || ((T * n_leads) & 1) || (((uintptr_t)dat) & 3)) return ECGB200_EUNSUPPORTED;
     const size_t smem = (size_t)T * n_leads * sizeof(short);
     if (smem > 200 * 1024) return ECGB200_EUNSUPPORTED;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(wfdb16_zscore_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-    }
     const int Cp = (n_leads + 15) / 16 * 16;
-    wfdb16_zscore_pack_kernel<<<B, 256, smem, (cudaStream_t)stream>>>((const short*)dat, gain, baseline, (uint4*)xb,
-                                                                     n_leads, Cp, T);
+    if (n_leads == 12) {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(wfdb16_zscore_pack_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+        }
+        wfdb16_zscore_pack_kernel<12><<<B, 256, smem, (cudaStream_t)stream>>>((const short*)dat, gain, baseline, (uint4*)xb,
+                                                                             n_leads, Cp, T);
+    } else {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(wfdb16_zscore_pack_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+        }
+        wfdb16_zscore_pack_kernel<0><<<B, 256, smem, (cudaStream_t)stream>>>((const short*)dat, gain, baseline, (uint4*)xb,
+                                                                            n_leads, Cp, T);
+    }
     return ecg_launch_status();
 }
 

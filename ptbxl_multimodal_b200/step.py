@@ -48,7 +48,7 @@ class _Seg:
 class TrainStep:
     def __init__(self, model, optimizer: FusedAdamW, batch_size: int, seq_len: int,
                  process_group=None, use_graph: bool = True, precision: str = "fp32", dp_mode: str = "auto",
-                 raw_input: bool = False, sync_bn: bool = False, pdl: bool = False):
+                 raw_input: bool = False, sync_bn: bool = False, pdl: bool = False, input_slots: int = 2):
         if not isinstance(model, (ECGCNN, ECGMultimodal)):
             raise EcgB200Error("TrainStep drives ecgb200 ECGCNN / ECGMultimodal models")
         if not isinstance(optimizer, FusedAdamW) or len(optimizer.param_groups) != 1:
@@ -90,6 +90,12 @@ class TrainStep:
         self.sync_bn = bool(sync_bn) and self.world > 1
         if self.sync_bn and not self.dp_fused:
             raise EcgB200Error("sync_bn=True needs the peer-memory exchange (precision='bf16', dp_mode 'auto' or 'fused')")
+        # input slots: batch i+1 .. i+slots-1 can be copied in (H2D) while the graph of slot i runs; one captured graph per
+        # slot.  Two are enough on one GPU; under data parallel every step ends in a cross-rank exchange, so one late
+        # host copy on ANY rank stalls all of them -- a deeper prefetch queue absorbs that jitter.
+        self.nslots = int(input_slots)
+        if self.nslots < 2 or self.nslots > 8:
+            raise EcgB200Error("input_slots must be in 2..8")
         self.use_graph = use_graph
         self.graph = None
         self.launches_per_step = 0
@@ -240,9 +246,9 @@ class TrainStep:
         self.nl = self.model.head.out_features
         self.feat = self.bb.proj.out_features
         # two input slots: the next batch can be copied in (H2D) while the graph of the other slot runs
-        self.xs = [e(B, self.chan[0], T), e(B, self.chan[0], T)]
-        self.ys = [e(B, self.nl), e(B, self.nl)]
-        self.demos = [None, None]
+        self.xs = [e(B, self.chan[0], T) for _ in range(self.nslots)]
+        self.ys = [e(B, self.nl) for _ in range(self.nslots)]
+        self.demos = [None] * self.nslots
         self.cur = 0
         self.x, self.y, self.demo = self.xs[0], self.ys[0], None
         self.acts = [self.x]                                       # input of conv l
@@ -282,7 +288,7 @@ class TrainStep:
             if self.raw_input:
                 # raw WFDB format-16 frames per input slot + per-lead calibration (.hea gain / baseline)
                 nlead = self.chan[0]
-                self.frames = [torch.zeros(B, T, nlead, dtype=torch.int16, device=dev) for _ in range(2)]
+                self.frames = [torch.zeros(B, T, nlead, dtype=torch.int16, device=dev) for _ in range(self.nslots)]
                 self.gain = torch.full((nlead,), 200.0, dtype=F32, device=dev)
                 self.baseline = torch.zeros(nlead, dtype=torch.int32, device=dev)
             if self.sync_bn:
@@ -298,7 +304,7 @@ class TrainStep:
         self.loss = torch.zeros((), dtype=F32, device=dev)
         if self.mm:
             dm = self.model.demo_encoder.mlp
-            self.demos = [e(B, dm[0].in_features), e(B, dm[0].in_features)]
+            self.demos = [e(B, dm[0].in_features) for _ in range(self.nslots)]
             self.demo = self.demos[0]
             self.h1, self.dh1 = e(B, dm[0].out_features), e(B, dm[0].out_features)
             self.h2, self.dh2 = e(B, dm[2].out_features), e(B, dm[2].out_features)
@@ -745,7 +751,7 @@ class TrainStep:
         keep = self.cur
         graphs = []
         try:
-            for slot in (0, 1):                      # one graph per input slot (same kernels, other input pointers)
+            for slot in range(self.nslots):          # one graph per input slot (same kernels, other input pointers)
                 self._select(slot)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=self.capture_stream):
@@ -847,12 +853,12 @@ class TrainStep:
 
     def load_batch(self, x, y, demo=None, slot=None):
         """Copy a batch (pinned host or device tensors) into an input slot (async on the current stream).
-        slot=None: the idle slot, which then becomes the one run() uses; an explicit slot (0/1) is only filled
-        (pipelined use: fill slot s on a copy stream while the graph of slot 1-s runs, then run(slot=s))."""
+        slot=None: the next slot, which then becomes the one run() uses; an explicit slot (0 .. input_slots-1) is only
+        filled (pipelined use: fill slot s on a copy stream while the graphs of the other slots run, then run(slot=s))."""
         if tuple(x.shape) != tuple(self.x.shape) or tuple(y.shape) != tuple(self.y.shape):
             raise EcgB200Error(f"TrainStep was built for x{tuple(self.x.shape)} y{tuple(self.y.shape)}, "
                                f"got x{tuple(x.shape)} y{tuple(y.shape)}")
-        s = (self.cur ^ 1) if slot is None else int(slot)
+        s = ((self.cur + 1) % self.nslots) if slot is None else int(slot)
         self.xs[s].copy_(x, non_blocking=True)
         self.ys[s].copy_(y, non_blocking=True)
         if self.mm:
@@ -867,7 +873,7 @@ class TrainStep:
         input slot; the graph decodes, z-scores and packs them on the device (set_calibration for gain / baseline)."""
         if not self.raw_input:
             raise EcgB200Error("load_frames() needs TrainStep(..., raw_input=True)")
-        s = (self.cur ^ 1) if slot is None else int(slot)
+        s = ((self.cur + 1) % self.nslots) if slot is None else int(slot)
         if tuple(frames.shape) != tuple(self.frames[s].shape) or frames.dtype != torch.int16:
             raise EcgB200Error(f"expected int16 frames {tuple(self.frames[s].shape)}, got {frames.dtype} {tuple(frames.shape)}")
         self.frames[s].copy_(frames, non_blocking=True)
