@@ -385,30 +385,47 @@ class TrainStep:
         PV, I4 = C.c_void_p * 4, C.c_int * 4
         wkeys = [f"{pre}backbone.{l}.net.0.weight" for l in range(4)]
         main = torch.cuda.current_stream(self.dev)
-        # critical path: pack the input + block-1 weights (+ step counter); blocks 2-4 and the proj transpose
-        # are re-laid beside the first conv on the side stream
         if self.raw_input:
+            # raw frames: the decode + z-score + pack kernel is the critical path; ALL weight re-layouts (+ proj transpose +
+            # step counter) are one launch beside it on the side stream, joined before conv 1
+            ev0 = torch.cuda.Event()
+            ev0.record(main)
+            if self.linear:
+                self.side = main
+            else:
+                self.side.wait_event(ev0)
+            with torch.cuda.stream(self.side):
+                self._k("prep_w", lib.ecgb200_step_prep_bf16, None, None, 0, 0, 0, 4,
+                        PV(*[Pp(k) for k in wkeys]), PV(*[_p(w) for w in self.wt]),
+                        PV(*[_p(w) for w in self.wd]), I4(*self.chan[1:5]), I4(*self.chan[0:4]),
+                        Pp(pre + "proj.weight"), _p(self.wpT),
+                        self.feat, self.chan[4], self.step_dev.data_ptr(), self.side.cuda_stream)
+                prep_done = torch.cuda.Event()
+                prep_done.record(self.side)
             self._k("decode", lib.ecgb200_wfdb16_zscore_pack_bf16, _p(self.frames[self.cur]), _p(self.gain),
                     _p(self.baseline), _p(self.acts[0]), B, self.chan[0], self.T, st)
-            n += 1
-        self._k("prep", lib.ecgb200_step_prep_bf16, None if self.raw_input else _p(self.x), _p(self.acts[0]), B, self.chan[0],
-                self.T, 1, PV(Pp(wkeys[0]), None, None, None), PV(_p(self.wt[0]), None, None, None), PV(None, None, None, None),
-                I4(self.chan[1], 0, 0, 0), I4(self.chan[0], 0, 0, 0), None, None, 0, 0, self.step_dev.data_ptr(), st)
-        ev_prep = torch.cuda.Event()
-        ev_prep.record(main)
-        # released by `prep`; its node is created before conv 1's (created after it measured slower: conv 2 then waits)
-        if self.linear:
-            self.side = main
+            main.wait_event(prep_done)
         else:
-            self.side.wait_event(ev_prep)
-        with torch.cuda.stream(self.side):
-            self._k("prep_w", lib.ecgb200_step_prep_bf16, None, None, 0, 0, 0, 3,
-                    PV(*[Pp(k) for k in wkeys[1:]], None), PV(*[_p(w) for w in self.wt[1:]], None),
-                    PV(*[_p(w) for w in self.wd[1:]], None), I4(*self.chan[2:5], 0), I4(*self.chan[1:4], 0),
-                    Pp(pre + "proj.weight"), _p(self.wpT),
-                    self.feat, self.chan[4], None, self.side.cuda_stream)
-            prep_done = torch.cuda.Event()
-            prep_done.record(self.side)
+            # critical path: pack the input + block-1 weights (+ step counter); blocks 2-4 and the proj transpose
+            # are re-laid beside the first conv on the side stream
+            self._k("prep", lib.ecgb200_step_prep_bf16, _p(self.x), _p(self.acts[0]), B, self.chan[0],
+                    self.T, 1, PV(Pp(wkeys[0]), None, None, None), PV(_p(self.wt[0]), None, None, None), PV(None, None, None, None),
+                    I4(self.chan[1], 0, 0, 0), I4(self.chan[0], 0, 0, 0), None, None, 0, 0, self.step_dev.data_ptr(), st)
+            ev_prep = torch.cuda.Event()
+            ev_prep.record(main)
+            # released by `prep`; its node is created before conv 1's (created after it measured slower: conv 2 then waits)
+            if self.linear:
+                self.side = main
+            else:
+                self.side.wait_event(ev_prep)
+            with torch.cuda.stream(self.side):
+                self._k("prep_w", lib.ecgb200_step_prep_bf16, None, None, 0, 0, 0, 3,
+                        PV(*[Pp(k) for k in wkeys[1:]], None), PV(*[_p(w) for w in self.wt[1:]], None),
+                        PV(*[_p(w) for w in self.wd[1:]], None), I4(*self.chan[2:5], 0), I4(*self.chan[1:4], 0),
+                        Pp(pre + "proj.weight"), _p(self.wpT),
+                        self.feat, self.chan[4], None, self.side.cuda_stream)
+                prep_done = torch.cuda.Event()
+                prep_done.record(self.side)
         n += 2
         for l in range(4):
             cip, co, L = self.cip[l], self.chan[l + 1], self.L[l]
