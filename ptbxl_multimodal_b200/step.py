@@ -390,6 +390,11 @@ class TrainStep:
             # step counter) are one launch beside it on the side stream, joined before conv 1
             ev0 = torch.cuda.Event()
             ev0.record(main)
+            # the critical path's node is created FIRST: ready graph nodes are launched in creation order, and with the side
+            # branch's root created first the whole weight-gradient branch won every later race for the SMs (multimodal
+            # B=1024: head_wgrad starved behind dgrad_4, step 1.20 -> 1.27 ms)
+            self._k("decode", lib.ecgb200_wfdb16_zscore_pack_bf16, _p(self.frames[self.cur]), _p(self.gain),
+                    _p(self.baseline), _p(self.acts[0]), B, self.chan[0], self.T, st)
             if self.linear:
                 self.side = main
             else:
@@ -402,8 +407,6 @@ class TrainStep:
                         self.feat, self.chan[4], self.step_dev.data_ptr(), self.side.cuda_stream)
                 prep_done = torch.cuda.Event()
                 prep_done.record(self.side)
-            self._k("decode", lib.ecgb200_wfdb16_zscore_pack_bf16, _p(self.frames[self.cur]), _p(self.gain),
-                    _p(self.baseline), _p(self.acts[0]), B, self.chan[0], self.T, st)
             main.wait_event(prep_done)
         else:
             # critical path: pack the input + block-1 weights (+ step counter); blocks 2-4 and the proj transpose
