@@ -175,3 +175,59 @@ def test_numpy_train_step_matches_the_live_reference(golden):
         # the first Adam step moves every weight by ~lr * g / (|g| + eps): entries whose gradient sits at the fp32 noise
         # floor move by a different fraction of lr in float64 -- bound the difference by a tenth of one step
         assert np.abs(v - ref).max() <= 0.1 * float(lr), k
+
+
+@pytest.mark.parametrize("kind", ["cnn", "mm"])
+def test_stock_module_restatement_equals_the_functional_oracle(kind):
+    """oracle/torch_stock.py (plain torch.nn module trees + torch.optim.AdamW: what bench.py times as the library path on
+    the GPU and tests/dp_check.py wraps in DDP) takes the SAME step as ecg_oracle.train_step, bit for bit: loss, every
+    parameter, every BatchNorm buffer."""
+    import torch
+    from oracle import ecg_oracle as O, torch_stock as S
+    sd = O.init_state_dict(kind, 5, seed=42)
+    sd2 = O.clone_sd(sd)
+    batch = O.synth_batch(6, 256, 5, seed=3, with_demo=(kind == "mm"))
+    x, y = batch[0], batch[-1]
+    demo = batch[1] if kind == "mm" else None
+    st = O.AdamWState(sd, 1e-3, 1e-4)
+    model = S.build(kind, sd2, 5).train()
+    assert list(model.state_dict().keys()) == list(sd.keys())
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    step = S.make_step(model, opt)
+    for _ in range(2):
+        ref = O.train_step(sd, x, y, st, demo=demo)
+        loss = step(x, y, demo) if demo is not None else step(x, y)
+        assert float(loss) == float(ref["loss"])
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+
+
+def test_bf16_definition_with_forced_activations_is_self_consistent():
+    """bf16_train_step(forced_conv=, forced_pool=) fed the definition's OWN stored activations reproduces the plain
+    definition exactly (the replacement is value-identical and gradient-transparent) -- the GPU test feeds it the
+    engine's stored activations instead, to separate rounding from routing."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import ecg_oracle as O
+    sd = O.init_state_dict("cnn", 5, seed=42)
+    x, y = O.synth_batch(4, 256, 5, seed=1)
+    ref = O.bf16_train_step(sd, x, y)
+    h = x.to(torch.bfloat16).float()
+    fc, fp = [], []
+    for i in range(4):
+        p = f"backbone.{i}."
+        a = F.conv1d(h, sd[p + "net.0.weight"].to(torch.bfloat16).float(), sd[p + "net.0.bias"], padding=7).to(torch.bfloat16).float()
+        fc.append(a)
+        bn = F.batch_norm(a, None, None, sd[p + "net.1.weight"], sd[p + "net.1.bias"], training=True, eps=1e-5)
+        pooled = F.max_pool1d(F.relu(bn), 2)
+        if i < 3:
+            h = pooled.to(torch.bfloat16).float()
+            fp.append(h)
+    got = O.bf16_train_step(sd, x, y, forced_conv=fc, forced_pool=fp)
+    assert float(got["loss"]) == float(ref["loss"])
+    for k in ref["grads"]:
+        assert torch.equal(got["grads"][k], ref["grads"][k]), k
+    # a perturbed stored activation changes the result (the forced values are really used)
+    fc[3] = fc[3].clone()
+    fc[3][:, :, ::2] *= 2.0
+    assert float(O.bf16_train_step(sd, x, y, forced_conv=fc, forced_pool=fp)["loss"]) != float(ref["loss"])
