@@ -501,7 +501,11 @@ def run_train(args, w, world, rank, local, dev, dist):
         main_stream.wait_event(staged[s])
         loss = eng.run(slot=s)
         freed[s].record(main_stream)
-        host_loss[i % 64].copy_(loss, non_blocking=True)  # D2H read of the step's result
+        # D2H read of the step's result, on the copy stream (the slot's loss scalar stays valid until the slot is run again), so
+        # that the compute stream holds nothing but graph launches
+        copy_stream.wait_event(freed[s])
+        with torch.cuda.stream(copy_stream):
+            host_loss[i % 64].copy_(loss, non_blocking=True)
 
     def reset_e2e():
         torch.cuda.synchronize(dev)

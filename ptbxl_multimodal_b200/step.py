@@ -301,7 +301,10 @@ class TrainStep:
         self.dz = e(B, self.feat)
         self.logits = e(B, self.nl)
         self.dlogits = e(B, self.nl)
-        self.loss = torch.zeros((), dtype=F32, device=dev)
+        # one loss scalar per input slot: the step of slot s leaves its loss in losses[s], where it stays valid until slot s
+        # is run again -- a caller can read it back on ANOTHER stream while the next steps run (bench.py's e2e leg does)
+        self.losses = [torch.zeros((), dtype=F32, device=dev) for _ in range(self.nslots)]
+        self.loss = self.losses[0]
         if self.mm:
             dm = self.model.demo_encoder.mlp
             self.demos = [e(B, dm[0].in_features) for _ in range(self.nslots)]
@@ -596,6 +599,7 @@ class TrainStep:
         """Make input slot `slot` the one the next _enqueue() / run() reads."""
         self.cur = slot
         self.x, self.y, self.demo = self.xs[slot], self.ys[slot], self.demos[slot]
+        self.loss = self.losses[slot]
         if not self.bf16:
             self.acts[0] = self.x                      # fp32 mode convolves the input buffer directly
 
@@ -920,8 +924,8 @@ class TrainStep:
                 delattr(self, name)
 
     def run(self, slot=None):
-        """One optimizer step on whatever input slot `slot` (default: the current one) holds.  Returns the loss
-        buffer (device scalar, overwritten by the next step)."""
+        """One optimizer step on whatever input slot `slot` (default: the current one) holds.  Returns that slot's loss
+        buffer (device scalar, overwritten the next time the same slot is run)."""
         if slot is not None and int(slot) != self.cur:
             self._select(int(slot))
         group = self.opt.param_groups[0]
