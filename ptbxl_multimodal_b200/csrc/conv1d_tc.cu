@@ -950,7 +950,8 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_consta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int z = blockIdx.x, S = gridDim.x, ncc = Cip / 8;
-    if (threadIdx.x == 0) CTA_SPAN(0);
+    long long* const trace = blockIdx.x == 0 ? g_conv_trace : nullptr;
+    if (threadIdx.x == 0) { CTR(0); CTA_SPAN(0); }
     const int tiles_t = (L + TC_TILE_M - 1) / TC_TILE_M;
     const int items = B * tiles_t;
     const int nloc = (items - z + S - 1) / S;            // items z, z+S, ...   (host guarantees >= 1)
@@ -984,6 +985,7 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_consta
                 tc::mbar_arrive_expect_tx(full + slot, stage_bytes);
                 tc::tma_load_3d(st, &dymap, full + slot, 2 * tt * TC_TILE_M, 0, b);          // one box: 128 rows x Co/8 chunks
                 tc::tma_load_4d(st + dybytes, &xmap, full + slot, 0, tt * TC_TILE_M - ECG_PAD, 0, b);   // {8, 144, Cip/8, 1}
+                if (n < 8) CTR(8 + n);
                 if (++slot == nst) { slot = 0; ephase ^= 1; }
                 b += db; tt += dt;
                 if (tt >= tiles_t) { tt -= tiles_t; ++b; }
@@ -1002,6 +1004,7 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_consta
             uint32_t fphase = 0, accum = 0;
             for (int n = 0; n < nloc; ++n) {
                 tc::mbar_wait(full + slot, fphase);
+                if (n < 8) CTR(16 + n);
                 tc::fence_after_sync();
                 const uint64_t alo = alo0 + (uint64_t)((uint32_t)slot * (stage_bytes >> 4));
                 const uint64_t blo = blo0 + (uint64_t)((uint32_t)slot * (stage_bytes >> 4));
@@ -1010,13 +1013,16 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_consta
                 else wgrad_thin_issue_item<1>(tmem_base, (uint32_t)Co, alo, blo, idesc, accum != 0);
                 accum = 1;
                 tc::mma_commit(empty + slot);
+                if (n < 8) CTR(24 + n);
                 if (++slot == nst) { slot = 0; fphase ^= 1; }
             }
             tc::mma_commit(accfull);
+            CTR(32);
         }
     } else {
         const int q = warp & 3;
         tc::mbar_wait(accfull, 0);
+        if (threadIdx.x == 64) CTR(33);
         tc::fence_after_sync();
         const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16);
         for (int i = 0; i < ncc; ++i) {
@@ -1030,6 +1036,7 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap dymap, const __grid_consta
                 for (int e = 0; e < 32; ++e) dst[(size_t)e * ncc * 128] = v[e];
             }
         }
+        if (threadIdx.x == 64) CTR(34);
     }
     tc::fence_before_sync();
     __syncthreads();
