@@ -140,24 +140,38 @@ def test_committed_bench_lines_follow_the_driver_contract():
     import json
     import os
     from conftest import ROOT
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_bench_v8_final.json")) +
-                   glob.glob(os.path.join(ROOT, "profiles", "r01_bench_n*_v2.json")))
-    assert files
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r02_bench_n[128].json")) +
+                   glob.glob(os.path.join(ROOT, "profiles", "r02_bench_c[234]_n[128].json")))
+    assert len(files) >= 6
+    configs = set()
     for f in files:
         with open(f) as fh:
             d = json.loads(fh.read().strip().splitlines()[-1])
         for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
-                  "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"):
+                  "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "step_roofline"):
             assert k in d, (f, k)
-        assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
+        assert d["higher_is_better"] is True and d["scaling"] in ("weak", "strong") and d["vs_baseline"] is None
         assert "workload" in d["config"] and d["dtype"] == "bf16" and d["data"] == "synthetic"
+        assert {"batch_per_gpu", "global_batch", "seq_len", "parallelism", "precision"} <= set(d["config"])
         assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
         assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["gpu_launches"] > 0
         assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
         assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        configs.add(d["config"]["workload"].split(":")[0])
         if d["n_gpus"] == 1:
             assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
             assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9
-    with open(os.path.join(ROOT, "profiles", "r01_bench_reference_arm.json")) as fh:
+            assert d["gpu_reference"]["best"] > 0 and d["speedup_vs_gpu_reference"]["device_timed"] > 1
+            if "layers" in d:                       # every C-ABI call of the step, with its roofline fraction
+                calls = {r["call"] for r in d["layers"]}
+                assert {"conv_fwd_L1", "conv_fwd_L4", "bn_relu_pool_L1", "bn_bwd_L4", "dgrad_L2", "wgrad_L1", "wgrad_L4"} <= calls
+                assert all({"call", "us", "model_us", "frac", "bound"} <= set(r) for r in d["layers"])
+                assert len(d["layers_worst3"]) == 3
+    assert configs == {"configs[1]", "configs[2]", "configs[3]", "configs[4]"}
+    with open(os.path.join(ROOT, "profiles", "r02_bench_n1.json")) as fh:
+        head = json.loads(fh.read().strip().splitlines()[-1])
+    assert head["roofline"]["traffic"] is not None and head["roofline"]["traffic_source"].startswith("profiles/")
+    with open(os.path.join(ROOT, "profiles", "r02_bench_reference_arm.json")) as fh:
         r = json.loads(fh.read().strip().splitlines()[-1])
     assert r["impl"] == "reference" and r["e2e"]["h2d_bytes_per_step"] == 0 and r["cpu_baseline"]["kind"] == "port"
+    assert set(r["config"]) <= set(head["config"])          # the two arms name the workload with the same keys
