@@ -374,6 +374,19 @@ int ecgb200_bn_fold_f32(const float* gamma, const float* beta, const float* runn
 int ecgb200_conv1d_bn_relu_pool_infer_bf16(const void* xb, const void* wprep, const float* scale,
                                            const float* shift, void* pb, float* gap_part, int B, int Ci,
                                            int Co, int L, void* stream);
+/* Split-precision ("fp32 on the tensor cores") forms of the same block: every fp32 value x travels as two bf16 planes
+ * hi = bf16(x), lo = bf16(x - hi); the products hi*hi + lo*hi + hi*lo are computed as THREE TIMES THE INPUT CHANNELS of the
+ * same tcgen05 implicit GEMM (activations [x_hi | x_lo | x_hi] against weights [w_hi | w_hi | w_lo], fp32 accumulation in
+ * TMEM), and the epilogue splits the pooled fp32 result again for the next block.  Only lo*lo (<= 2^-18 relative) is
+ * dropped: logits agree with the fp32 reference path to ~1e-5 (tests/test_gpu_infer.py) at ~1/3 of the bf16 engine's rate.
+ * ecgb200_split_channels(C) = channel count of a split tensor (3 planes of C rounded up to 16, zero-padded to 64 / a
+ * multiple of 64).  Replaces Conv1d + BatchNorm1d(eval) + ReLU + MaxPool1d (ecg_cnn.py:13-16) for fp32-exact callers. */
+int ecgb200_split_channels(int Ci);
+int ecgb200_pack_input_split_bf16(const float* x, void* xb, int B, int Ci, int T, void* stream);
+int ecgb200_conv1d_prep_weights_split_bf16(const float* w, void* wf, int Co, int Ci, void* stream);
+int ecgb200_conv1d_bn_relu_pool_infer_split_bf16(const void* xb, const void* wprep, const float* scale,
+                                                 const float* shift, void* pb, float* gap_part, int B, int Ci,
+                                                 int Co, int L, void* stream);
 /* Fused inference head: gap = inv_lp * sum of a window's `nparts` partials; z = proj(gap) (wpT = proj.weight
  * transposed, (C4, F)); with demo != NULL the DemoEncoder -> film_gen -> FiLM chain of
  * src/models/ecg_multimodal.py:44-59,88-99 (w1 (H,D0); w2 and wf TRANSPOSED: (H_in,H_out) and (H,2F)); logits = head(.) (ecg_cnn.py:63-64);

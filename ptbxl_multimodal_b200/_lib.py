@@ -80,6 +80,10 @@ _SIGS = {
     "ecgb200_bn_relu_pool_bwd_apply_bf16": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "ecgb200_bn_fold_f32": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _F, _P]),
     "ecgb200_conv1d_bn_relu_pool_infer_bf16": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "ecgb200_split_channels": (_I, [_I]),
+    "ecgb200_pack_input_split_bf16": (_I, [_P, _P, _I, _I, _I, _P]),
+    "ecgb200_conv1d_prep_weights_split_bf16": (_I, [_P, _P, _I, _I, _P]),
+    "ecgb200_conv1d_bn_relu_pool_infer_split_bf16": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "ecgb200_infer_head_f32": (_I, [_P, _I, _F] + [_P] * 14 + [_I] * 6 + [_P]),
     "ecgb200_transpose_f32": (_I, [_P, _P, _I, _I, _P]),
 }

@@ -180,6 +180,7 @@ struct Conv2Cfg {
     int total_tiles, tiles_t, ngroups;
     uint32_t tmem_cols, xbytes_al;
     int wide;                        // input tiles through the 8-byte-element maps (per chunk: 2 KB + 256 B boxes)
+    int Cn;                          // MODE 5: channels of the OUTPUT tensor (3 split planes of Co channels, padded)
 };
 
 // All MMAs of one weight stage: RC tiles x NJ K-steps, fully unrolled so that every descriptor is
@@ -263,6 +264,11 @@ __device__ __forceinline__ void conv_issue_group_stream(uint32_t acc0, uint64_t 
 //        MaxPool1d(2) in the epilogue -- the two time steps of a pool pair are adjacent TMEM lanes = adjacent
 //        threads, which swap half of their 32 channels with one shuffle each -- and only the POOLED bf16 rows go
 //        to HBM (`y` = pooled output [B][Co/8][L/2][8]): the conv output itself never leaves the SM.
+// MODE 5 (split-precision inference): as MODE 1, but the pooled fp32 value p is stored as THREE bf16 planes
+//        [hi | lo | hi] with hi = bf16(p), lo = bf16(p - hi) (`y` = [B][Cn/8][L/2][8], plane p at channel p * Co):
+//        the next conv, whose weights are laid out as [w_hi | w_hi | w_lo], then computes
+//        x_hi*w_hi + x_lo*w_hi + x_hi*w_lo with fp32 accumulation -- fp32-accurate to ~1e-5 (only lo*lo is dropped) at
+//        three times the bf16 MMA count, on the same tcgen05 kernel.
 // MODE 2 (inference, last block): as MODE 1 but nothing is stored: the pooled rows are summed over time per
 //        (tile, lane quarter) for AdaptiveAvgPool1d(1) (`stat_part` = gap_part[tile][4][Co], fixed order).
 constexpr int C2_THREADS = 320;
@@ -353,7 +359,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmapA, const __grid_constant_
                 uint32_t ephase = 1;                             // first pass over the ring: slots start free
                 for (int gi = 0; gi < ngl; ++gi) {
                     // the next group's input tiles are requested once this group's MMAs are under way
-                    const int xat = nstage - 1 < P.NST ? nstage - 1 : P.NST;
+                    // (single input buffer: only after ALL of this group's weight stages are on their way -- the buffer is
+                    // released by the group's last MMA, which needs those stages; asking earlier would deadlock the ring)
+                    const int xat = P.NXB == 1 ? nstage - 1 : (nstage - 1 < P.NST ? nstage - 1 : P.NST);
                     for (int s = 0; s < nstage; ++s) {
                         if (!(gi == 0 && s < P.NST)) tc::mbar_wait(wempty + slot, ephase);
                         tc::mbar_arrive_expect_tx(wfull + slot, stage_bytes);
@@ -481,8 +489,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmapA, const __grid_constant_
                     float bv[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) bv[i] = bias != nullptr ? __ldg(bias + c0 + i) : 0.f;
-                    float sh[(MODE == 1 || MODE == 2) ? 32 : 1];
-                    if constexpr (MODE == 1 || MODE == 2) {
+                    float sh[(MODE == 1 || MODE == 2 || MODE == 5) ? 32 : 1];
+                    if constexpr (MODE == 1 || MODE == 2 || MODE == 5) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) sh[i] = __ldg(shift + c0 + i);
                     }
@@ -496,7 +504,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmapA, const __grid_constant_
                         float v[32];
                         tc::tmem_ld32(taddr, v);
                         tc::tmem_ld_wait();
-                        if constexpr (MODE == 1 || MODE == 2) {
+                        if constexpr (MODE == 1 || MODE == 2 || MODE == 5) {
                             // relu(scale * conv + shift), then max over the pool pair (lanes 2p, 2p+1): the even lane
                             // keeps channels 0-15 of the block, the odd lane 16-31
                             const bool even = (lane & 1) == 0;
@@ -510,7 +518,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmapA, const __grid_constant_
                                 const float send = even ? c : a, keep = even ? a : c;
                                 m[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
                             }
-                            if constexpr (MODE == 1) {
+                            if constexpr (MODE == 5) {
+                                if (plive) {
+                                    uint32_t hi[8], lo[8];
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) {
+                                        hi[j] = tc::pack_bf16(m[2 * j], m[2 * j + 1]);
+                                        const float2 h = tc::unpack_bf16(hi[j]);
+                                        lo[j] = tc::pack_bf16(m[2 * j] - h.x, m[2 * j + 1] - h.y);
+                                    }
+                                    const size_t cs = (size_t)Lp * 8;                    // elements between chunks
+                                    __nv_bfloat16* prow = y + ((size_t)b * (P.Cn / 8) * Lp + tp) * 8 +
+                                                          (size_t)(c0 / 8 + (even ? 0 : 2)) * cs;
+                                    const uint4 h0 = make_uint4(hi[0], hi[1], hi[2], hi[3]), h1 = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                                    const size_t plane = (size_t)(Co / 8) * cs;
+                                    *reinterpret_cast<uint4*>(prow) = h0;
+                                    *reinterpret_cast<uint4*>(prow + cs) = h1;
+                                    *reinterpret_cast<uint4*>(prow + plane) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                                    *reinterpret_cast<uint4*>(prow + plane + cs) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                                    *reinterpret_cast<uint4*>(prow + 2 * plane) = h0;
+                                    *reinterpret_cast<uint4*>(prow + 2 * plane + cs) = h1;
+                                }
+                            } else if constexpr (MODE == 1) {
                                 if (plive) {
                                     __nv_bfloat16* prow = y + ((size_t)b * (Co / 8) * Lp + tp) * 8 +
                                                           (size_t)(c0 / 8 + (even ? 0 : 2)) * ((size_t)Lp * 8);
@@ -632,14 +661,21 @@ static int conv2_cfg(int B, int Ci, int Co, int L, Conv2Cfg* P, size_t* smem_out
     const bool resident = wbytes <= 64 * 1024;
     const size_t budget = 225 * 1024 - TC_HDR - C2_STATB;
     int bestR = 1, bestSpan = 1 << 30;
+    bool found = false, single = false;
     const int rmax = Co >= 256 ? 2 : (512 / (2 * Co) < 4 ? 512 / (2 * Co) : 4);
+    // second pass (single = true) only when no R fits with double-buffered input tiles: the 3x-wide inputs of the
+    // split-precision (fp32-accurate) inference layers keep ONE input buffer (the next group's tiles load after this
+    // group's MMAs have consumed it)
+    for (int pass = 0; pass < 2 && !found; ++pass)
     for (int R = rmax; R >= 1; R >>= 1) {
         const int ng = ecg_cdiv(P->total_tiles, R);
         const int grid = ng < nsm ? ng : nsm;
         const int span = ecg_cdiv(ng, grid) * R;                     // tiles on the busiest CTA
-        const int nxb = ecg_cdiv(ng, grid) > 1 ? 2 : 1;
+        const int nxb = (ecg_cdiv(ng, grid) > 1 && pass == 0) ? 2 : 1;
         const size_t need = (size_t)nxb * R * P->xbytes_al + (resident ? wbytes : 3 * stage);
         if (need > budget) continue;
+        found = true;
+        single = pass == 1;
         // streamed weights: fewer, larger groups halve the L2->SM weight traffic, so prefer the larger R
         if (span < bestSpan || (!resident && span == bestSpan && R > bestR)) { bestSpan = span; bestR = R; }
         // streamed weights: keep the largest R unless a smaller one shortens the busiest CTA (small batches: with
@@ -652,7 +688,8 @@ static int conv2_cfg(int B, int Ci, int Co, int L, Conv2Cfg* P, size_t* smem_out
     P->AS = 2 * bestR * Co <= 512 ? 2 : 1;
     P->ngroups = ecg_cdiv(P->total_tiles, bestR);
     const int grid = P->ngroups < nsm ? P->ngroups : nsm;
-    P->NXB = ecg_cdiv(P->ngroups, grid) > 1 ? 2 : 1;
+    if (!found) return -1;
+    P->NXB = (ecg_cdiv(P->ngroups, grid) > 1 && !single) ? 2 : 1;
     const size_t xall = (size_t)P->NXB * bestR * P->xbytes_al;
     if (resident) {
         P->NST = 0;
@@ -671,7 +708,7 @@ static int conv2_cfg(int B, int Ci, int Co, int L, Conv2Cfg* P, size_t* smem_out
 extern "C" int ecgb200_conv1d_stat_parts_bf16(int B, int Ci, int Co, int L) {
     Conv2Cfg P;
     size_t smem;
-    if (B <= 0 || L <= 0 || Ci <= 0 || (Ci & 15) || Ci > 256 || (Ci > 64 && (Ci & 63)) || Co <= 0 || (Co & 31) || Co > 256) return 0;
+    if (B <= 0 || L <= 0 || Ci <= 0 || (Ci & 15) || Ci > 384 || (Ci > 64 && (Ci & 63)) || Co <= 0 || (Co & 31) || Co > 256) return 0;
     const int g = conv2_cfg(B, Ci, Co, L, &P, &smem);
     return g > 0 ? g : 0;
 }
@@ -682,8 +719,8 @@ extern "C" int ecgb200_conv1d_stat_parts_bf16(int B, int Ci, int Co, int L) {
 // {sum, sum of squares} of the bf16-rounded outputs.
 template <int MODE>
 static int conv_tc_launch(const void* xb, const void* wprep, const float* bias, const float* shift, void* yb,
-                          float* stat_part, int B, int Ci, int Co, int L, void* stream) {
-    if (Ci <= 0 || (Ci & 15) || Ci > 256 || (Ci > 64 && (Ci & 63)) || Co <= 0 || (Co & 31) || Co > 256) return ECGB200_EUNSUPPORTED;
+                          float* stat_part, int B, int Ci, int Co, int L, void* stream, int Cn = 0) {
+    if (Ci <= 0 || (Ci & 15) || Ci > 384 || (Ci > 64 && (Ci & 63)) || Co <= 0 || (Co & 31) || Co > 256) return ECGB200_EUNSUPPORTED;
     // Input tiles: one 4-D box of 16-byte rows per tile for the thin layers; from 128 input channels on, two wide-row
     // boxes per 8-channel chunk (measured, CTA time at B=256: 128->256 32.5 -> 31.8 us, 256->128 31.7 -> 30.6 us,
     // 128->64 26.5 -> 25.6 us; for <= 64 input channels the 2 x Ci/8 instructions per tile cost more than they save)
@@ -698,6 +735,7 @@ static int conv_tc_launch(const void* xb, const void* wprep, const float* bias, 
     const int grid = conv2_cfg(B, Ci, Co, L, &P, &smem);
     if (grid <= 0) return ECGB200_EUNSUPPORTED;
     P.wide = wide;
+    P.Cn = Cn > 0 ? Cn : Co;
     {   // the attribute is per device: set it on every call (cheap, legal during stream capture)
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
         if (e != cudaSuccess) return (int)e;
@@ -725,6 +763,90 @@ extern "C" int ecgb200_conv1d_bn_relu_pool_infer_bf16(const void* xb, const void
     if (!xb || !wprep || !scale || !shift || (!pb && !gap_part) || B <= 0 || L < 2) return ECGB200_EINVAL;
     if (gap_part != nullptr) return conv_tc_launch<2>(xb, wprep, scale, shift, nullptr, gap_part, B, Ci, Co, L, stream);
     return conv_tc_launch<1>(xb, wprep, scale, shift, pb, nullptr, B, Ci, Co, L, stream);
+}
+
+// ---------------------------------------------------------------- split-precision (fp32-accurate) inference
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi); the three products hi*hi + lo*hi + hi*lo are THREE TIMES THE INPUT
+// CHANNELS of the same implicit GEMM: activations [x_hi | x_lo | x_hi], weights [w_hi | w_hi | w_lo], fp32 accumulation in
+// TMEM.  Plane width = Ci rounded up to 16; the three planes are padded with zeros to a multiple of 64 (16 when <= 64).
+extern "C" int ecgb200_split_channels(int Ci) {
+    const int cpl = (Ci + 15) / 16 * 16, c3 = 3 * cpl;
+    return c3 <= 64 ? 64 : (c3 + 63) / 64 * 64;
+}
+
+// x fp32 (B, Ci, T) -> xb bf16 [B][Ct/8][T][8], Ct = ecgb200_split_channels(Ci): planes [hi | lo | hi | 0]
+__global__ void pack_input_split_bf16_kernel(const float* __restrict__ x, uint4* __restrict__ xb, int B, int Ci, int Cpl,
+                                             int Ct, int T) {
+    const long long n = (long long)B * (Ct / 8) * T;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i % T);
+        const int cc = (int)((i / T) % (Ct / 8));
+        const int b = (int)(i / ((long long)T * (Ct / 8)));
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int ch = cc * 8 + j, plane = ch / Cpl, c = ch - plane * Cpl;
+            float val = 0.f;
+            if (plane < 3 && c < Ci) {
+                const float xv = __ldg(x + ((size_t)b * Ci + c) * T + t);
+                const float hi = __bfloat162float(__float2bfloat16(xv));
+                val = plane == 1 ? xv - hi : xv;          // rounded to bf16 below: hi for planes 0 / 2, lo for plane 1
+            }
+            v[j] = val;
+        }
+        xb[i] = make_uint4(tc::pack_bf16(v[0], v[1]), tc::pack_bf16(v[2], v[3]), tc::pack_bf16(v[4], v[5]),
+                           tc::pack_bf16(v[6], v[7]));
+    }
+}
+
+// w fp32 (Co, Ci, 15) -> wf bf16 [15][Ct/8][Co][8]: planes [w_hi | w_hi | w_lo | 0] against the activations' [hi | lo | hi]
+__global__ void prep_weights_split_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf, int Co, int Ci,
+                                               int Cpl, int Ct) {
+    const int n = ECG_KS * Ct * Co;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int j = i & 7;
+        const int o = (i >> 3) % Co;
+        const int cc = (i / (8 * Co)) % (Ct / 8);
+        const int k = i / (8 * Co * (Ct / 8));
+        const int ch = cc * 8 + j, plane = ch / Cpl, c = ch - plane * Cpl;
+        float val = 0.f;
+        if (plane < 3 && c < Ci) {
+            const float wv = w[((size_t)o * Ci + c) * ECG_KS + k];
+            const float hi = __bfloat162float(__float2bfloat16(wv));
+            val = plane == 2 ? wv - hi : wv;
+        }
+        wf[i] = __float2bfloat16(val);
+    }
+}
+
+extern "C" int ecgb200_pack_input_split_bf16(const float* x, void* xb, int B, int Ci, int T, void* stream) {
+    if (!x || !xb || B <= 0 || Ci <= 0 || T <= 0) return ECGB200_EINVAL;
+    const int Cpl = (Ci + 15) / 16 * 16, Ct = ecgb200_split_channels(Ci);
+    const long long n = (long long)B * (Ct / 8) * T;
+    const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+    pack_input_split_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (uint4*)xb, B, Ci, Cpl, Ct, T);
+    return ecg_launch_status();
+}
+
+extern "C" int ecgb200_conv1d_prep_weights_split_bf16(const float* w, void* wf, int Co, int Ci, void* stream) {
+    if (!w || !wf || Co <= 0 || Ci <= 0 || (Co & 7)) return ECGB200_EINVAL;
+    const int Cpl = (Ci + 15) / 16 * 16, Ct = ecgb200_split_channels(Ci);
+    const int n = ECG_KS * Ct * Co;
+    prep_weights_split_bf16_kernel<<<ecg_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)wf, Co, Ci, Cpl, Ct);
+    return ecg_launch_status();
+}
+
+// One ConvBlock in eval mode at fp32 accuracy: xb [B][Ct/8][L][8] split planes of the Ci input channels
+// (Ct = ecgb200_split_channels(Ci)), wprep from ecgb200_conv1d_prep_weights_split_bf16.  pb != NULL: the pooled output as
+// split planes [B][Cn/8][L/2][8], Cn = ecgb200_split_channels(Co) (zero the buffer once: the padding plane is never written);
+// gap_part != NULL (last block): per-tile time sums as ecgb200_conv1d_bn_relu_pool_infer_bf16.
+extern "C" int ecgb200_conv1d_bn_relu_pool_infer_split_bf16(const void* xb, const void* wprep, const float* scale,
+                                                            const float* shift, void* pb, float* gap_part, int B,
+                                                            int Ci, int Co, int L, void* stream) {
+    if (!xb || !wprep || !scale || !shift || (!pb && !gap_part) || B <= 0 || L < 2 || Ci <= 0) return ECGB200_EINVAL;
+    const int Ct = ecgb200_split_channels(Ci);
+    if (gap_part != nullptr) return conv_tc_launch<2>(xb, wprep, scale, shift, nullptr, gap_part, B, Ct, Co, L, stream);
+    return conv_tc_launch<5>(xb, wprep, scale, shift, pb, nullptr, B, Ct, Co, L, stream, ecgb200_split_channels(Co));
 }
 
 extern "C" int ecgb200_conv1d_fwd_bf16(const void* xb, const void* wprep, const float* bias, void* yb,

@@ -13,7 +13,10 @@ reduces over time for AdaptiveAvgPool1d instead of storing anything, and one fus
 stay on the device until the caller reads them.
 
 Numerics: bf16 operands, fp32 accumulation / BN / head (stated tolerance in tests/test_gpu_infer.py).
-The fp32-exact path is the nn.Module forward (``model(x)``); this engine is the throughput path."""
+``precision="fp32x3"`` keeps the same kernels and graph but carries every activation and weight as two bf16 planes
+(hi = bf16(x), lo = bf16(x - hi)) and computes hi*hi + lo*hi + hi*lo as three times the input channels of each
+implicit GEMM (fp32 accumulation in TMEM): logits within ~1e-5 of the fp32 reference path -- the north_star's
+1e-4 bar -- at about a third of the bf16 engine's rate and several times the CUDA-core fp32 module forward."""
 from __future__ import annotations
 
 from typing import Optional
@@ -33,7 +36,7 @@ def _p(t: Optional[torch.Tensor]):
 
 
 class InferStep:
-    def __init__(self, model, batch_size: int, seq_len: int, use_graph: bool = True):
+    def __init__(self, model, batch_size: int, seq_len: int, use_graph: bool = True, precision: str = "bf16"):
         if not isinstance(model, (ECGCNN, ECGMultimodal)):
             raise EcgB200Error("InferStep drives ecgb200 ECGCNN / ECGMultimodal models")
         self.model = model
@@ -45,6 +48,10 @@ class InferStep:
         self.dev = next(model.parameters()).device
         if self.dev.type != "cuda":
             raise EcgB200Error("InferStep needs the model on a CUDA device (no CPU fallback)")
+        if precision not in ("bf16", "fp32x3"):
+            raise EcgB200Error("precision must be 'bf16' or 'fp32x3' (split-precision: fp32-accurate on the tensor cores)")
+        self.x3 = precision == "fp32x3"
+        self.precision = precision
         self.use_graph = use_graph
         self.graphs = None
         self.launches_per_batch = 6
@@ -82,9 +89,16 @@ class InferStep:
             self.wfT = e(self.hid, 2 * self.feat)
         self.cur = 0
         self.rows = [B, B]                                         # live windows per slot (ragged last batch)
-        self.acts = [eb(B, self.cip[0] // 8, T, 8)] + \
-                    [eb(B, self.chan[l + 1] // 8, self.L[l] // 2, 8) for l in range(3)]
-        self.wt = [eb(15, self.cip[l] // 8, self.chan[l + 1], 8) for l in range(4)]
+        if self.x3:
+            # split tensors: [hi | lo | hi] planes of every activation, [w_hi | w_hi | w_lo] of every weight
+            self.ct = [lib.ecgb200_split_channels(c) for c in self.chan[:4]]
+            zb = lambda *s: torch.zeros(*s, dtype=BF16, device=dev)    # noqa: E731  (the padding plane is never written)
+            self.acts = [zb(B, self.ct[0] // 8, T, 8)] + [zb(B, self.ct[l + 1] // 8, self.L[l] // 2, 8) for l in range(3)]
+            self.wt = [eb(15, self.ct[l] // 8, self.chan[l + 1], 8) for l in range(4)]
+        else:
+            self.acts = [eb(B, self.cip[0] // 8, T, 8)] + \
+                        [eb(B, self.chan[l + 1] // 8, self.L[l] // 2, 8) for l in range(3)]
+            self.wt = [eb(15, self.cip[l] // 8, self.chan[l + 1], 8) for l in range(4)]
         self.scale = [e(self.chan[l + 1]) for l in range(4)]
         self.shift = [e(self.chan[l + 1]) for l in range(4)]
         self.nparts = 4 * ((self.L[3] + 127) // 128)
@@ -104,8 +118,12 @@ class InferStep:
             for t in (conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var):
                 if t.dtype != F32 or not t.is_cuda or not t.is_contiguous():
                     raise EcgB200Error("InferStep needs contiguous float32 CUDA parameters")
-            check(lib.ecgb200_conv1d_prep_weights_bf16(conv.weight.data_ptr(), _p(self.wt[l]), None, self.chan[l + 1],
-                                                       self.chan[l], st), "prep_weights")
+            if self.x3:
+                check(lib.ecgb200_conv1d_prep_weights_split_bf16(conv.weight.data_ptr(), _p(self.wt[l]), self.chan[l + 1],
+                                                                 self.chan[l], st), "prep_weights_split")
+            else:
+                check(lib.ecgb200_conv1d_prep_weights_bf16(conv.weight.data_ptr(), _p(self.wt[l]), None, self.chan[l + 1],
+                                                           self.chan[l], st), "prep_weights")
             check(lib.ecgb200_bn_fold_f32(bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(),
                                           bn.running_var.data_ptr(), _p(conv.bias), _p(self.scale[l]),
                                           _p(self.shift[l]), self.chan[l + 1], float(bn.eps), st), "bn_fold")
@@ -135,13 +153,22 @@ class InferStep:
     def _enqueue(self, slot: int):
         st = torch.cuda.current_stream(self.dev).cuda_stream
         B = self.B
-        check(lib.ecgb200_pack_input_bf16(_p(self.xs[slot]), _p(self.acts[0]), B, self.chan[0], self.T, st), "pack")
-        for l in range(4):
-            last = l == 3
-            check(lib.ecgb200_conv1d_bn_relu_pool_infer_bf16(
-                _p(self.acts[l]), _p(self.wt[l]), _p(self.scale[l]), _p(self.shift[l]),
-                None if last else _p(self.acts[l + 1]), _p(self.gap_part) if last else None,
-                B, self.cip[l], self.chan[l + 1], self.L[l], st), f"conv_infer_L{l + 1}")
+        if self.x3:
+            check(lib.ecgb200_pack_input_split_bf16(_p(self.xs[slot]), _p(self.acts[0]), B, self.chan[0], self.T, st), "pack_split")
+            for l in range(4):
+                last = l == 3
+                check(lib.ecgb200_conv1d_bn_relu_pool_infer_split_bf16(
+                    _p(self.acts[l]), _p(self.wt[l]), _p(self.scale[l]), _p(self.shift[l]),
+                    None if last else _p(self.acts[l + 1]), _p(self.gap_part) if last else None,
+                    B, self.chan[l], self.chan[l + 1], self.L[l], st), f"conv_infer_split_L{l + 1}")
+        else:
+            check(lib.ecgb200_pack_input_bf16(_p(self.xs[slot]), _p(self.acts[0]), B, self.chan[0], self.T, st), "pack")
+            for l in range(4):
+                last = l == 3
+                check(lib.ecgb200_conv1d_bn_relu_pool_infer_bf16(
+                    _p(self.acts[l]), _p(self.wt[l]), _p(self.scale[l]), _p(self.shift[l]),
+                    None if last else _p(self.acts[l + 1]), _p(self.gap_part) if last else None,
+                    B, self.cip[l], self.chan[l + 1], self.L[l], st), f"conv_infer_L{l + 1}")
         m, bb = self.model, self.bb
         if self.mm:
             dm = m.demo_encoder.mlp
@@ -161,6 +188,8 @@ class InferStep:
         of the 4th Conv1d (what the reference's forward hook captures, src/interpretability/grad_cam_1d.py:36-43),
         returned as fp32 (rows, C4, T/8) together with block 4's eval bn_state {mean, rstd, scale, shift} for
         ecgb200_gradcam_f32.  Un-captured (seven launches); the buffers are overwritten by the next call."""
+        if self.x3:
+            raise EcgB200Error("the Grad-CAM front end runs on the bf16 engine (precision='bf16') or the fp32 module path")
         n = int(x.shape[0]) if x.dim() == 3 else -1
         if n < 1 or n > self.B or tuple(x.shape[1:]) != tuple(self.xs[0].shape[1:]):
             raise EcgB200Error(f"InferStep was built for x{tuple(self.xs[0].shape)} (or fewer windows), "

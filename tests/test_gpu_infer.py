@@ -297,3 +297,47 @@ def test_engine_at_benchmark_sizes_vs_fp32_module_path(kind, nl, B, T):
     perm = torch.randperm(B, generator=torch.Generator().manual_seed(1)).to(DEV)
     again = eng(x[perm].contiguous(), None if demo is None else demo[perm].contiguous())
     assert torch.equal(again, logits[perm])
+
+
+@pytest.mark.parametrize("kind,nl,B,T", [("cnn", 5, 6, 1000), ("cnn", 1, 3, 5000), ("mm", 5, 9, 1000), ("cnn", 5, 2, 250),
+                                         ("cnn", 5, 300, 1000)])
+def test_split_precision_engine_meets_the_fp32_bar(kind, nl, B, T):
+    """InferStep(precision='fp32x3'): the SAME tcgen05 kernels with every activation / weight carried as bf16 hi + lo planes
+    (3x the input channels: hi*hi + lo*hi + hi*lo, fp32 accumulation).  north_star's fp32 bar: logits within 1e-4 relative
+    of the reference's fp32 path (measured ~1e-5), i.e. 200x tighter than the bf16 engine's 2e-2."""
+    sd = O.init_state_dict(kind, nl, seed=42)
+    _randomise_bn(sd, 7)
+    model = (P.ECGMultimodal() if kind == "mm" else P.ECGCNN(12, 256, nl))
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV).eval()
+    x = gen(B, 12, T, seed=11)
+    demo = gen(B, 5, seed=12).abs() if kind == "mm" else None
+    ref = O.multimodal_forward(sd, x, demo) if kind == "mm" else O.ecgcnn_forward(sd, x)
+    eng = P.InferStep(model, B, T, precision="fp32x3")
+    logits = eng(x.to(DEV), None if demo is None else demo.to(DEV)).clone()
+    torch.cuda.synchronize()
+    err = rel_inf(logits, ref)
+    print(f"fp32x3 {kind} B={B} T={T}: logits rel_inf vs fp32 oracle {err:.2e}")
+    assert err < 1e-4, err
+    assert rel_inf(eng.prob, torch.sigmoid(ref)) < 1e-4
+    assert torch.equal(eng(x.to(DEV), None if demo is None else demo.to(DEV)), logits)      # bit reproducible
+    with pytest.raises(P.EcgB200Error):
+        eng.conv4(x.to(DEV))
+
+
+def test_split_precision_engine_on_shipped_checkpoints(demo_inputs, expected_probs, golden):
+    """Thresholded predictions of the three shipped checkpoints on the demo records, bit-exact against the reference's
+    fp32 logits -- on the tensor cores."""
+    x, d = demo_inputs
+    cases = [("ecg_baseline_best.pth", P.ECGCNN(12, 256, 5), None, "eval/baseline_logits", slice(None)),
+             ("af_binary_best.pth", P.ECGCNN(12, 256, 1), None, "eval/af_logits", slice(None)),
+             ("ecg_multimodal_best.pth", P.ECGMultimodal(), d, "eval/mm_logits", slice(3, None))]
+    for ckpt, model, demo, lk, sl in cases:
+        model.load_state_dict(load_ckpt(ckpt), strict=True)
+        model = model.to(DEV).eval()
+        xs = x[sl]
+        eng = P.InferStep(model, xs.shape[0], xs.shape[2], precision="fp32x3")
+        logits = eng(xs.to(DEV), None if demo is None else demo.to(DEV)).cpu()
+        ref = torch.from_numpy(golden[lk])
+        assert rel_inf(logits, ref) < 1e-4, (ckpt, rel_inf(logits, ref))
+        assert torch.equal(O.predict(eng.prob.cpu()), O.predict(torch.sigmoid(ref))), ckpt
