@@ -592,6 +592,24 @@ def run_train(args, w, world, rank, local, dev, dist):
                           "launches_per_batch": inf.launches_per_batch,
                           "roofline_frac": 176.7 * T / 1000.0 * 1e-9 * B / (ms_inf / 100 * 1e-3),
                           "note": "eval forward, bf16 tcgen05 engine, inputs resident; 176.7 ns/window fused-inference model"}
+        del inf
+        # the same forward at fp32 accuracy on the tensor cores (split precision: 3 x the MMA work) and on the CUDA cores
+        inf3 = P.InferStep(model, B, T, precision="fp32x3")
+        inf3.load_batch(dx[0], slot=0)
+        inf3.load_batch(dx[1], slot=1)
+        inf3.capture()
+        for i in range(5):
+            inf3.run(slot=i & 1)
+        ms3 = tm.timed(lambda i: inf3.run(slot=i & 1), 100)
+        with torch.no_grad():
+            for _ in range(2):
+                model(dx[0])
+            ms32 = tm.timed(lambda i: model(dx[i & 1]), 10)
+        extra["infer_fp32"] = {"split_precision_tcgen05": {"value": B * 100 / (ms3 / 1000.0), "unit": UNIT, "ms_per_batch": ms3 / 100},
+                               "module_path_cuda_cores": {"value": B * 10 / (ms32 / 1000.0), "unit": UNIT, "ms_per_batch": ms32 / 10},
+                               "note": "eval forward at fp32 accuracy: InferStep(precision='fp32x3') (hi*hi + lo*hi + hi*lo on the "
+                                       "bf16 tensor cores, logits within 1e-5 of the fp32 oracle) vs the fp32-exact module forward"}
+        del inf3
         model.train()
 
     # ---- the library path on the same GPU(s): stock PyTorch (cuDNN / ATen / torch.optim.AdamW [/ DDP])
@@ -705,6 +723,18 @@ def run_cam(args, w, world, rank, local, dev, dist):
                          "peak_source": pk["src"], "algorithmic_bytes": by,
                          "note": "the conv stack itself is tensor-bound (see step_roofline for the per-layer model)"}
     extra["repeats_ms"] = [round(r / K, 4) for r in runs]
+    # side figure: the same pass with the forward at fp32 accuracy on the tensor cores (exact peak indices)
+    if world == 1:
+        inf3 = P.InferStep(model, chunk, T, precision="fp32x3")
+
+        def step3(i):
+            for x in dx:
+                P.gradcam_batch(model, x, signal_length=T, engine=inf3)
+        step3(0)
+        ms3 = tm.timed(step3, K)
+        extra["fp32_accurate"] = {"value": N * K / (ms3 / 1000.0), "unit": UNIT, "ms_per_step": ms3 / K,
+                                  "note": "forward on InferStep(precision='fp32x3'): CAM peak indices equal to the fp32 oracle's"}
+        del inf3
     if not args.no_gpu_reference:
         try:
             extra["gpu_reference"] = gpu_reference_cam(T, dev)

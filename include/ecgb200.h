@@ -387,6 +387,10 @@ int ecgb200_conv1d_prep_weights_split_bf16(const float* w, void* wf, int Co, int
 int ecgb200_conv1d_bn_relu_pool_infer_split_bf16(const void* xb, const void* wprep, const float* scale,
                                                  const float* shift, void* pb, float* gap_part, int B, int Ci,
                                                  int Co, int L, void* stream);
+/* y (B, Co, L) fp32 = conv(xb) + bias from split-plane inputs: the RAW 4th-conv output the reference's Grad-CAM forward
+ * hook captures (src/interpretability/grad_cam_1d.py:36-43), at fp32 accuracy on the tensor cores. */
+int ecgb200_conv1d_fwd_split_f32(const void* xb, const void* wprep, const float* bias, float* y, int B, int Ci, int Co,
+                                 int L, void* stream);
 /* Fused inference head: gap = inv_lp * sum of a window's `nparts` partials; z = proj(gap) (wpT = proj.weight
  * transposed, (C4, F)); with demo != NULL the DemoEncoder -> film_gen -> FiLM chain of
  * src/models/ecg_multimodal.py:44-59,88-99 (w1 (H,D0); w2 and wf TRANSPOSED: (H_in,H_out) and (H,2F)); logits = head(.) (ecg_cnn.py:63-64);

@@ -84,6 +84,7 @@ _SIGS = {
     "ecgb200_pack_input_split_bf16": (_I, [_P, _P, _I, _I, _I, _P]),
     "ecgb200_conv1d_prep_weights_split_bf16": (_I, [_P, _P, _I, _I, _P]),
     "ecgb200_conv1d_bn_relu_pool_infer_split_bf16": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "ecgb200_conv1d_fwd_split_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "ecgb200_infer_head_f32": (_I, [_P, _I, _F] + [_P] * 14 + [_I] * 6 + [_P]),
     "ecgb200_transpose_f32": (_I, [_P, _P, _I, _I, _P]),
 }

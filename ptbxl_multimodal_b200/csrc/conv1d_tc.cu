@@ -269,6 +269,8 @@ __device__ __forceinline__ void conv_issue_group_stream(uint32_t acc0, uint64_t 
 //        the next conv, whose weights are laid out as [w_hi | w_hi | w_lo], then computes
 //        x_hi*w_hi + x_lo*w_hi + x_hi*w_lo with fp32 accumulation -- fp32-accurate to ~1e-5 (only lo*lo is dropped) at
 //        three times the bf16 MMA count, on the same tcgen05 kernel.
+// MODE 6 (split-precision Grad-CAM front end): the RAW conv output + bias in fp32, (B, Co, L) NCL (`stat_part` = the fp32
+//        output): what the reference's forward hook on the 4th Conv1d captures, at fp32 accuracy from split inputs.
 // MODE 2 (inference, last block): as MODE 1 but nothing is stored: the pooled rows are summed over time per
 //        (tile, lane quarter) for AdaptiveAvgPool1d(1) (`stat_part` = gap_part[tile][4][Co], fixed order).
 constexpr int C2_THREADS = 320;
@@ -504,6 +506,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmapA, const __grid_constant_
                         float v[32];
                         tc::tmem_ld32(taddr, v);
                         tc::tmem_ld_wait();
+                        if constexpr (MODE == 6) {
+                            // lane = time step: for a fixed channel the warp's 32 lanes are 128 contiguous bytes of (b, c, :)
+                            if (live) {
+                                float* arow = stat_part + ((size_t)b * Co + c0) * L + t;
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) arow[(size_t)i * L] = v[i] + bv[i];
+                            }
+                            continue;
+                        }
                         if constexpr (MODE == 1 || MODE == 2 || MODE == 5) {
                             // relu(scale * conv + shift), then max over the pool pair (lanes 2p, 2p+1): the even lane
                             // keeps channels 0-15 of the block, the odd lane 16-31
@@ -847,6 +858,13 @@ extern "C" int ecgb200_conv1d_bn_relu_pool_infer_split_bf16(const void* xb, cons
     const int Ct = ecgb200_split_channels(Ci);
     if (gap_part != nullptr) return conv_tc_launch<2>(xb, wprep, scale, shift, nullptr, gap_part, B, Ct, Co, L, stream);
     return conv_tc_launch<5>(xb, wprep, scale, shift, pb, nullptr, B, Ct, Co, L, stream, ecgb200_split_channels(Co));
+}
+
+// Raw conv output + bias in fp32 (B, Co, L) from split-plane inputs (the Grad-CAM front end's 4th conv at fp32 accuracy).
+extern "C" int ecgb200_conv1d_fwd_split_f32(const void* xb, const void* wprep, const float* bias, float* y, int B, int Ci,
+                                            int Co, int L, void* stream) {
+    if (!xb || !wprep || !y || B <= 0 || L <= 0 || Ci <= 0) return ECGB200_EINVAL;
+    return conv_tc_launch<6>(xb, wprep, bias, nullptr, nullptr, y, B, ecgb200_split_channels(Ci), Co, L, stream);
 }
 
 extern "C" int ecgb200_conv1d_fwd_bf16(const void* xb, const void* wprep, const float* bias, void* yb,

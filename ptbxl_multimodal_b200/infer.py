@@ -188,8 +188,6 @@ class InferStep:
         of the 4th Conv1d (what the reference's forward hook captures, src/interpretability/grad_cam_1d.py:36-43),
         returned as fp32 (rows, C4, T/8) together with block 4's eval bn_state {mean, rstd, scale, shift} for
         ecgb200_gradcam_f32.  Un-captured (seven launches); the buffers are overwritten by the next call."""
-        if self.x3:
-            raise EcgB200Error("the Grad-CAM front end runs on the bf16 engine (precision='bf16') or the fp32 module path")
         n = int(x.shape[0]) if x.dim() == 3 else -1
         if n < 1 or n > self.B or tuple(x.shape[1:]) != tuple(self.xs[0].shape[1:]):
             raise EcgB200Error(f"InferStep was built for x{tuple(self.xs[0].shape)} (or fewer windows), "
@@ -202,13 +200,26 @@ class InferStep:
             self.bnst4 = torch.empty(4, c4, dtype=F32, device=self.dev)
         self.xs[0][:n].copy_(x, non_blocking=True)
         self.rows[0] = n
+        blk = self.bb.backbone[3]
+        conv, bn = blk.net[0], blk.net[1]
+        if self.x3:
+            # split precision: blocks 1-3 fused, then the raw 4th conv straight to fp32 (B, C4, T/8)
+            check(lib.ecgb200_pack_input_split_bf16(_p(self.xs[0]), _p(self.acts[0]), B, self.chan[0], self.T, st), "pack_split")
+            for l in range(3):
+                check(lib.ecgb200_conv1d_bn_relu_pool_infer_split_bf16(
+                    _p(self.acts[l]), _p(self.wt[l]), _p(self.scale[l]), _p(self.shift[l]), _p(self.acts[l + 1]), None,
+                    B, self.chan[l], self.chan[l + 1], self.L[l], st), f"conv_infer_split_L{l + 1}")
+            check(lib.ecgb200_conv1d_fwd_split_f32(_p(self.acts[3]), _p(self.wt[3]), _p(conv.bias), _p(self.A), B, self.chan[3],
+                                                   c4, L4, st), "conv4_split")
+            check(lib.ecgb200_bn_eval_state_f32(bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(),
+                                                bn.running_var.data_ptr(), _p(self.bnst4), c4, float(bn.eps), st),
+                  "bn_eval_state")
+            return self.A[:n], self.bnst4
         check(lib.ecgb200_pack_input_bf16(_p(self.xs[0]), _p(self.acts[0]), B, self.chan[0], self.T, st), "pack")
         for l in range(3):
             check(lib.ecgb200_conv1d_bn_relu_pool_infer_bf16(
                 _p(self.acts[l]), _p(self.wt[l]), _p(self.scale[l]), _p(self.shift[l]), _p(self.acts[l + 1]), None,
                 B, self.cip[l], self.chan[l + 1], self.L[l], st), f"conv_infer_L{l + 1}")
-        blk = self.bb.backbone[3]
-        conv, bn = blk.net[0], blk.net[1]
         check(lib.ecgb200_conv1d_fwd_bf16(_p(self.acts[3]), _p(self.wt[3]), _p(conv.bias), _p(self.y4), B, self.cip[3],
                                           c4, L4, st), "conv4")
         check(lib.ecgb200_unpack_act_bf16(_p(self.y4), _p(self.A), B, c4, L4, st), "unpack")

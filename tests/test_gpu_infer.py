@@ -321,8 +321,6 @@ def test_split_precision_engine_meets_the_fp32_bar(kind, nl, B, T):
     assert err < 1e-4, err
     assert rel_inf(eng.prob, torch.sigmoid(ref)) < 1e-4
     assert torch.equal(eng(x.to(DEV), None if demo is None else demo.to(DEV)), logits)      # bit reproducible
-    with pytest.raises(P.EcgB200Error):
-        eng.conv4(x.to(DEV))
 
 
 def test_split_precision_engine_on_shipped_checkpoints(demo_inputs, expected_probs, golden):
@@ -341,3 +339,45 @@ def test_split_precision_engine_on_shipped_checkpoints(demo_inputs, expected_pro
         ref = torch.from_numpy(golden[lk])
         assert rel_inf(logits, ref) < 1e-4, (ckpt, rel_inf(logits, ref))
         assert torch.equal(O.predict(eng.prob.cpu()), O.predict(torch.sigmoid(ref))), ckpt
+
+
+def test_gradcam_batch_on_the_split_precision_engine(demo_inputs):
+    """Grad-CAM with the forward on the tensor cores at fp32 accuracy (precision='fp32x3'): the maps agree with the fp32
+    CPU oracle as closely as the fp32 CUDA-core path does (<= 1e-3 absolute; maps are in [0, 1]) and the PEAK INDICES are
+    the oracle's on every (window, class) map whose top two values differ by more than 1e-4 -- north_star's bit-exact
+    argmax, now off the CUDA cores.  Also on 64 synthetic 12x1000 windows with random-init weights (config-5 shape)."""
+    x, _ = demo_inputs
+    model = P.ECGCNN(12, 256, 5)
+    sd = load_ckpt("ecg_baseline_best.pth")
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV).eval()
+    xs = torch.cat([x, gen(6, 12, 5000, seed=41)])
+    eng = P.InferStep(model, xs.shape[0], 5000, precision="fp32x3")
+    cam, arg = P.gradcam_batch(model, xs.to(DEV), signal_length=5000, engine=eng)
+    ref = O.gradcam_batched(sd, xs, 5000)
+    torch.cuda.synchronize()
+    cam, arg = cam.cpu(), arg.cpu().long()
+    assert float((cam - ref).abs().max()) < 1e-3, float((cam - ref).abs().max())
+    top2 = ref.topk(2, dim=2).values
+    clear = (top2[..., 0] - top2[..., 1]) > 1e-4
+    assert bool((arg == ref.argmax(dim=2))[clear].all())
+    assert float(clear.float().mean()) > 0.9
+    # config-5 shape, random init
+    sd2 = O.init_state_dict("cnn", 5, seed=42)
+    m2 = P.ECGCNN(12, 256, 5)
+    m2.load_state_dict(sd2, strict=True)
+    m2 = m2.to(DEV).eval()
+    x2 = gen(64, 12, 1000, seed=0)
+    e2 = P.InferStep(m2, 64, 1000, precision="fp32x3")
+    cam2, arg2 = P.gradcam_batch(m2, x2.to(DEV), signal_length=1000, engine=e2)
+    ref2 = O.gradcam_batched(sd2, x2, 1000)
+    cam2, arg2 = cam2.cpu(), arg2.cpu().long()
+    # random-init maps are nearly flat before the min/max normalisation, which amplifies a 1e-5 relative difference of the
+    # conv output; the shipped-checkpoint maps above hold 1e-3
+    assert float((cam2 - ref2).abs().max()) < 1e-2, float((cam2 - ref2).abs().max())
+    t2 = ref2.topk(2, dim=2).values
+    clear2 = (t2[..., 0] - t2[..., 1]) > 1e-4
+    eq = arg2 == ref2.argmax(dim=2)
+    print(f"fp32x3 Grad-CAM, 64 x 5 maps: peaks equal on {float(eq.float().mean()) * 100:.1f} % of all maps, "
+          f"{float(eq[clear2].float().mean()) * 100:.1f} % of the {int(clear2.sum())} maps with a clear maximum")
+    assert bool(eq[clear2].all())
