@@ -307,6 +307,11 @@ int ecgb200_set_pdl(int on);
 /* Debug only: when buf != NULL, CTA 0 of the bf16 conv kernel writes clock64() stamps of its pipeline
  * events into buf[0..63] (device memory).  NULL switches tracing off (the default). */
 int ecgb200_debug_set_trace(long long* buf);
+/* A/B switch: the streamed-weight conv layers (>= 64 input channels, weights larger than 64 KB: blocks 3 and 4 of
+ * src/models/ecg_cnn.py:29-33, forward and dgrad) run as CTA PAIRS with tcgen05 cta_group::2 (M = 256 per instruction, each
+ * SM staging half of the weight slab); 0 selects the one-SM kernel for them.  On by default; results are bit-identical.
+ * Do not flip it between ecgb200_conv1d_stat_parts_bf16 and the launch that call sizes. */
+int ecgb200_debug_set_conv_pair(int on);
 /* Debug only: when buf != NULL every CTA of the tcgen05 conv / wgrad kernels writes %globaltimer (ns) at its first
  * and after its last instruction to buf[2 * linear block id + {0, 1}] (launch ramp, spread and tail of a grid). */
 int ecgb200_debug_set_cta_span(unsigned long long* buf);

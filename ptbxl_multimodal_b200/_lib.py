@@ -74,6 +74,7 @@ _SIGS = {
     "ecgb200_debug_set_trace": (_I, [_P]),
     "ecgb200_debug_set_diag": (_I, [_P]),
     "ecgb200_debug_set_cta_span": (_I, [_P]),
+    "ecgb200_debug_set_conv_pair": (_I, [_I]),
     "ecgb200_set_spin_timeout_ms": (_I, [C.c_uint, C.c_uint]),
     "ecgb200_debug_stamp": (_I, [_P, _I, _P]),
     "ecgb200_adamw_flat_f32": (_I, [_P, _P, _P, _P, C.c_int64, _P, _P, _P]),

@@ -716,9 +716,22 @@ static int conv2_cfg(int B, int Ci, int Co, int L, Conv2Cfg* P, size_t* smem_out
     return grid;
 }
 
+#include "conv1d_tc2.cuh"
+
+// A/B switch for the two-SM (cta_group::2) kernel of the streamed-weight layers (default on).  Not for use between
+// ecgb200_conv1d_stat_parts_bf16 and the launch it sizes.
+extern "C" int ecgb200_debug_set_conv_pair(int on) {
+    g_conv_pair = on != 0;
+    return 0;
+}
+
 extern "C" int ecgb200_conv1d_stat_parts_bf16(int B, int Ci, int Co, int L) {
     Conv2Cfg P;
     size_t smem;
+    if (B > 0 && L > 0) {
+        const int gp = conv_pair_cfg(B, Ci, Co, L, &P, &smem);
+        if (gp > 0) return gp;
+    }
     if (B <= 0 || L <= 0 || Ci <= 0 || (Ci & 15) || Ci > 384 || (Ci > 64 && (Ci & 63)) || Co <= 0 || (Co & 31) || Co > 256) return 0;
     const int g = conv2_cfg(B, Ci, Co, L, &P, &smem);
     return g > 0 ? g : 0;
@@ -732,6 +745,13 @@ template <int MODE>
 static int conv_tc_launch(const void* xb, const void* wprep, const float* bias, const float* shift, void* yb,
                           float* stat_part, int B, int Ci, int Co, int L, void* stream, int Cn = 0) {
     if (Ci <= 0 || (Ci & 15) || Ci > 384 || (Ci > 64 && (Ci & 63)) || Co <= 0 || (Co & 31) || Co > 256) return ECGB200_EUNSUPPORTED;
+    if constexpr (MODE == 0 || MODE == 3) {
+        // streamed-weight layers (blocks 3 and 4, forward and dgrad): the two-SM kernel
+        Conv2Cfg PP;
+        size_t smem2;
+        const int gp = conv_pair_cfg(B, Ci, Co, L, &PP, &smem2);
+        if (gp > 0) return conv_tc_pair_launch<MODE>(xb, wprep, bias, yb, stat_part, B, Ci, Co, L, PP, gp, smem2, stream);
+    }
     // Input tiles: one 4-D box of 16-byte rows per tile for the thin layers; from 128 input channels on, two wide-row
     // boxes per 8-channel chunk (measured, CTA time at B=256: 128->256 32.5 -> 31.8 us, 256->128 31.7 -> 30.6 us,
     // 128->64 26.5 -> 25.6 us; for <= 64 input channels the 2 x Ci/8 instructions per tile cost more than they save)

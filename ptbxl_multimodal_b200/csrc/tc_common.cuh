@@ -218,6 +218,72 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                  ::"r"(smem_u32(bar)) : "memory");
 }
+// ---------------------------------------------------------------- CTA pair (cta_group::2, cluster of two CTAs on one TPC)
+// Rank 0 of the pair issues every tcgen05.mma for both SMs: M = 256 (each CTA's own 128 rows of A and its own TMEM lanes),
+// B split by N (each CTA's shared memory holds N/2 columns at the SAME offset).  Barriers live at the same offsets in both
+// CTAs; `mapa` gives the shared::cluster address of the leader's copy.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {          // every thread of both CTAs
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t cta_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {     // possibly the peer CTA's barrier
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// 3-D tiled load into THIS CTA's shared memory whose bytes are counted on a barrier given by its shared::cluster address
+// (the pair leader's): the .cta_group::2 form is what allows destination and barrier to sit in different CTAs of the pair
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1,
+                                                 int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr),
+          "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot_in_smem, uint32_t cols) {   // the same warp of BOTH CTAs
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(slot_in_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t cols) {           // the same warp of BOTH CTAs
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+template <int ACCMASK>
+__device__ __forceinline__ void mma_pair_bf16_x4(const uint32_t* d, const uint64_t* ad, const uint64_t* bd, uint32_t idesc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pa0, pa1, pa2, pa3;\n\t"
+        "setp.ne.b32 pa0, %13, 0;\n\t"
+        "setp.ne.b32 pa1, %14, 0;\n\t"
+        "setp.ne.b32 pa2, %15, 0;\n\t"
+        "setp.ne.b32 pa3, %16, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %4, %8, %12, pa0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%1], %5, %9, %12, pa1;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%2], %6, %10, %12, pa2;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%3], %7, %11, %12, pa3;\n\t"
+        "}"
+        ::"r"(d[0]), "r"(d[1]), "r"(d[2]), "r"(d[3]),
+          "l"(ad[0]), "l"(ad[1]), "l"(ad[2]), "l"(ad[3]),
+          "l"(bd[0]), "l"(bd[1]), "l"(bd[2]), "l"(bd[3]),
+          "r"(idesc),
+          "n"(ACCMASK & 1), "n"((ACCMASK >> 1) & 1), "n"((ACCMASK >> 2) & 1), "n"((ACCMASK >> 3) & 1)
+        : "memory");
+}
+// all MMAs issued so far by this thread complete -> one arrival on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void mma_pair_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);

@@ -4,12 +4,13 @@ import torch
 import ptbxl_multimodal_b200 as P
 from ptbxl_multimodal_b200._lib import lib, check, ptr, stream
 BF = torch.bfloat16
+lib.ecgb200_debug_set_conv_pair(int(os.environ.get('PAIR', '1')))
 names = {0: 'start', 1: 'setup done', 2: 'end', 3: 'W resident'}
 for g in range(4):
     names[8 + g] = f'x{g} issued'; names[16 + g] = f'x{g} landed'; names[24 + g] = f'acc{g} free'
     names[32 + g] = f'mma{g} issued'; names[40 + g] = f'acc{g} full'; names[48 + g] = f'epi{g} done'
-for (B, Ci, Co, L) in [(256, 16, 32, 1000), (256, 32, 64, 500), (256, 64, 128, 250), (256, 128, 256, 125),
-                       (256, 256, 128, 125), (256, 128, 64, 250), (256, 64, 32, 500)]:
+SH = [(256, 64, 128, 250), (256, 128, 256, 125), (256, 256, 128, 125), (256, 128, 64, 250)] if os.environ.get('BIG') else [(256, 16, 32, 1000), (256, 32, 64, 500), (256, 64, 128, 250), (256, 128, 256, 125), (256, 256, 128, 125), (256, 128, 64, 250), (256, 64, 32, 500)]
+for (B, Ci, Co, L) in SH:
     xb = torch.randn(B, Ci // 8, L, 8, device='cuda').to(BF)
     wf = (torch.randn(15, Ci // 8, Co, 8, device='cuda') * 0.05).to(BF)
     yb = torch.empty(B, Co // 8, L, 8, dtype=BF, device='cuda')
