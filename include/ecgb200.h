@@ -307,11 +307,13 @@ int ecgb200_set_pdl(int on);
 /* Debug only: when buf != NULL, CTA 0 of the bf16 conv kernel writes clock64() stamps of its pipeline
  * events into buf[0..63] (device memory).  NULL switches tracing off (the default). */
 int ecgb200_debug_set_trace(long long* buf);
-/* A/B switch: the streamed-weight conv layers (>= 64 input channels, weights larger than 64 KB: blocks 3 and 4 of
- * src/models/ecg_cnn.py:29-33, forward and dgrad) run as CTA PAIRS with tcgen05 cta_group::2 (M = 256 per instruction, each
- * SM staging half of the weight slab); 0 selects the one-SM kernel for them.  On by default; results are bit-identical.
- * Do not flip it between ecgb200_conv1d_stat_parts_bf16 and the launch that call sizes. */
-int ecgb200_debug_set_conv_pair(int on);
+/* A/B switch for the CTA-pair (tcgen05 cta_group::2, M = 256 per instruction) kernels of the wide layers -- blocks 3 and 4 of
+ * src/models/ecg_cnn.py:29-33.  Bit 0: forward and dgrad (>= 64 input channels, weights larger than 64 KB; each SM stages half of
+ * the weight slab; bit-identical to the one-SM kernel).  Bit 1: wgrad (128 / 256 output channels; taps as M, each SM stages half
+ * of the dY tile).  Bit 2: also for small problems where the pair form does not pay (one tile per SM; few items per split) --
+ * for tests.  Default 3; 0 selects the one-SM kernels.  Do not flip it between ecgb200_conv1d_stat_parts_bf16 /
+ * ecgb200_conv1d_wgrad_bf16_ws_bytes and the launches those calls size. */
+int ecgb200_debug_set_conv_pair(int mask);
 /* Debug only: when buf != NULL every CTA of the tcgen05 conv / wgrad kernels writes %globaltimer (ns) at its first
  * and after its last instruction to buf[2 * linear block id + {0, 1}] (launch ramp, spread and tail of a grid). */
 int ecgb200_debug_set_cta_span(unsigned long long* buf);

@@ -718,10 +718,11 @@ static int conv2_cfg(int B, int Ci, int Co, int L, Conv2Cfg* P, size_t* smem_out
 
 #include "conv1d_tc2.cuh"
 
-// A/B switch for the two-SM (cta_group::2) kernel of the streamed-weight layers (default on).  Not for use between
-// ecgb200_conv1d_stat_parts_bf16 and the launch it sizes.
-extern "C" int ecgb200_debug_set_conv_pair(int on) {
-    g_conv_pair = on != 0;
+// A/B switch for the two-SM (cta_group::2) kernels of the wide layers: bit 0 = forward / dgrad, bit 1 = wgrad,
+// bit 2 = also for shapes where the pair form does not pay (tests); default 3.
+// Not for use between ecgb200_conv1d_stat_parts_bf16 and the launch it sizes.
+extern "C" int ecgb200_debug_set_conv_pair(int mask) {
+    g_conv_pair = mask & 7;
     return 0;
 }
 
@@ -1288,6 +1289,8 @@ static int wgrad_launch_reduce(const float4* pw, const float* db_part, float* dw
     return ecg_launch_status();
 }
 
+#include "wgrad_tc2.cuh"
+
 static void wgrad_tc_cfg(int B, int Cip, int Co, int L, int* ncc, int* S) {
     *ncc = Cip / 8 < 4 ? Cip / 8 : 4;
     if (wgrad_is_thin(Cip, Co)) *ncc = Cip / 8;
@@ -1307,6 +1310,8 @@ extern "C" size_t ecgb200_conv1d_wgrad_bf16_ws_bytes(int B, int Ci, int Co, int 
     const int Cip = (Ci + 15) / 16 * 16;
     int ncc, S;
     wgrad_tc_cfg(B, Cip, Co, L, &ncc, &S);
+    int pncc, pncb, pS;
+    if (wgrad_pair_cfg(B, Cip, Co, L, &pncc, &pncb, &pS) && pS > S) S = pS;
     return (size_t)S * Co * Cip * 16 * sizeof(float);
 }
 
@@ -1338,6 +1343,33 @@ extern "C" int ecgb200_conv1d_wgrad_bf16(const void* dyb, const void* xb, float*
         rc = ecg_launch_status();
         if (rc) return rc;
         return wgrad_launch_reduce((const float4*)ws, db_part, dw, db, S, Co, Ci, Cip, ndb, st);
+    }
+    int pncc, pncb, pS;
+    if (wgrad_pair_cfg(B, Cip, Co, L, &pncc, &pncb, &pS)) {
+        // wide layers: taps as M on CTA pairs, each SM staging half of the dY tile and its own chunks of the X tile
+        CUtensorMap dymap, xmap;
+        int rc = ecg_make_act_tmap64(&dymap, dyb, B, Co, L, TC_TILE_M, Co / 16);
+        if (rc) return rc;
+        rc = ecg_make_act_tmap(&xmap, xb, B, Cip, L, TC_ROWS, pncc);
+        if (rc) return rc;
+        const size_t stage = (size_t)(Co / 2) * 256 + (size_t)pncc * TC_ROWS * 16;
+        int nst = (int)(WT_SMEM_BUDGET / stage);
+        if (nst > WT_MAXST) nst = WT_MAXST;
+        const size_t smem = TC_HDR + (size_t)nst * stage;
+        cudaError_t e = cudaFuncSetAttribute(wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * pncb * pS); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, wgrad_pair_kernel, dymap, xmap, (float*)ws, Co, Cip, L, B, pncc, pncb, nst);
+        if (e != cudaSuccess) return (int)e;
+        rc = ecg_launch_status();
+        if (rc) return rc;
+        return wgrad_launch_reduce((const float4*)ws, db_part, dw, db, pS, Co, Ci, Cip, ndb, st);
     }
     const int ochunks = Co >= 128 ? 16 : Co / 8;
     CUtensorMap dymap, xmapA, xmapB;

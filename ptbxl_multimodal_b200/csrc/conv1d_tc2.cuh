@@ -310,9 +310,9 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap xmapA, const __grid_cons
 
 // Shape -> schedule of the pair kernel.  Returns the grid size (2 x pairs; = number of stat partials), or 0 when the layer is
 // not one the pair kernel takes (weights that fit in shared memory stay with the one-SM kernel: nothing to halve there).
-static int g_conv_pair = 1;                        // A/B switch: ecgb200_debug_set_conv_pair
+static int g_conv_pair = 3;                        // A/B switch (bit 0: forward / dgrad, bit 1: wgrad, bit 2: even where it does not pay): ecgb200_debug_set_conv_pair
 static int conv_pair_cfg(int B, int Ci, int Co, int L, Conv2Cfg* P, size_t* smem_out) {
-    if (!g_conv_pair) return 0;
+    if (!(g_conv_pair & 1)) return 0;
     if (Ci < 64 || (Ci & 63) || Ci > 384 || Co < 64 || (Co & 63) || Co > 256) return 0;
     if ((size_t)ECG_KS * Ci * Co * 2 <= 64 * 1024) return 0;
     const int npmax = ecg_num_sms() / 2;
@@ -322,20 +322,28 @@ static int conv_pair_cfg(int B, int Ci, int Co, int L, Conv2Cfg* P, size_t* smem
     P->xbytes_al = ((uint32_t)Ci * TC_ROWS * 2 + 1023u) & ~1023u;
     const size_t half = (size_t)64 * (Co / 2) * 2;
     const size_t budget = 225 * 1024 - TC_HDR - C2_STATB;
-    // R tiles per CTA per group (two accumulator stages in the 512 TMEM columns): the R with the fewest tiles on the busiest
-    // pair; on a tie the larger one (fewer weight passes: less L2 traffic, a longer look-ahead per ring slot)
-    int R = 0, best = 1 << 30;
+    // R tiles per CTA per group (two accumulator stages in the 512 TMEM columns).  Cost of a choice = rounds on the busiest
+    // pair x (R + 1/2): every round streams the whole weight tensor again (at R = 1 a 128-channel layer pulls 32 B/clk per SM
+    // out of L2 -- three quarters of what L2 delivers to 148 SMs) and pays its ramp; on a tie the larger R.
+    int R = 0, best = 1 << 30, tiles_busiest = 0;
+    bool multi = false;
     for (int r = 256 / Co; r >= 1; r >>= 1) {
         const int npg = ecg_cdiv(P->total_tiles, 2 * r);
         const int rounds = ecg_cdiv(npg, npmax);
         if ((size_t)(rounds > 1 ? 2 : 1) * r * P->xbytes_al + 4 * half > budget) continue;
-        if (rounds * r < best) { best = rounds * r; R = r; }
+        const int cost = rounds * (2 * r + 1);
+        if (cost < best) { best = cost; R = r; tiles_busiest = rounds * r; multi = rounds > 1; }
     }
     if (R < 1) return 0;
+    // The next group's input tiles go out as one burst of 2 * R * Ci/8 TMA instructions (~50 cycles each) in front of the
+    // weight stages queued behind them; with 64 of them the ring runs dry (measured, pair vs one-SM: 256-channel dgrad at
+    // batch 1024 136 vs 110 us, 128-channel dgrad 80 vs 77 us, while the forward layers with bursts of 32 gain 8-10 %).
+    // Spreading the burst over the stages made the producer thread -- and with it every kernel -- slower.
+    if (multi && 2 * R * (Ci / 8) > 32 && !(g_conv_pair & 4)) return 0;
     // one tile per CTA: nothing for the second accumulator stage to overlap, and the pair's extra set-up / tear-down
     // (cluster barriers, multicast commits: ~1.5 us per kernel) costs more than the lighter main loop saves
     // (measured at batch 64: step 0.253 -> 0.267 ms)
-    if (best < 2) return 0;
+    if (tiles_busiest < 2 && !(g_conv_pair & 4)) return 0;
     P->R = R; P->AS = 2;
     P->ngroups = ecg_cdiv(P->total_tiles, 2 * R);                     // pair groups
     const int npairs = P->ngroups < npmax ? P->ngroups : npmax;

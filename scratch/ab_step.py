@@ -7,10 +7,11 @@ from ptbxl_multimodal_b200.step import TrainStep
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
 from ptbxl_multimodal_b200._lib import lib
-variants = [dict(pair=0), dict(pair=1)]
+variants = [dict(pair=int(c)) for c in (sys.argv[3] if len(sys.argv) > 3 else '0303')]
 for kw in variants:
     kw = dict(kw)
-    lib.ecgb200_debug_set_conv_pair(kw.pop('pair', 1))
+    pm = kw.pop('pair', 3)
+    lib.ecgb200_debug_set_conv_pair(pm)
     torch.manual_seed(42)
     m = P.ECGCNN(12, 256, 5).cuda().train()
     o = P.FusedAdamW(m.parameters(), lr=1.5e-3, weight_decay=1e-4)
@@ -27,5 +28,5 @@ for kw in variants:
         for i in range(200): e.run(slot=i & 1)
         e1.record(); torch.cuda.synchronize()
         runs.append(e0.elapsed_time(e1) / 200)
-    print(json.dumps({'opts': kw, 'pair': bool(lib.ecgb200_conv1d_stat_parts_bf16(B, 128, 256, T // 8) % 2 == 0 and lib.ecgb200_conv1d_stat_parts_bf16(B, 128, 256, T // 8) != 128), 'ms_per_step': statistics.median(runs), 'windows_per_s': B / statistics.median(runs) * 1e3,
+    print(json.dumps({'opts': kw, 'pair_mask': pm, 'ms_per_step': statistics.median(runs), 'windows_per_s': B / statistics.median(runs) * 1e3,
                       'loss': float(e.loss)}))

@@ -10,7 +10,7 @@ T = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
 kind = sys.argv[3] if len(sys.argv) > 3 else 'cnn'
 ITERS = 10
 from ptbxl_multimodal_b200._lib import lib
-lib.ecgb200_debug_set_conv_pair(int(os.environ.get('PAIR', '1')))
+lib.ecgb200_debug_set_conv_pair(int(os.environ.get('PAIR', '3')))
 torch.manual_seed(42)
 m = (P.ECGCNN(12, 256, 5) if kind == 'cnn' else P.ECGMultimodal()).cuda().train()
 o = P.FusedAdamW(m.parameters(), lr=1.5e-3, weight_decay=1e-4)

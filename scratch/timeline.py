@@ -6,6 +6,8 @@ import ptbxl_multimodal_b200 as P
 from ptbxl_multimodal_b200.step import TrainStep
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
+from ptbxl_multimodal_b200._lib import lib
+lib.ecgb200_debug_set_conv_pair(int(os.environ.get('PAIR', '3')))
 torch.manual_seed(42)
 m = P.ECGCNN(12, 256, 5).cuda().train()
 o = P.FusedAdamW(m.parameters(), lr=1.5e-3, weight_decay=1e-4)

@@ -4,7 +4,7 @@ import torch
 import ptbxl_multimodal_b200 as P
 from ptbxl_multimodal_b200._lib import lib, check, ptr, stream
 BF = torch.bfloat16
-lib.ecgb200_debug_set_conv_pair(int(os.environ.get('PAIR', '1')))
+lib.ecgb200_debug_set_conv_pair(int(os.environ.get('PAIR', '3')))
 names = {0: 'start', 1: 'setup done', 2: 'end', 3: 'W resident'}
 for g in range(4):
     names[8 + g] = f'x{g} issued'; names[16 + g] = f'x{g} landed'; names[24 + g] = f'acc{g} free'
