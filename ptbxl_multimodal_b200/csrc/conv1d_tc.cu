@@ -347,7 +347,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmapA, const __grid_constant_
                 }
                 if (gi < 4) CTR(8 + gi);                         // x load of group gi issued
             };
-            if (ngl > 0) load_x(0);
+            // wide input tiles (2 x Ci/8 TMA instructions each) are issued by the epilogue warps, eight threads in parallel
+            const bool xhere = !P.wide;
+            if (ngl > 0 && xhere) load_x(0);
             if (resident) {
                 const uint32_t wbytes = (uint32_t)nstage * stage_bytes;
                 tc::mbar_arrive_expect_tx(wfull, wbytes);
@@ -355,7 +357,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmapA, const __grid_constant_
                     const uint32_t n = wbytes - off < 16384u ? wbytes - off : 16384u;
                     tc::bulk_load(wsm + off, reinterpret_cast<const uint8_t*>(wprep) + off, n, wfull);
                 }
-                for (int gi = 1; gi < ngl; ++gi) load_x(gi);
+                if (xhere)
+                    for (int gi = 1; gi < ngl; ++gi) load_x(gi);
             } else {
                 int slot = 0;
                 uint32_t ephase = 1;                             // first pass over the ring: slots start free
@@ -370,7 +373,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmapA, const __grid_constant_
                         tc::bulk_load(wsm + (size_t)slot * stage_bytes,
                                       reinterpret_cast<const uint8_t*>(wprep) + (size_t)s * stage_bytes, stage_bytes,
                                       wfull + slot);
-                        if (s == xat && gi + 1 < ngl) load_x(gi + 1);
+                        if (s == xat && gi + 1 < ngl && xhere) load_x(gi + 1);
                         if (++slot == P.NST) { slot = 0; ephase ^= 1; }
                     }
                 }
@@ -472,6 +475,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmapA, const __grid_constant_
             ssum[cb] += vs[0];
             ssq[cb] += qs[0];
         };
+        // Wide input tiles (>= 128 input channels: per 8-channel chunk a 2 KB box for rows [t0-7, t0+121) and a 256 B box for
+        // rows [t0+121, t0+137)): ONE thread gets a TMA instruction out only every ~50 cycles (operands through R2UR), 3-6 k
+        // cycles per group.  Lane 0 of each of the eight epilogue warps takes every eighth chunk instead: the first NXB groups at
+        // the start of the kernel, group g + NXB at the start of the epilogue of group g (its accumulators being complete means
+        // that the MMAs have finished reading that input buffer).
+        auto load_tiles = [&](int gi) {
+            const int xb = gi % P.NXB;
+            const int tile0 = ((int)blockIdx.x + gi * (int)gridDim.x) * R;
+            const int rcount = min(R, P.total_tiles - tile0);
+            if (warp == 2) tc::mbar_arrive_expect_tx(xfull + xb, xbytes * (uint32_t)rcount);
+            for (int r = 0; r < rcount; ++r) {
+                const int tile = tile0 + r;
+                const int b = tile / P.tiles_t, t2 = 2 * ((tile - b * P.tiles_t) * TC_TILE_M - ECG_PAD);
+                uint8_t* dst = xs + (size_t)(xb * R + r) * P.xbytes_al + (size_t)(warp - 2) * (TC_ROWS * 16);
+                for (int c = warp - 2; c < Ci / 8; c += 8, dst += 8 * TC_ROWS * 16) {
+                    tc::tma_load_3d(dst, &xmapA, xfull + xb, t2, c, b);
+                    tc::tma_load_3d(dst + 128 * 16, &xmapB, xfull + xb, t2 + 256, c, b);
+                }
+            }
+        };
+        if (P.wide && lane == 0)
+            for (int gi = 0; gi < P.NXB && gi < ngl; ++gi) load_tiles(gi);
+        __syncwarp();
         for (int gi = 0; gi < ngl; ++gi) {
             const int as = gi % P.AS;
             const int tile0 = ((int)blockIdx.x + gi * (int)gridDim.x) * R;
@@ -479,6 +505,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap xmapA, const __grid_constant_
             tc::mbar_wait(accfull + as, (gi / P.AS) & 1);
             if (gi < 4 && threadIdx.x == 64) CTR(40 + gi);       // accumulators of group gi complete
             tc::fence_after_sync();
+            if (P.wide && lane == 0 && gi + P.NXB < ngl) load_tiles(gi + P.NXB);
+            __syncwarp();
 #pragma unroll
             for (int cb = 0; cb < 8; ++cb) {
                 // work split between the two warps of a lane quarter: by channel block, or by tile when there is one block

@@ -10,9 +10,11 @@
 // layer (R = 1, two accumulator stages in the 512 TMEM columns), so that the epilogue of group g runs under the MMAs of g+1.
 //
 // Barriers sit at the same shared-memory offsets in both CTAs:
-//   wfull / xfull   leader's copy only: the leader's producer arms it with the bytes of BOTH CTAs, both CTAs' TMA loads
+//   wfull / xfull   leader's copy only: a thread of the leader arms it with the bytes of BOTH CTAs, both CTAs' TMA loads
 //                   complete on it (cp.async.bulk.tensor ... .cta_group::2 with the leader's shared::cluster address)
-//   wempty / xempty / accfull   both copies: tcgen05.commit ... multicast::cluster from the leader's MMA thread
+//   wempty / accfull   both copies: tcgen05.commit ... multicast::cluster from the leader's MMA thread
+//                   (accfull of group g also tells the epilogue warps that input buffer g % 2 may be refilled: they issue
+//                   the input-tile loads, eight threads in parallel -- a single thread manages one TMA instruction per ~50 cycles)
 //   accempty        leader's copy, 16 arrivals: the eight epilogue warps of each CTA (mbarrier.arrive on the mapa'd address)
 // MODE 0: training forward (+ BatchNorm partial statistics, one partial per CTA); MODE 3: dgrad / plain conv.
 #pragma once
@@ -116,32 +118,11 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap xmapA, const __grid_cons
 
     if (warp == 0) {
         if (lane == 0) {
-            const uint32_t xfull_l = tc::mapa_u32(tc::smem_u32(xfull), 0);
             const uint32_t wfull_l = tc::mapa_u32(tc::smem_u32(wfull), 0);
-            auto load_x = [&](int gi) {
-                const int xb = gi % P.NXB;
-                if (gi >= P.NXB) tc::mbar_wait(xempty + xb, ((gi / P.NXB) - 1) & 1);
-                const int base = group_base(gi);
-                const int rc0 = count_of(base, 0), rc1 = count_of(base, 1);
-                if (rank == 0) tc::mbar_arrive_expect_tx(xfull + xb, xbytes * (uint32_t)(rc0 + rc1));
-                const int tile0 = base + (int)rank * R, rcount = rank ? rc1 : rc0;
-                for (int r = 0; r < rcount; ++r) {
-                    const int tile = tile0 + r;
-                    const int b = tile / P.tiles_t, t0 = (tile - b * P.tiles_t) * TC_TILE_M;
-                    uint8_t* dst = xs + (size_t)(xb * R + r) * P.xbytes_al;
-                    // per 8-channel chunk: rows [t0-7, t0+121) as one 2 KB box, rows [t0+121, t0+137) as a 256 B box
-                    for (int c = 0; c < Ci / 8; ++c, dst += TC_ROWS * 16) {
-                        tc::tma_load_3d_pair(dst, &xmapA, xfull_l + 8u * (uint32_t)xb, 2 * (t0 - ECG_PAD), c, b);
-                        tc::tma_load_3d_pair(dst + 128 * 16, &xmapB, xfull_l + 8u * (uint32_t)xb, 2 * (t0 - ECG_PAD + 128), c, b);
-                    }
-                }
-                if (gi < 4) CTR(8 + gi);
-            };
-            if (ngl > 0) load_x(0);
+            // weights only: the input tiles are issued by the epilogue warps (below)
             int slot = 0;
             uint32_t ephase = 1;                                 // first pass over the ring: slots start free
             for (int gi = 0; gi < ngl; ++gi) {
-                const int xat = P.NXB == 1 ? nstage - 1 : (nstage - 1 < P.NST ? nstage - 1 : P.NST);
                 for (int s = 0; s < nstage; ++s) {
                     if (!(gi == 0 && s < P.NST)) tc::mbar_wait(wempty + slot, ephase);
                     if (rank == 0) tc::mbar_arrive_expect_tx(wfull + slot, 2u * half_bytes);
@@ -149,7 +130,6 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap xmapA, const __grid_cons
                     // this CTA's Co/2 columns of the 64-channel slab of tap k, channel group g: 8 rows of (Co/2) * 16 bytes
                     tc::tma_load_3d_pair(wsm + (size_t)slot * half_bytes, &wmap, wfull_l + 8u * (uint32_t)slot,
                                          (int)rank * Co, g * (kch / 8), k);
-                    if (s == xat && gi + 1 < ngl) load_x(gi + 1);
                     if (++slot == P.NST) { slot = 0; ephase ^= 1; }
                 }
             }
@@ -182,7 +162,6 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap xmapA, const __grid_cons
 #define ECG_PSTR(RC_) conv_pair_issue_group<RC_>(acc0, alo_g, blo0, (uint32_t)Co, xal16, bstep, stage16, gstep, groups, idesc, wfull, wempty, P.NST, slot, wphase)
                 if (rcount == 4) ECG_PSTR(4); else if (rcount == 3) ECG_PSTR(3); else if (rcount == 2) ECG_PSTR(2); else ECG_PSTR(1);
 #undef ECG_PSTR
-                tc::mma_pair_commit(xempty + xb);
                 tc::mma_pair_commit(accfull + as);
                 if (gi < 4) CTR(32 + gi);
             }
@@ -196,6 +175,35 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap xmapA, const __grid_cons
         const size_t chunk_stride = (size_t)L * 8;
         const bool want_stats = MODE == 0 && stat_part != nullptr;
         const uint32_t accempty_l = tc::mapa_u32(tc::smem_u32(accempty), 0);
+        // Input tiles.  A tile is 2 x Ci/8 TMA instructions (per 8-channel chunk a 2 KB box for rows [t0-7, t0+121) and a 256 B
+        // box for rows [t0+121, t0+137)), and ONE thread gets a TMA instruction out only every ~50 cycles (its operands travel
+        // through R2UR): 3-6 k cycles per group from the producer thread, in front of the weight stages queued behind them.
+        // So lane 0 of each of the eight epilogue warps takes every eighth chunk: groups 0 and 1 at the start of the kernel
+        // (both buffers are free), group g+2 at the start of the epilogue of group g -- its accumulators being complete means
+        // that the MMAs have finished reading buffer g % 2 -- so that the tiles land under the MMAs of group g+1.
+        const uint32_t xfull_l = tc::mapa_u32(tc::smem_u32(xfull), 0);
+        auto load_tiles = [&](int gi) {
+            const int xb = gi % P.NXB;
+            const int base = group_base(gi);
+            const int rc0 = count_of(base, 0), rc1 = count_of(base, 1);
+            if (rank == 0 && warp == 2) tc::mbar_arrive_expect_tx(xfull + xb, xbytes * (uint32_t)(rc0 + rc1));
+            const int tile0 = base + (int)rank * R, rcount = rank ? rc1 : rc0;
+            const uint32_t bar = xfull_l + 8u * (uint32_t)xb;
+            for (int r = 0; r < rcount; ++r) {
+                const int tile = tile0 + r;
+                const int b = tile / P.tiles_t, t2 = 2 * ((tile - b * P.tiles_t) * TC_TILE_M - ECG_PAD);
+                uint8_t* dst = xs + (size_t)(xb * R + r) * P.xbytes_al + (size_t)(warp - 2) * (TC_ROWS * 16);
+                for (int c = warp - 2; c < Ci / 8; c += 8, dst += 8 * TC_ROWS * 16) {
+                    tc::tma_load_3d_pair(dst, &xmapA, bar, t2, c, b);
+                    tc::tma_load_3d_pair(dst + 128 * 16, &xmapB, bar, t2 + 256, c, b);
+                }
+            }
+        };
+        if (lane == 0) {
+            if (ngl > 0) load_tiles(0);
+            if (ngl > 1) load_tiles(1);                  // more than one group per pair: two input buffers (conv_pair_cfg)
+        }
+        __syncwarp();
         float ssum[8], ssq[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
@@ -225,6 +233,8 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap xmapA, const __grid_cons
             tc::mbar_wait(accfull + as, (gi / P.AS) & 1);
             if (gi < 4 && threadIdx.x == 64) CTR(40 + gi);
             tc::fence_after_sync();
+            if (lane == 0 && gi + 2 < ngl) load_tiles(gi + 2);
+            __syncwarp();
 #pragma unroll
             for (int cb = 0; cb < 8; ++cb) {
                 if (cb < nblk && (nblk == 1 || (cb & 1) == half)) {
@@ -326,20 +336,14 @@ static int conv_pair_cfg(int B, int Ci, int Co, int L, Conv2Cfg* P, size_t* smem
     // pair x (R + 1/2): every round streams the whole weight tensor again (at R = 1 a 128-channel layer pulls 32 B/clk per SM
     // out of L2 -- three quarters of what L2 delivers to 148 SMs) and pays its ramp; on a tie the larger R.
     int R = 0, best = 1 << 30, tiles_busiest = 0;
-    bool multi = false;
     for (int r = 256 / Co; r >= 1; r >>= 1) {
         const int npg = ecg_cdiv(P->total_tiles, 2 * r);
         const int rounds = ecg_cdiv(npg, npmax);
         if ((size_t)(rounds > 1 ? 2 : 1) * r * P->xbytes_al + 4 * half > budget) continue;
         const int cost = rounds * (2 * r + 1);
-        if (cost < best) { best = cost; R = r; tiles_busiest = rounds * r; multi = rounds > 1; }
+        if (cost < best) { best = cost; R = r; tiles_busiest = rounds * r; }
     }
     if (R < 1) return 0;
-    // The next group's input tiles go out as one burst of 2 * R * Ci/8 TMA instructions (~50 cycles each) in front of the
-    // weight stages queued behind them; with 64 of them the ring runs dry (measured, pair vs one-SM: 256-channel dgrad at
-    // batch 1024 136 vs 110 us, 128-channel dgrad 80 vs 77 us, while the forward layers with bursts of 32 gain 8-10 %).
-    // Spreading the burst over the stages made the producer thread -- and with it every kernel -- slower.
-    if (multi && 2 * R * (Ci / 8) > 32 && !(g_conv_pair & 4)) return 0;
     // one tile per CTA: nothing for the second accumulator stage to overlap, and the pair's extra set-up / tear-down
     // (cluster barriers, multicast commits: ~1.5 us per kernel) costs more than the lighter main loop saves
     // (measured at batch 64: step 0.253 -> 0.267 ms)
@@ -352,6 +356,11 @@ static int conv_pair_cfg(int B, int Ci, int Co, int L, Conv2Cfg* P, size_t* smem
     int nst = (int)((budget - xall) / half);
     if (nst > C2P_MAXST) nst = C2P_MAXST;
     if (nst < 2) return 0;
+    // The ring has to cover the latency of a weight load under load (~2 us): slots x MMA time per slot.  The 256 -> 128
+    // channel dgrad with two 72 KB input buffers keeps 9 slots of 256 cycles and starves (batch 1024: 114 us against 97 us
+    // for the one-SM kernel); every other pair configuration of this network holds >= 4.6 k cycles.
+    const int mma_cyc = Co <= 64 ? 47 : (Co <= 128 ? 64 : 128);
+    if (nst * R * 4 * mma_cyc < 4000 && !(g_conv_pair & 4)) return 0;
     P->NST = nst;
     P->wide = 1; P->Cn = Co;
     P->tmem_cols = tmem_cols_for(2 * R * Co);
