@@ -781,10 +781,11 @@ static int conv_tc_launch(const void* xb, const void* wprep, const float* bias, 
         const int gp = conv_pair_cfg(B, Ci, Co, L, &PP, &smem2);
         if (gp > 0) return conv_tc_pair_launch<MODE>(xb, wprep, bias, yb, stat_part, B, Ci, Co, L, PP, gp, smem2, stream);
     }
-    // Input tiles: one 4-D box of 16-byte rows per tile for the thin layers; from 128 input channels on, two wide-row
-    // boxes per 8-channel chunk (measured, CTA time at B=256: 128->256 32.5 -> 31.8 us, 256->128 31.7 -> 30.6 us,
-    // 128->64 26.5 -> 25.6 us; for <= 64 input channels the 2 x Ci/8 instructions per tile cost more than they save)
-    const int wide = Ci >= 128;
+    // Input tiles: one 4-D box of 16-byte rows per tile for the 16-channel stem (the copy engine moves ~one 16-byte row per
+    // cycle); from 32 input channels on, two wide-row boxes per 8-channel chunk, issued by the eight epilogue threads in
+    // parallel (kernel time at B=256, wide + parallel issue against the one-box form: 32->64 17.5 -> 16.6 us, 64->32 dgrad
+    // 21.3 -> 20.0 us, 256->128 dgrad 29.7 -> 27.1 us; with ONE issuing thread the wide form only paid from 128 channels on)
+    const int wide = Ci >= 32;
     CUtensorMap xmapA, xmapB;
     int rc = wide ? ecg_make_act_tmap64(&xmapA, xb, B, Ci, L, 128, 1) : ecg_make_act_tmap(&xmapA, xb, B, Ci, L, TC_ROWS, Ci / 8);
     if (rc) return rc;
