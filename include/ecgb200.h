@@ -102,6 +102,21 @@ int ecgb200_bn_relu_pool_fwd_train_bf16(const void* yb, const float* stat_part, 
                                         int64_t* num_batches_tracked, float* bn_state, void* pb, float* gap,
                                         int B, int C, int L, float momentum, float eps, int nrep, void* stream);
 
+/* Last block (gap != NULL; its pooled output only feeds AdaptiveAvgPool1d, ecg_cnn.py:46,62): the same call, which also leaves
+ * the routing summary route[2][B][C] fp32 -- per (window, channel) the number of pool pairs with a ReLU-positive maximum and the
+ * sum of the raw conv outputs at those (first-index-wins) positions.  Every pooled position of (b, c) receives the same gradient
+ * dgap[b][c] / (L/2), so the two batch reductions of the BatchNorm backward are sums of dgap * route over B x C:
+ * ecgb200_bn_relu_pool_bwd_route_bf16 then needs ONE pass over y (to write dy) instead of two.  Same results as
+ * ecgb200_bn_relu_pool_bwd_bf16 up to fp32 summation order. */
+int ecgb200_bn_relu_pool_fwd_train_route_bf16(const void* yb, const float* stat_part, int nparts, const float* gamma,
+                                              const float* beta, float* running_mean, float* running_var,
+                                              int64_t* num_batches_tracked, float* bn_state, void* pb, float* gap,
+                                              float* route, int B, int C, int L, float momentum, float eps, int nrep,
+                                              void* stream);
+int ecgb200_bn_relu_pool_bwd_route_bf16(const void* yb, const float* bn_state, const float* dgap, const float* route,
+                                        void* dyb, float* dgamma, float* dbeta, float* db_part, int B, int C, int L,
+                                        int train, void* stream);
+
 /* dW (Co,Ci,15) fp32 and db (Co) fp32 from blocked-bf16 dy [B][Co/8][L][8] and x [B][Cip/8][L][8]
  * (Cip = Ci rounded up to 16) on tcgen05, accumulators resident in TMEM across the whole batch
  * share of a CTA; split-K partials in ws (ecgb200_conv1d_wgrad_bf16_ws_bytes) are reduced in a

@@ -57,6 +57,8 @@ _SIGS = {
     "ecgb200_conv1d_fwd_stats_bf16": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "ecgb200_conv1d_stat_parts_bf16": (_I, [_I, _I, _I, _I]),
     "ecgb200_bn_relu_pool_fwd_train_bf16": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _I, _P]),
+    "ecgb200_bn_relu_pool_fwd_train_route_bf16": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _I, _P]),
+    "ecgb200_bn_relu_pool_bwd_route_bf16": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "ecgb200_step_prep_bf16": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
     "ecgb200_head_fwd_bwd_f32": (_I, [_P] * 13 + [_I, _I, _I, _I, _F, _P]),
     "ecgb200_head_loss_parts": (_I, [_I]),

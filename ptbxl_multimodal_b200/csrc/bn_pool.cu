@@ -397,6 +397,48 @@ __device__ __forceinline__ void merge_parts8(const float* __restrict__ part, int
     __syncthreads();
 }
 
+// Sum of v[0..7] over the 32 lanes with a transposing butterfly: 4 + 2 + 1 + 1 + 1 = 9 shuffles instead of 8 x 5.  Afterwards
+// v[0] of lane l is the total of element 4 * bit4(l) + 2 * bit3(l) + bit2(l) (the same value in the four lanes l, l^1, l^2, l^3).
+__device__ __forceinline__ float warp_sum8_transposed(float* v, int lane) {
+#pragma unroll
+    for (int o = 16, half = 4; o >= 4; o >>= 1, half >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = up ? v[i] : v[i + half], keep = up ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+    return v[0];
+}
+
+// Block 4 (GAP gradient): the same two batch sums {sum g, sum g*a} from the forward pass's routing summary
+// route[0][b][c] = routed pool pairs, route[1][b][c] = sum of the raw conv outputs at the routed positions, with g = dgap[b][c] / Lp
+// for every routed position of (b, c).  Fixed order, double accumulation, every block for its own 8 channels.
+__device__ __forceinline__ void merge_route8(const float* __restrict__ route, const float* __restrict__ dgap, int B, int C,
+                                             int cc, float inv_lp, double* shd /* [32*16] */, double* out /* [16] */) {
+    const int ch = threadIdx.x & 7, grp = threadIdx.x >> 3;
+    double a = 0.0, b = 0.0;
+    for (int i = grp; i < B; i += 32) {
+        const size_t o = (size_t)i * C + cc * 8 + ch;
+        const double g = (double)(__ldg(dgap + o) * inv_lp);
+        a += g * (double)__ldg(route + o);
+        b += g * (double)__ldg(route + (size_t)B * C + o);
+    }
+    shd[grp * 16 + ch] = a;
+    shd[grp * 16 + 8 + ch] = b;
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        double t = 0.0;
+#pragma unroll 8
+        for (int g = 0; g < 32; ++g) t += shd[g * 16 + threadIdx.x];
+        out[threadIdx.x] = t;
+    }
+    __syncthreads();
+}
+
 // {sum, centred M2} per (channel, split): part[c][s], part[C + c][s]
 __global__ void __launch_bounds__(256)
 bn_stats_bf16_kernel(const uint4* __restrict__ y, float* __restrict__ part, int B, int C, int L, int tile_b) {
@@ -550,14 +592,18 @@ extern "C" int ecgb200_bn_relu_pool_fwd_bf16(const void* yb, const float* bn_sta
 // {sum, sum of squares} partials into mean / rstd / scale / shift for its 8 channels (identical in
 // every block; block row 0 publishes bn_state and updates the running statistics), then applies
 // BN + ReLU + MaxPool1d(2) (GAP variant: also the mean over time of the UNROUNDED pooled values).
-template <bool GAP>
-__global__ void __launch_bounds__(256, 4)
+// ROUTE (block 4, whose pooled output only feeds the time average): also leaves, per (window, channel), the number of pool
+// pairs that route a gradient (ReLU-positive maximum) and the sum of the raw conv outputs at the routed positions --
+// route[0][b][c], route[1][b][c].  The gradient of every pooled position of (b, c) is the same dgap[b][c] / Lp, so the two batch
+// reductions of the BatchNorm backward become sums over B x C of dgap * route instead of a pass over y (ecgb200_bn_relu_pool_bwd_route_bf16).
+template <bool GAP, bool ROUTE>
+__global__ void __launch_bounds__(256, ROUTE ? 3 : 4)
 bn_fwd_train_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__ part, int nparts,
                          const float* __restrict__ gamma, const float* __restrict__ beta,
                          float* __restrict__ running_mean, float* __restrict__ running_var,
                          int64_t* __restrict__ nbt, float* __restrict__ bn_state, uint4* __restrict__ p,
                          float* __restrict__ gap, int B, int C, int L, int Lp, int tile_b, float momentum,
-                         float eps, int nrep) {
+                         float eps, int nrep, float* __restrict__ route) {
     __shared__ double shd[32 * 16], mom[16];
     __shared__ float scs[8], sfs[8];
     const int cc = blockIdx.x;
@@ -613,9 +659,13 @@ bn_fwd_train_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__ 
         const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
         for (int bl = w; bl < nb; bl += nw) {
             const size_t row = (size_t)(b0 + bl) * (C / 8) + cc;
-            float acc[8];
+            float acc[8], cnt[ROUTE ? 8 : 1], sa[ROUTE ? 8 : 1];
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+            if constexpr (ROUTE) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { cnt[i] = 0.f; sa[i] = 0.f; }
+            }
             for (int j0 = lane; j0 < Lp; j0 += 64) {
                 uint4 u0[2], u1[2];
 #pragma unroll
@@ -636,41 +686,81 @@ bn_fwd_train_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__ 
                         const float r0 = fmaxf(fmaf(a0[i], sc[i], sf[i]), 0.f), r1 = fmaxf(fmaf(a1[i], sc[i], sf[i]), 0.f);
                         m[i] = fmaxf(r0, r1);
                         acc[i] += m[i];
+                        if constexpr (ROUTE) {                       // pool_sel: first index wins ties, ReLU mask
+                            const bool s0 = (r0 >= r1) && (r0 > 0.f), s1 = r1 > r0;
+                            cnt[i] += (s0 || s1) ? 1.f : 0.f;
+                            sa[i] += s0 ? a0[i] : (s1 ? a1[i] : 0.f);
+                        }
                     }
                     if (p != nullptr) p[row * Lp + j] = bf8_pack(m);
                 }
             }
+            if constexpr (ROUTE) {
+                const float tg = warp_sum8_transposed(acc, lane), tc = warp_sum8_transposed(cnt, lane),
+                            ts = warp_sum8_transposed(sa, lane);
+                if ((lane & 3) == 0) {
+                    const size_t o = (size_t)(b0 + bl) * C + cc * 8 + 4 * ((lane >> 4) & 1) + 2 * ((lane >> 3) & 1) + ((lane >> 2) & 1);
+                    gap[o] = tg / (float)Lp;
+                    route[o] = tc;
+                    route[(size_t)B * C + o] = ts;
+                }
+            } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = warp_sum(acc[i]);
-            if (lane < 8) {
-                float t = 0.f;
+                for (int i = 0; i < 8; ++i) acc[i] = warp_sum(acc[i]);
+                if (lane < 8) {
+                    float t = 0.f;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) if (i == lane) t = acc[i];
-                gap[(size_t)(b0 + bl) * C + cc * 8 + lane] = t / (float)Lp;
+                    for (int i = 0; i < 8; ++i) if (i == lane) t = acc[i];
+                    gap[(size_t)(b0 + bl) * C + cc * 8 + lane] = t / (float)Lp;
+                }
             }
         }
     }
 }
 
 // yb blocked bf16; stat_part float[nparts][2][C] from ecgb200_conv1d_fwd_stats_bf16.
-extern "C" int ecgb200_bn_relu_pool_fwd_train_bf16(const void* yb, const float* stat_part, int nparts,
+static int bn_fwd_train_launch(const void* yb, const float* stat_part, int nparts,
                                                    const float* gamma, const float* beta, float* running_mean,
                                                    float* running_var, int64_t* nbt, float* bn_state, void* pb,
                                                    float* gap, int B, int C, int L, float momentum, float eps,
-                                                   int nrep, void* stream) {
+                                                   int nrep, float* route, void* stream) {
     if (!yb || !stat_part || nparts <= 0 || !gamma || !beta || !bn_state || (!pb && !gap) || B <= 0 || C <= 0 ||
         (C & 7) || L < 2 || nrep < 1)
         return ECGB200_EINVAL;
     const int Lp = L / 2;
     const int tile_b = bnb_tile_b(B, C, 3), NS = (B + tile_b - 1) / tile_b;
     cudaStream_t st = (cudaStream_t)stream;
-    if (gap != nullptr)
-        return ecg_launch_pdl(bn_fwd_train_bf16_kernel<true>, dim3(C / 8, NS), dim3(256), 0, st, (const uint4*)yb,
+    if (gap != nullptr && route != nullptr)
+        return ecg_launch_pdl(bn_fwd_train_bf16_kernel<true, true>, dim3(C / 8, NS), dim3(256), 0, st, (const uint4*)yb,
                               stat_part, nparts, gamma, beta, running_mean, running_var, nbt, bn_state, (uint4*)pb, gap,
-                              B, C, L, Lp, tile_b, momentum, eps, nrep);
-    return ecg_launch_pdl(bn_fwd_train_bf16_kernel<false>, dim3(C / 8, NS), dim3(256), 0, st, (const uint4*)yb,
+                              B, C, L, Lp, tile_b, momentum, eps, nrep, route);
+    if (gap != nullptr)
+        return ecg_launch_pdl(bn_fwd_train_bf16_kernel<true, false>, dim3(C / 8, NS), dim3(256), 0, st, (const uint4*)yb,
+                              stat_part, nparts, gamma, beta, running_mean, running_var, nbt, bn_state, (uint4*)pb, gap,
+                              B, C, L, Lp, tile_b, momentum, eps, nrep, (float*)nullptr);
+    return ecg_launch_pdl(bn_fwd_train_bf16_kernel<false, false>, dim3(C / 8, NS), dim3(256), 0, st, (const uint4*)yb,
                           stat_part, nparts, gamma, beta, running_mean, running_var, nbt, bn_state, (uint4*)pb,
-                          (float*)nullptr, B, C, L, Lp, tile_b, momentum, eps, nrep);
+                          (float*)nullptr, B, C, L, Lp, tile_b, momentum, eps, nrep, (float*)nullptr);
+}
+
+extern "C" int ecgb200_bn_relu_pool_fwd_train_bf16(const void* yb, const float* stat_part, int nparts,
+                                                   const float* gamma, const float* beta, float* running_mean,
+                                                   float* running_var, int64_t* nbt, float* bn_state, void* pb,
+                                                   float* gap, int B, int C, int L, float momentum, float eps,
+                                                   int nrep, void* stream) {
+    return bn_fwd_train_launch(yb, stat_part, nparts, gamma, beta, running_mean, running_var, nbt, bn_state, pb, gap, B, C, L,
+                               momentum, eps, nrep, nullptr, stream);
+}
+
+// Last block (gap != NULL) with the routing summary route[2][B][C] for ecgb200_bn_relu_pool_bwd_route_bf16.
+extern "C" int ecgb200_bn_relu_pool_fwd_train_route_bf16(const void* yb, const float* stat_part, int nparts,
+                                                         const float* gamma, const float* beta, float* running_mean,
+                                                         float* running_var, int64_t* nbt, float* bn_state, void* pb,
+                                                         float* gap, float* route, int B, int C, int L, float momentum,
+                                                         float eps, int nrep, void* stream) {
+    if (!gap || !route) return ECGB200_EINVAL;
+    return bn_fwd_train_launch(yb, stat_part, nparts, gamma, beta, running_mean, running_var, nbt, bn_state, pb, gap, B, C, L,
+                               momentum, eps, nrep, route, stream);
 }
 
 // Routing of one pool pair in terms of the raw conv outputs a0, a1 (first index wins ties, ReLU mask):
@@ -768,7 +858,7 @@ bn_bwd_apply_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__ 
                          const uint4* __restrict__ dp, const float* __restrict__ dgap,
                          const float* __restrict__ part, uint4* __restrict__ dy, float* __restrict__ dgamma,
                          float* __restrict__ dbeta, float* __restrict__ db_part, int B, int C, int L, int Lp,
-                         float inv_n, int train, int tile_b, int nparts, int local_idx) {
+                         float inv_n, int train, int tile_b, int nparts, int local_idx, const float* __restrict__ route) {
     __shared__ float sh[8 * 8];
     __shared__ float cA[8], cB[8];
     __shared__ double shd[32 * 16], mom[16];
@@ -776,7 +866,8 @@ bn_bwd_apply_bf16_kernel(const uint4* __restrict__ y, const float* __restrict__ 
     const int b0 = blockIdx.y * tile_b, nb = min(tile_b, B - b0);
     const float inv_lp = 1.0f / (float)Lp;
     ecg_pdl_wait();                         // `part` comes from the reduce kernel launched just before
-    merge_parts8(part, nparts > 0 ? nparts : NS, C, cc, shd, mom);     // nparts > 0: an exchanged (SyncBN) partial list
+    if (route != nullptr) merge_route8(route, dgap, B, C, cc, inv_lp, shd, mom);   // block 4: no reduce pass over y
+    else merge_parts8(part, nparts > 0 ? nparts : NS, C, cc, shd, mom);     // nparts > 0: an exchanged (SyncBN) partial list
     if (threadIdx.x < 8) {
         const int c = cc * 8 + threadIdx.x;
         const double sg = mom[threadIdx.x], sga = mom[8 + threadIdx.x];
@@ -868,7 +959,22 @@ extern "C" int ecgb200_bn_relu_pool_bwd_bf16(const void* yb, const float* bn_sta
     // wait (griddepcontrol.wait = full completion + flush of the reduce kernel) before they read `part`
     return ecg_launch_pdl_if(true, bn_bwd_apply_bf16_kernel, dim3(C / 8, NS), dim3(256), 0, st, (const uint4*)yb, bn_state,
                              (const uint4*)dpb, dgap, (const float*)part, (uint4*)dyb, dgamma, dbeta, db_part, B, C, L, Lp,
-                             inv_n, train, tile_b, 0, -1);
+                             inv_n, train, tile_b, 0, -1, (const float*)nullptr);
+}
+
+// Block 4 in ONE pass: the batch reductions come from the routing summary the forward pass left
+// (ecgb200_bn_relu_pool_fwd_train_route_bf16), so y is read once (to write dy) instead of twice.
+extern "C" int ecgb200_bn_relu_pool_bwd_route_bf16(const void* yb, const float* bn_state, const float* dgap,
+                                                   const float* route, void* dyb, float* dgamma, float* dbeta,
+                                                   float* db_part, int B, int C, int L, int train, void* stream) {
+    if (!yb || !bn_state || !dgap || !route || !dyb || B <= 0 || C <= 0 || (C & 7) || L < 2) return ECGB200_EINVAL;
+    if (((uintptr_t)dgap & 15) != 0) return ECGB200_EINVAL;
+    const int Lp = L / 2;
+    const int tile_b = bnb_tile_b(B, C, 3), NS = (B + tile_b - 1) / tile_b;
+    const float inv_n = 1.0f / ((float)B * (float)L);
+    return ecg_launch_pdl(bn_bwd_apply_bf16_kernel, dim3(C / 8, NS), dim3(256), 0, (cudaStream_t)stream, (const uint4*)yb,
+                          bn_state, (const uint4*)nullptr, dgap, (const float*)nullptr, (uint4*)dyb, dgamma, dbeta, db_part, B, C,
+                          L, Lp, inv_n, train, tile_b, 0, -1, route);
 }
 
 // The two passes as separate calls, for SyncBN under data parallel: pass 1 leaves this replica's partials
@@ -899,5 +1005,5 @@ extern "C" int ecgb200_bn_relu_pool_bwd_apply_bf16(const void* yb, const float* 
     const float inv_n = 1.0f / ((float)B * (float)L * (float)nrep);
     return ecg_launch_pdl_if(false, bn_bwd_apply_bf16_kernel, dim3(C / 8, NS), dim3(256), 0, (cudaStream_t)stream,
                              (const uint4*)yb, bn_state, (const uint4*)dpb, dgap, part, (uint4*)dyb, dgamma,
-                             dbeta, db_part, B, C, L, Lp, inv_n, train, tile_b, nparts, local_idx);
+                             dbeta, db_part, B, C, L, Lp, inv_n, train, tile_b, nparts, local_idx, (const float*)nullptr);
 }

@@ -297,6 +297,7 @@ class TrainStep:
         c4 = self.chan[4]
         self.gap = e(B, c4)
         self.dgap = e(B, c4)
+        self.route = e(2, B, c4)                # block 4's pool routing summary (BatchNorm backward in one pass)
         self.z = e(B, self.feat)
         self.dz = e(B, self.feat)
         self.logits = e(B, self.nl)
@@ -446,11 +447,18 @@ class TrainStep:
             if self.sync_bn:
                 stat, nparts, nrep = self._bn_exchange(l, 0, self.statp[l], self.nstat[l], st), self.world, self.world
                 n += 1
-            self._k("bn_relu_pool", lib.ecgb200_bn_relu_pool_fwd_train_bf16, _p(self.ybuf[l]), _p(stat),
-                    nparts, Pp(k + "1.weight"), Pp(k + "1.bias"), bn.running_mean.data_ptr(),
-                    bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(), _p(self.bnst[l]),
-                    _p(self.acts[l + 1]) if l < 3 else None, _p(self.gap) if l == 3 else None, B, co, L,
-                    float(bn.momentum), float(bn.eps), nrep, st)
+            if l == 3 and not self.sync_bn:
+                # last block: also the routing summary that lets its BatchNorm backward skip the reduce pass over y
+                self._k("bn_relu_pool", lib.ecgb200_bn_relu_pool_fwd_train_route_bf16, _p(self.ybuf[l]), _p(stat),
+                        nparts, Pp(k + "1.weight"), Pp(k + "1.bias"), bn.running_mean.data_ptr(),
+                        bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(), _p(self.bnst[l]), None,
+                        _p(self.gap), _p(self.route), B, co, L, float(bn.momentum), float(bn.eps), nrep, st)
+            else:
+                self._k("bn_relu_pool", lib.ecgb200_bn_relu_pool_fwd_train_bf16, _p(self.ybuf[l]), _p(stat),
+                        nparts, Pp(k + "1.weight"), Pp(k + "1.bias"), bn.running_mean.data_ptr(),
+                        bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(), _p(self.bnst[l]),
+                        _p(self.acts[l + 1]) if l < 3 else None, _p(self.gap) if l == 3 else None, B, co, L,
+                        float(bn.momentum), float(bn.eps), nrep, st)
             n += 2
         return n
 
@@ -505,6 +513,11 @@ class TrainStep:
                         _p(merged), self.world, self.rank, self.world, _p(dy), Gp(k + "1.weight"), Gp(k + "1.bias"),
                         _p(self.dbpart[l]), B, co, L, 1, st)
                 n += 3
+            elif l == 3:
+                # one pass: the batch reductions come from the forward pass's routing summary (GAP gradient)
+                self._k("bn_bwd", lib.ecgb200_bn_relu_pool_bwd_route_bf16, _p(self.ybuf[l]), _p(self.bnst[l]), dgap,
+                        _p(self.route), _p(dy), Gp(k + "1.weight"), Gp(k + "1.bias"), _p(self.dbpart[l]), B, co, L, 1, st)
+                n += 1
             else:
                 self._k("bn_bwd", lib.ecgb200_bn_relu_pool_bwd_bf16, _p(self.ybuf[l]), _p(self.bnst[l]), dpb, dgap, _p(dy),
                         Gp(k + "1.weight"), Gp(k + "1.bias"), _p(self.dbpart[l]), _p(self.ws2), B, co, L, 1, st)

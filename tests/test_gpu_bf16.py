@@ -413,3 +413,51 @@ def test_fused_multimodal_head(B):
     for (w, b), (kw, kb) in zip(zip(dw, db), (("wp", "bp"), ("wh", "bh"), ("wf", "bf"), ("w2", "b2"), ("w0", "b0"))):
         assert rel_inf(w, L[kw].grad) < tol, kw
         assert rel_inf(b, L[kb].grad) < tol, kb
+
+
+@pytest.mark.parametrize("B,C,L", [(5, 256, 125), (2, 128, 31), (256, 256, 125), (64, 256, 625), (3, 64, 250)])
+def test_last_block_bn_backward_in_one_pass_from_the_routing_summary(B, C, L):
+    """Block 4 (pooled output -> time average): the forward pass leaves per (window, channel) the number of routed pool pairs
+    and the sum of the raw conv outputs at the routed positions; the backward pass forms its two batch reductions from
+    dgap * route and reads y once.  Against autograd (small shapes) and against the two-pass kernels (all shapes)."""
+    y = (gen(B, C, L, seed=5) * 1.7 + 0.3).to(BF).float().requires_grad_(True)
+    gamma = (1 + 0.2 * gen(C, seed=6)).requires_grad_(True)
+    beta = (0.1 * gen(C, seed=7)).requires_grad_(True)
+    yb = to_blocked(y.detach()).to(DEV)
+    gg, bg = gamma.detach().to(DEV), beta.detach().to(DEV)
+    yy = y.detach().double()
+    part = torch.stack([yy.sum((0, 2)), (yy * yy).sum((0, 2))]).float().reshape(1, 2, C).to(DEV)
+    st = torch.empty(4, C, device=DEV)
+    gap = torch.empty(B, C, device=DEV)
+    route = torch.full((2, B, C), float("nan"), device=DEV)
+    check(lib.ecgb200_bn_relu_pool_fwd_train_route_bf16(ptr(yb), ptr(part), 1, ptr(gg), ptr(bg), None, None, None, ptr(st), None,
+                                                        ptr(gap), ptr(route), B, C, L, 0.1, 1e-5, 1, stream()), "fwd_route")
+    dout = gen(B, C, seed=10)
+    dgap = dout.to(DEV)
+    ws = torch.empty(lib.ecgb200_bn_bwd_ws_bytes(B, C), dtype=torch.uint8, device=DEV)
+    ns = lib.ecgb200_bn_nsplit(B, C)
+    res = []
+    for one_pass in (False, True):
+        dyb = torch.empty(B, C // 8, L, 8, dtype=BF, device=DEV)
+        dgm, dbt = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+        dbp = torch.empty(C, ns, device=DEV)
+        if one_pass:
+            check(lib.ecgb200_bn_relu_pool_bwd_route_bf16(ptr(yb), ptr(st), ptr(dgap), ptr(route), ptr(dyb), ptr(dgm), ptr(dbt),
+                                                          ptr(dbp), B, C, L, 1, stream()), "bwd_route")
+        else:
+            check(lib.ecgb200_bn_relu_pool_bwd_bf16(ptr(yb), ptr(st), None, ptr(dgap), ptr(dyb), ptr(dgm), ptr(dbt), ptr(dbp),
+                                                    ptr(ws), B, C, L, 1, stream()), "bwd")
+        torch.cuda.synchronize()
+        res.append((from_blocked(dyb.cpu(), C), dgm.cpu(), dbt.cpu(), dbp.sum(1).cpu()))
+    (dy2, dg2, db2, s2), (dy1, dg1, db1, s1) = res
+    cnt = route[0].cpu()
+    assert float(cnt.min()) >= 0 and float(cnt.max()) <= L // 2 and torch.equal(cnt, cnt.round())
+    assert rel_inf(dg1, dg2) < 1e-5 and rel_inf(db1, db2) < 1e-5
+    assert rel_inf(dy1, dy2) < 8e-3                                   # the same values up to one bf16 rounding
+    assert (dy1 != dy2).float().mean().item() < 0.02
+    if B <= 8:
+        p_ref, out_ref, _, _, _ = None, None, None, None, None
+        h = F.batch_norm(y, torch.zeros(C), torch.ones(C), gamma, beta, training=True, momentum=0.1, eps=1e-5)
+        F.max_pool1d(F.relu(h), 2).mean(dim=2).backward(dout)
+        assert rel_inf(dg1, gamma.grad) < 1e-4 and rel_inf(db1, beta.grad) < 1e-4
+        assert rel_inf(dy1, y.grad) < 6e-3
