@@ -331,6 +331,7 @@ class TrainStep:
         del big
         self.side = torch.cuda.Stream(device=dev) if (self.world > 1 or self.bf16) else None
         self.linear = False
+        self.split_adamw = True                 # one GPU: optimizer for everything but block 1 beside wgrad_1 (A/B switch)
         self.comm = torch.cuda.Stream(device=dev) if (self.world > 1 and self.bf16) else None
 
     # ------------------------------------------------------------------ the kernel sequence
@@ -561,7 +562,35 @@ class TrainStep:
             n += 2
             if l == 3:
                 ev_wg4 = wg_done[l & 1]
+            if l == 0 and self._adamw_split():
+                # One GPU: every gradient but conv 1's is final once wgrad_2 and bn_bwd_1 are.  The optimizer takes
+                # [n1, total) on the main stream now, beside wgrad_1 -- a thin tensor kernel that leaves the memory system
+                # idle -- and only block 1's 5.9 k parameters after it (beside bn_bwd_1 instead, the 20 MB AdamW pass slowed
+                # that kernel on the critical path: 0.403 -> 0.412 ms).
+                n1 = self._block1_span()
+                main.wait_event(wg_done[1])                    # wgrad_2 (and everything before it on that stream)
+                self._prof_tag = ""
+                self._k("adamw_rest", lib.ecgb200_adamw_flat_f32, self.P.data_ptr() + 4 * n1, self.G.data_ptr() + 4 * n1,
+                        self.M.data_ptr() + 4 * n1, self.V.data_ptr() + 4 * n1, self.total_pad - n1, self.hyper.data_ptr(),
+                        self.step_dev.data_ptr(), st)
+                n += 1
         return n
+
+    def _block1_span(self):
+        """Length of the flat-buffer prefix that holds exactly block 1's parameters (0 if they are not a 16-byte aligned prefix)."""
+        pre = ("ecg_backbone." if self.mm else "") + "backbone.0."
+        segs = sorted(self.seg.values(), key=lambda s: s.off)
+        n1 = 0
+        for s in segs:
+            if s.name.startswith(pre):
+                if s.off != n1:
+                    return 0
+                n1 = s.off + s.n
+        return n1 if n1 % 4 == 0 and all(s.off >= n1 or s.name.startswith(pre) for s in segs) else 0
+
+    def _adamw_split(self):
+        return (self.split_adamw and self.bf16 and self.world == 1 and not self.linear and not self.sync_bn
+                and self._block1_span() > 0)
 
     def _dp_exchange(self, which, st):
         """Bucket `which` (0 = block 4, 1 = the rest): reduce-scatter + AdamW on the owned shard + all-gather, one
@@ -710,6 +739,9 @@ class TrainStep:
                 ev4 = torch.cuda.Event()
                 ev4.record(self.comm)
                 main.wait_event(ev4)                            # join the bucket-A exchange
+            elif self._adamw_split():
+                self._k("adamw", lib.ecgb200_adamw_flat_f32, self.P.data_ptr(), self.G.data_ptr(), self.M.data_ptr(),
+                        self.V.data_ptr(), self._block1_span(), self.hyper.data_ptr(), self.step_dev.data_ptr(), st)
             else:
                 self._k("adamw", lib.ecgb200_adamw_flat_f32, self.P.data_ptr(), self.G.data_ptr(), self.M.data_ptr(),
                         self.V.data_ptr(), self.total_pad, self.hyper.data_ptr(), self.step_dev.data_ptr(), st)
