@@ -370,6 +370,9 @@ def layers_table(prof, B, chan, Ls, n_params, T, pk, dtype_bytes):
     """Every C-ABI call of the step: measured us (timed alone, warm), its roofline time from the per-layer model
     (max of bytes / HBM peak and FLOPs / sustained tensor peak -- BASELINE.md section 4) and the fraction."""
     rows = []
+    # the optimizer of the one-GPU engine is two launches (everything but block 1 beside wgrad_1, block 1 after it): one row
+    rest = sum(t for n, t in prof if n == "adamw_rest")
+    prof = [(n, t + rest if n == "adamw" else t) for n, t in prof if n != "adamw_rest"]
     for name, t_ms in prof:
         km = kernel_model(name, B, chan, Ls, n_params, T, dtype_bytes)
         row = {"call": name, "us": round(t_ms * 1e3, 2), "model_us": None, "frac": None, "bound": None}

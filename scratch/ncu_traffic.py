@@ -27,7 +27,7 @@ def g(r, k, scaled=False):
 SEQ = {"wfdb16_zscore_pack_kernel": ["decode"], "conv_tc_kernel<0>": ["conv_fwd_L1", "conv_fwd_L2"],
        "conv_tc_pair_kernel<0>": ["conv_fwd_L3", "conv_fwd_L4"],
        "bn_fwd_train_bf16_kernel": [f"bn_relu_pool_L{l}" for l in (1, 2, 3, 4)], "head_fwd_bwd_kernel": ["head_fwd_bwd"],
-       "bn_bwd_reduce_bf16_kernel": [f"bn_bwd_L{l}" for l in (4, 3, 2, 1)], "bn_bwd_apply_bf16_kernel": [f"bn_bwd_L{l}" for l in (4, 3, 2, 1)],
+       "bn_bwd_reduce_bf16_kernel": [f"bn_bwd_L{l}" for l in (3, 2, 1)], "bn_bwd_apply_bf16_kernel": [f"bn_bwd_L{l}" for l in (4, 3, 2, 1)],
        "conv_tc_pair_kernel<3>": ["dgrad_L4", "dgrad_L3"], "conv_tc_kernel<3>": ["dgrad_L2"],
        "wgrad_pair_kernel": ["wgrad_L4", "wgrad_L3"],
        "wgrad_thin_kernel": ["wgrad_L2", "wgrad_L1"], "wgrad_tc_reduce_kernel": [f"wgrad_L{l}" for l in (4, 3, 2, 1)]}
