@@ -175,3 +175,31 @@ def test_committed_bench_lines_follow_the_driver_contract():
         r = json.loads(fh.read().strip().splitlines()[-1])
     assert r["impl"] == "reference" and r["e2e"]["h2d_bytes_per_step"] == 0 and r["cpu_baseline"]["kind"] == "port"
     assert set(r["config"]) <= set(head["config"])          # the two arms name the workload with the same keys
+
+
+def test_pair_kernel_selection_rules_on_the_host():
+    """conv_pair_cfg / wgrad_pair_cfg run on the host (148 SMs assumed without a device): which shapes of the network take the
+    CTA-pair kernels.  A pair grid is even and never larger than the SM count; small problems stay with the one-SM kernels."""
+    from ptbxl_multimodal_b200._lib import lib
+    try:
+        def parts(mask, *shape):
+            lib.ecgb200_debug_set_conv_pair(mask)
+            return lib.ecgb200_conv1d_stat_parts_bf16(*shape)
+        # benchmark batch: blocks 3 / 4 forward (B, Ci, Co, L) as pairs; their grids are even
+        for shape in [(256, 64, 128, 250), (256, 128, 256, 125), (256, 256, 128, 125), (256, 128, 64, 250)]:
+            p = parts(3, *shape)
+            assert p % 2 == 0 and 0 < p <= 148, (shape, p)
+        # stem layers (weights fit in shared memory) and one-tile-per-SM batches: the same grid with and without the switch
+        for shape in [(256, 16, 32, 1000), (256, 32, 64, 500), (256, 64, 32, 500), (64, 128, 256, 125), (64, 64, 128, 250)]:
+            assert parts(3, *shape) == parts(0, *shape), shape
+        # the 256 -> 128 channel dgrad with two input buffers (multi-round) keeps the one-SM kernel: its ring would be too short
+        assert parts(3, 1024, 256, 128, 125) == parts(0, 1024, 256, 128, 125)
+        assert parts(3, 1024, 128, 256, 125) % 2 == 0
+        # forced (tests): pairs wherever the kernel can run
+        assert parts(7, 64, 128, 256, 125) % 2 == 0 and parts(7, 64, 128, 256, 125) <= 148
+        # the split-K workspace never shrinks below what either weight-gradient kernel needs
+        for mask in (0, 3, 7):
+            lib.ecgb200_debug_set_conv_pair(mask)
+            assert lib.ecgb200_conv1d_wgrad_bf16_ws_bytes(256, 128, 256, 125) >= 18 * 256 * 128 * 16 * 4
+    finally:
+        lib.ecgb200_debug_set_conv_pair(3)
