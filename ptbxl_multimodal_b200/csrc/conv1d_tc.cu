@@ -774,12 +774,13 @@ template <int MODE>
 static int conv_tc_launch(const void* xb, const void* wprep, const float* bias, const float* shift, void* yb,
                           float* stat_part, int B, int Ci, int Co, int L, void* stream, int Cn = 0) {
     if (Ci <= 0 || (Ci & 15) || Ci > 384 || (Ci > 64 && (Ci & 63)) || Co <= 0 || (Co & 31) || Co > 256) return ECGB200_EUNSUPPORTED;
-    if constexpr (MODE == 0 || MODE == 3) {
-        // streamed-weight layers (blocks 3 and 4, forward and dgrad): the two-SM kernel
+    if constexpr (MODE == 0 || MODE == 3 || MODE == 1 || MODE == 2) {
+        // streamed-weight layers (blocks 3 and 4: training forward, dgrad, inference): the two-SM kernel
         Conv2Cfg PP;
         size_t smem2;
         const int gp = conv_pair_cfg(B, Ci, Co, L, &PP, &smem2);
-        if (gp > 0) return conv_tc_pair_launch<MODE>(xb, wprep, bias, yb, stat_part, B, Ci, Co, L, PP, gp, smem2, stream);
+        if (gp > 0)
+            return conv_tc_pair_launch<MODE>(xb, wprep, bias, shift, yb, stat_part, B, Ci, Co, L, PP, gp, smem2, stream);
     }
     // Input tiles: one 4-D box of 16-byte rows per tile for the 16-channel stem (the copy engine moves ~one 16-byte row per
     // cycle); from 32 input channels on, two wide-row boxes per 8-channel chunk, issued by the eight epilogue threads in

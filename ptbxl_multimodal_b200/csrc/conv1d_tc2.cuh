@@ -16,7 +16,9 @@
 //                   (accfull of group g also tells the epilogue warps that input buffer g % 2 may be refilled: they issue
 //                   the input-tile loads, eight threads in parallel -- a single thread manages one TMA instruction per ~50 cycles)
 //   accempty        leader's copy, 16 arrivals: the eight epilogue warps of each CTA (mbarrier.arrive on the mapa'd address)
-// MODE 0: training forward (+ BatchNorm partial statistics, one partial per CTA); MODE 3: dgrad / plain conv.
+// MODE 0: training forward (+ BatchNorm partial statistics, one partial per CTA); MODE 3: dgrad / plain conv;
+// MODE 1 / 2: inference blocks (folded BatchNorm + ReLU + MaxPool in the epilogue; 2 = last block, time sums only) -- the
+// epilogues of conv_tc_kernel.
 #pragma once
 
 constexpr int C2P_MAXST = 16;       // weight ring depth (max): half slabs are small, the ring has to cover the L2 latency
@@ -65,13 +67,13 @@ template <int MODE>
 __global__ void __launch_bounds__(C2_THREADS, 1)
 conv_tc_pair_kernel(const __grid_constant__ CUtensorMap xmapA, const __grid_constant__ CUtensorMap xmapB,
                     const __grid_constant__ CUtensorMap wmap, const float* __restrict__ bias,
-                    __nv_bfloat16* __restrict__ y, float* __restrict__ stat_part, const Conv2Cfg P) {
+                    const float* __restrict__ shift, __nv_bfloat16* __restrict__ y, float* __restrict__ stat_part,
+                    const Conv2Cfg P) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* wfull = reinterpret_cast<uint64_t*>(smem);           // [C2P_MAXST]
     uint64_t* wempty = wfull + C2P_MAXST;                           // [C2P_MAXST]
     uint64_t* xfull = wempty + C2P_MAXST;                           // [2]
-    uint64_t* xempty = xfull + 2;                                   // [2]
-    uint64_t* accfull = xempty + 2;                                 // [2]
+    uint64_t* accfull = xfull + 2;                                  // [2]
     uint64_t* accempty = accfull + 2;                               // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + 2);
     float* statsh = reinterpret_cast<float*>(smem + TC_HDR);        // [4][2][256]
@@ -95,7 +97,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap xmapA, const __grid_cons
     if (threadIdx.x == 0) {
         for (int i = 0; i < C2P_MAXST; ++i) { tc::mbar_init(wfull + i, 1); tc::mbar_init(wempty + i, 1); }
         for (int i = 0; i < 2; ++i) {
-            tc::mbar_init(xfull + i, 1); tc::mbar_init(xempty + i, 1);
+            tc::mbar_init(xfull + i, 1);
             tc::mbar_init(accfull + i, 1); tc::mbar_init(accempty + i, 16);
         }
         tc::fence_barrier_init();
@@ -246,6 +248,11 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap xmapA, const __grid_cons
                     float bv[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) bv[i] = bias != nullptr ? __ldg(bias + c0 + i) : 0.f;
+                    float sh[(MODE == 1 || MODE == 2) ? 32 : 1];
+                    if constexpr (MODE == 1 || MODE == 2) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) sh[i] = __ldg(shift + c0 + i);
+                    }
                     for (int r = 0; r < rcount; ++r) {
                         if (nblk == 1 && (r & 1) != half) continue;
                         const int tile = tile0 + r;
@@ -256,6 +263,49 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap xmapA, const __grid_cons
                         float v[32];
                         tc::tmem_ld32(taddr, v);
                         tc::tmem_ld_wait();
+                        if constexpr (MODE == 1 || MODE == 2) {
+                            // inference (see conv_tc_kernel): relu(scale * conv + shift) (`bias` = scale), max over the pool pair
+                            // (lanes 2p, 2p+1): the even lane keeps channels 0-15 of the block, the odd lane 16-31
+                            const bool even = (lane & 1) == 0;
+                            const int Lp = L >> 1, tp = t >> 1;
+                            const bool plive = tp < Lp;
+                            float m[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const float a = fmaxf(fmaf(v[i], bv[i], sh[i]), 0.f);
+                                const float c = fmaxf(fmaf(v[16 + i], bv[16 + i], sh[16 + i]), 0.f);
+                                const float send = even ? c : a, keep = even ? a : c;
+                                m[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+                            }
+                            if constexpr (MODE == 1) {
+                                if (plive) {
+                                    __nv_bfloat16* prow = y + ((size_t)b * (Co / 8) * Lp + tp) * 8 +
+                                                          (size_t)(c0 / 8 + (even ? 0 : 2)) * ((size_t)Lp * 8);
+                                    *reinterpret_cast<uint4*>(prow) =
+                                        make_uint4(tc::pack_bf16(m[0], m[1]), tc::pack_bf16(m[2], m[3]),
+                                                   tc::pack_bf16(m[4], m[5]), tc::pack_bf16(m[6], m[7]));
+                                    *reinterpret_cast<uint4*>(prow + (size_t)Lp * 8) =
+                                        make_uint4(tc::pack_bf16(m[8], m[9]), tc::pack_bf16(m[10], m[11]),
+                                                   tc::pack_bf16(m[12], m[13]), tc::pack_bf16(m[14], m[15]));
+                                }
+                            } else {
+                                // sum over the 16 pool pairs of this warp (transposing butterfly over lane bits 4..1):
+                                // lane l ends with channel c0 + 16*(l&1) + (l>>1)
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) m[i] = plive ? m[i] : 0.f;
+#pragma unroll
+                                for (int o = 8; o > 0; o >>= 1) {
+                                    const bool up = (lane & (2 * o)) != 0;
+#pragma unroll
+                                    for (int i = 0; i < o; ++i) {
+                                        const float send = up ? m[i] : m[i + o], keep = up ? m[i + o] : m[i];
+                                        m[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2 * o);
+                                    }
+                                }
+                                stat_part[((size_t)tile * 4 + q) * Co + c0 + 16 * (lane & 1) + (lane >> 1)] = m[0];
+                            }
+                            continue;
+                        }
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             uint32_t pk[4];
@@ -369,8 +419,9 @@ static int conv_pair_cfg(int B, int Ci, int Co, int L, Conv2Cfg* P, size_t* smem
 }
 
 template <int MODE>
-static int conv_tc_pair_launch(const void* xb, const void* wprep, const float* bias, void* yb, float* stat_part,
-                               int B, int Ci, int Co, int L, const Conv2Cfg& P, int grid, size_t smem, void* stream) {
+static int conv_tc_pair_launch(const void* xb, const void* wprep, const float* bias, const float* shift, void* yb,
+                               float* stat_part, int B, int Ci, int Co, int L, const Conv2Cfg& P, int grid, size_t smem,
+                               void* stream) {
     CUtensorMap xmapA, xmapB, wmap;
     int rc = ecg_make_act_tmap64(&xmapA, xb, B, Ci, L, 128, 1);
     if (rc) return rc;
@@ -388,6 +439,6 @@ static int conv_tc_pair_launch(const void* xb, const void* wprep, const float* b
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, conv_tc_pair_kernel<MODE>, xmapA, xmapB, wmap, bias, (__nv_bfloat16*)yb, stat_part, P);
+    e = cudaLaunchKernelEx(&cfg, conv_tc_pair_kernel<MODE>, xmapA, xmapB, wmap, bias, shift, (__nv_bfloat16*)yb, stat_part, P);
     return e == cudaSuccess ? ecg_launch_status() : (int)e;
 }

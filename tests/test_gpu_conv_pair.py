@@ -129,3 +129,34 @@ def test_pair_wgrad_equals_one_sm_wgrad(B, Ci, Co, L):
         w = torch.zeros(Co, Ci, 15, requires_grad=True)
         F.conv1d(x.to(BF).float(), w, None, padding=7).backward(dy.to(BF).float())
         assert float((dw1 - w.grad).abs().max() / w.grad.abs().max()) < 2e-3
+
+
+@pytest.mark.parametrize("B,Ci,Co,L", [(256, 64, 128, 250), (256, 128, 256, 125), (77, 128, 256, 125), (3, 64, 128, 250),
+                                       (512, 64, 128, 1250)])
+@pytest.mark.parametrize("last", [False, True])
+def test_pair_inference_blocks_equal_one_sm(B, Ci, Co, L, last):
+    """Inference blocks (folded BatchNorm + ReLU + MaxPool in the conv epilogue; last block: time sums only) on the pair kernel:
+    bit-identical to the one-SM kernel (forced on the small shapes)."""
+    x = gen(B, Ci, L, seed=2)
+    w = gen(Co, Ci, 15, seed=3, scale=0.05)
+    scale = (1 + 0.2 * gen(Co, seed=4)).to(DEV)
+    shift = (0.1 * gen(Co, seed=5)).to(DEV)
+    xb = to_blocked(x).to(DEV)
+    wf = torch.empty(15, Ci // 8, Co, 8, dtype=BF, device=DEV)
+    wd = torch.empty(15, Co // 8, Ci, 8, dtype=BF, device=DEV)
+    check(lib.ecgb200_conv1d_prep_weights_bf16(ptr(w.to(DEV)), ptr(wf), ptr(wd), Co, Ci, stream()), "prep")
+    tiles = B * ((L + 127) // 128)
+    out = []
+    for mask in (0, 7):
+        lib.ecgb200_debug_set_conv_pair(mask)
+        try:
+            pb = None if last else torch.full((B, Co // 8, L // 2, 8), float("nan"), dtype=BF, device=DEV)
+            gp = torch.full((tiles, 4, Co), float("nan"), device=DEV) if last else None
+            check(lib.ecgb200_conv1d_bn_relu_pool_infer_bf16(ptr(xb), ptr(wf), ptr(scale), ptr(shift), ptr(pb) if pb is not None else None,
+                                                             ptr(gp) if gp is not None else None, B, Ci, Co, L, stream()), "infer")
+            torch.cuda.synchronize()
+            out.append(gp if last else pb)
+        finally:
+            lib.ecgb200_debug_set_conv_pair(3)
+    assert not torch.isnan(out[1].float()).any()
+    assert torch.equal(out[0], out[1])
