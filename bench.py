@@ -26,6 +26,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("TQDM_DISABLE", "1")      # the reference's loops wrap their loader in tqdm: bars off (read at tqdm import)
 
 UNIT = "samples/s"
 
@@ -85,12 +86,18 @@ def resolve(args, world):
     return w
 
 
-def workload_config(w, world, precision, extra=None):
-    """The `config` object -- SAME keys in the b200 and the reference arm."""
-    c = {"workload": f"{w['tag']}: {w['desc']}", "batch_per_gpu": w["per_gpu"], "global_batch": w["global_batch"],
-         "seq_len": w["T"], "parallelism": f"dp{world}", "precision": precision}
-    c.update(extra or {})
-    return c
+def workload_config(w, world, precision):
+    """The `config` object: names the workload and nothing else, so it is IDENTICAL (keys and values) in the b200 and
+    the reference arm of the same command line.  How a run was timed goes under the line's `method` key."""
+    if w["kind"] == "cam":
+        l2 = f"{w['per_gpu'] * 12 * w['T'] * 4 / 1e6:.0f} MB of windows per rank > 126 MB L2"
+    else:
+        rank_mb = w["per_gpu"] * w["T"] / 1000.0           # activations + gradients of one step: ~1 MB per 12x1000 window
+        l2 = (f"step working set ~{rank_mb:.0f} MB per rank (~1 MB per 12x1000 window) "
+              + ("> 126 MB L2" if rank_mb > 126 else "<= 126 MB L2, not flushed (a step rewrites every buffer it reads)")
+              + "; inputs alternate between the engine's resident input slots")
+    return {"workload": f"{w['tag']}: {w['desc']}", "batch_per_gpu": w["per_gpu"], "global_batch": w["global_batch"],
+            "seq_len": w["T"], "parallelism": f"dp{world}", "precision": precision, "l2": l2}
 
 
 def peaks():
@@ -169,36 +176,88 @@ def synth(w, B, seed):
 
 
 # --------------------------------------------------------------------------- CPU reference arm
+class _Batches:
+    """Stands in for the DataLoader the reference's loops iterate: pre-collated synthetic batches (the Dataset /
+    WFDB reading side is outside the metric), `len(loader.dataset)` as loop.py:38 reads it."""
+
+    def __init__(self, batches):
+        self.batches = batches
+        self.dataset = range(sum(int(b[0].size(0)) for b in batches))
+
+    def __iter__(self):
+        return iter(self.batches)
+
+    def __len__(self):
+        return len(self.batches)
+
+
+def reference_runner(w, x, y, demo):
+    """One step of the path through the UNMODIFIED reference (oracle/_ref, staged by oracle/make_ref.py): the
+    reference's own modules, loop functions and torch.optim.AdamW on the host CPU.  None when oracle/_ref is absent."""
+    import torch
+    from oracle import make_ref
+    R = make_ref.load()
+    if R is None:
+        return None
+    dev = torch.device("cpu")
+    torch.manual_seed(42)
+    if w["kind"] == "cam":
+        model = R.ecg_cnn.ECGCNN(12, 256, 5).eval()
+        cam = R.grad_cam_1d.GradCAM1D(model, model.backbone[-1].net[0])
+        return lambda xi, c: cam.generate_cam(xi, c, signal_length=w["T"])
+    if w["kind"] == "mm":
+        model = R.ecg_multimodal.ECGMultimodal(num_labels=w["nl"])
+        opt = torch.optim.AdamW(model.parameters(), lr=w["lr"], weight_decay=w["wd"])
+        return lambda xb, yb, db: R.loop_demo.train_one_epoch_demo(model, _Batches([(xb, db, yb)]), opt, dev)
+    model = R.ecg_cnn.ECGCNN(12, 256, w["nl"])
+    opt = torch.optim.AdamW(model.parameters(), lr=w["lr"], weight_decay=w["wd"])
+    return lambda xb, yb, db: R.loop.train_one_epoch(model, _Batches([(xb, yb)]), opt, dev)
+
+
 def cpu_steps(w, batch: int, steps: int, warmup: int, budget_s: float):
-    """Reference CPU implementation of the path (oracle port of the reference modules: same ATen ops, fp32) on all
-    host cores, on a bounded sample of the workload.  Returns (samples/s, batch used, steps timed, seconds, what)."""
+    """Reference CPU implementation of the path on all host cores, on a bounded sample of the workload: the
+    unmodified reference modules + loops from oracle/_ref when staged (kind "reference"), else the oracle port of
+    them (same ATen ops, fp32, bit-identical: tests/test_reference_arm.py; kind "port").
+    Returns (samples/s, batch used, steps timed, seconds, what, kind)."""
+    import warnings
     import torch
     from oracle import ecg_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     if w["kind"] == "cam":
         # the reference's Grad-CAM: one forward + one full backward per (window, class) (grad_cam_1d.py:53-103)
-        sd = O.init_state_dict("cnn", 5, seed=42)
         x, _, _ = synth(w, 64, 0)
-        O.gradcam_v1(sd, x[:1], 0, w["T"])
-        t0 = time.perf_counter()
-        done = 0
-        for i in range(64):
-            for c in range(5):
-                O.gradcam_v1(sd, x[i:i + 1], c, w["T"])
-            done += 1
-            if time.perf_counter() - t0 > budget_s:
-                break
+        ref = reference_runner(w, x, None, None)
+        kind = "reference" if ref is not None else "port"
+        if ref is None:
+            sd = O.init_state_dict("cnn", 5, seed=42)
+            ref = lambda xi, c: O.gradcam_v1(sd, xi, c, w["T"])      # noqa: E731
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")                   # register_backward_hook deprecation (grad_cam_1d.py:36)
+            ref(x[:1], 0)
+            t0 = time.perf_counter()
+            done = 0
+            for i in range(64):
+                for c in range(5):
+                    ref(x[i:i + 1], c)
+                done += 1
+                if time.perf_counter() - t0 > budget_s:
+                    break
         dt = time.perf_counter() - t0
-        return done / dt, 1, done, dt, f"{done} windows x 5 classes, one GradCAM1D-order call per (window, class)"
-    kind = w["kind"]
-    sd = O.init_state_dict(kind, w["nl"], seed=42)
-    st = O.AdamWState(sd, w["lr"], w["wd"])
+        return done / dt, 1, done, dt, f"{done} windows x 5 classes, one GradCAM1D.generate_cam call per (window, class)", kind
     b = batch
     x, y, demo = synth(w, b, 0)
-    run = lambda: O.train_step(sd, x, y, st, demo=demo)      # noqa: E731
-    run()                                                      # cold (thread pool, allocator): not representative
+    ref = reference_runner(w, x, y, demo)
+    if ref is not None:
+        kind = "reference"
+        step = lambda: ref(x, y, demo)                               # noqa: E731
+    else:
+        kind = "port"
+        sd = O.init_state_dict(w["kind"], w["nl"], seed=42)
+        st = O.AdamWState(sd, w["lr"], w["wd"])
+        step = lambda: O.train_step(sd, x, y, st, demo=demo)         # noqa: E731
+    step()                                                     # cold (thread pool, allocator): not representative
     t0 = time.perf_counter()
-    run()
+    step()
     one = time.perf_counter() - t0
     while b > 8 and one * (b / batch) * (steps + warmup) > budget_s:       # bound the per-step sample
         b //= 2
@@ -206,16 +265,19 @@ def cpu_steps(w, batch: int, steps: int, warmup: int, budget_s: float):
         x, y = x[:b].contiguous(), y[:b].contiguous()
         demo = demo[:b].contiguous() if demo is not None else None
     for _ in range(max(0, warmup - 2)):
-        run()
+        step()
     t0 = time.perf_counter()
     done = 0
     for _ in range(steps):
-        run()
+        step()
         done += 1
         if time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
-    return done * b / dt, b, done, dt, f"{done} train steps of batch {b} x 12 x {w['T']}"
+    return done * b / dt, b, done, dt, f"{done} train steps of batch {b} x 12 x {w['T']}", kind
+
+
+CPU_KIND_TEXT = {"reference": "unmodified reference modules + loop (oracle/_ref)", "port": "oracle port of the reference modules"}
 
 
 def run_reference(args):
@@ -226,15 +288,15 @@ def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     w = resolve(args, world)
     steps = args.steps if args.steps is not None else 20
-    val, b, done, dt, what = cpu_steps(w, w["per_gpu"], steps, args.warmup, budget_s=150.0)
+    val, b, done, dt, what, kind = cpu_steps(w, w["per_gpu"], steps, args.warmup, budget_s=150.0)
     cores = torch.get_num_threads()
-    sample = f"{what} (oracle port of the reference modules, fp32, {cores} host threads, {dt:.1f} s)"
+    sample = f"{what} ({CPU_KIND_TEXT[kind]}, fp32, {cores} host threads, {dt:.1f} s)"
     line = {
         "impl": "reference", "metric": w["metric"], "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
         "warmup": args.warmup, "ms_per_step": 1000.0 * dt / max(done, 1), "higher_is_better": True,
         "scaling": w["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(w, world, "bf16" if args.precision == "auto" else args.precision),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -632,9 +694,9 @@ def run_train(args, w, world, rank, local, dev, dist):
 
     # ---- CPU baseline beside the GPU number (rank 0, N == 1 only; bounded sample)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, b, done, dt, what = cpu_steps(w, B, steps=80, warmup=2, budget_s=15.0)
-        extra["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                                 "sample": f"{what}, oracle port of the reference modules on the host CPU, fp32, {dt:.1f} s"}
+        v, b, done, dt, what, kind = cpu_steps(w, B, steps=80, warmup=2, budget_s=15.0)
+        extra["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+                                 "sample": f"{what}, {CPU_KIND_TEXT[kind]} on the host CPU, fp32, {dt:.1f} s"}
 
     if rank != 0:
         return None, eng
@@ -642,13 +704,13 @@ def run_train(args, w, world, rank, local, dev, dist):
         "metric": w["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None,
         "dtype": "f32" if precision == "fp32" else "bf16", "data": "synthetic",
-        "config": workload_config(w, world, precision, {
-            "l2": "step working set (~1 MB per window) > 126 MB L2; inputs alternate between the engine's two resident input slots",
+        "config": workload_config(w, world, precision),
+        "method": {
             "repeats": R, "timing": f"median of {R} timed regions of {K} steps each (CUDA events, max over ranks)",
             "e2e_input": "int16 WFDB frames, decoded + z-scored + packed on the device" if raw else "fp32 windows",
             "input_slots": NS,
             "grad_exchange": ("fused peer-memory reduce-scatter + AdamW + all-gather kernels (block-4 bucket under backward)" if eng.dp_fused
-                              else ("nccl all-reduce" if world > 1 else "none"))}),
+                              else ("nccl all-reduce" if world > 1 else "none"))},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / K, "last_loss": last_loss, "repeats_ms": [round(r / K, 5) for r in e2e_runs]},
@@ -745,15 +807,16 @@ def run_cam(args, w, world, rank, local, dev, dist):
         except Exception as e:
             extra["gpu_reference"] = {"best": None, "error": repr(e)[:300]}
     if world == 1 and not args.no_cpu_baseline:
-        v, b, done, dt, what = cpu_steps(w, 1, steps=1, warmup=0, budget_s=15.0)
-        extra["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                                 "sample": f"{what}, oracle port on the host CPU, fp32, {dt:.1f} s"}
+        v, b, done, dt, what, kind = cpu_steps(w, 1, steps=1, warmup=0, budget_s=15.0)
+        extra["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+                                 "sample": f"{what}, {CPU_KIND_TEXT[kind]} on the host CPU, fp32, {dt:.1f} s"}
     line = {
         "metric": w["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": workload_config(w, world, "bf16", {"chunk": chunk, "repeats": R,
-                                                      "l2": f"{N * 12 * T * 4 / 1e6:.0f} MB of windows per rank > 126 MB L2"}),
+        "config": workload_config(w, world, "bf16"),
+        "method": {"chunk": chunk, "repeats": R,
+                   "timing": f"median of {R} timed regions of {K} passes each (CUDA events, max over ranks)"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N * 12 * T * 4, "d2h_bytes_per_step": N * 5 * 4,
                 "ms_per_step": ms_e2e / K},

@@ -1,0 +1,144 @@
+"""The reference arm of bench.py: oracle/_ref (the unmodified reference files, staged by oracle/make_ref.py) runs the
+path through the reference's OWN loop functions, and the oracle port used everywhere else as the checker is
+bit-identical to it -- same loss, same post-AdamW parameters, same running statistics, same CAMs (CPU, fp32).
+
+oracle/_ref is git-ignored; it is staged by `__graft_entry__.build()` whenever /root/reference is present.  Where neither
+exists (a checkout without the reference) these tests skip: the committed golden vectors (tests/test_oracle_golden.py)
+pin the port independently."""
+import json
+import os
+import subprocess
+import sys
+import warnings
+
+import pytest
+import torch
+
+from conftest import ROOT
+from oracle import ecg_oracle as O
+from oracle import make_ref
+
+
+@pytest.fixture(scope="module")
+def ref():
+    make_ref.build()                       # no-op without /root/reference
+    R = make_ref.load()
+    if R is None:
+        pytest.skip("oracle/_ref not staged and /root/reference absent")
+    os.environ.setdefault("TQDM_DISABLE", "1")
+    return R
+
+
+def _bench():
+    sys.path.insert(0, ROOT)
+    import bench
+    return bench
+
+
+def test_staged_files_are_the_reference_byte_for_byte(ref):
+    assert make_ref.verify()
+    for rel in make_ref.FILES:
+        src = os.path.join("/root/reference", rel)
+        if os.path.exists(src):
+            with open(src, "rb") as a, open(os.path.join(make_ref.DEST, rel), "rb") as b:
+                assert a.read() == b.read(), rel
+    # git never sees them
+    out = subprocess.run(["git", "-C", ROOT, "check-ignore", "oracle/_ref/src/models/ecg_cnn.py"], capture_output=True, text=True)
+    assert out.returncode == 0
+    with open(os.path.join(ROOT, ".gpurunignore")) as f:
+        assert "oracle" not in f.read()      # ... but the directory travels to the GPU box
+
+
+def test_reference_train_loop_equals_the_port_bit_for_bit(ref):
+    """train_one_epoch (src/training/loop.py:14-38) over three batches == three O.train_step calls."""
+    bench = _bench()
+    torch.set_num_threads(4)
+    torch.manual_seed(42)
+    model = ref.ecg_cnn.ECGCNN(12, 256, 5)
+    opt = torch.optim.AdamW(model.parameters(), lr=1.5e-3, weight_decay=1e-4)
+    sd = O.init_state_dict("cnn", 5, seed=42)
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, sd[k]), k                       # same initial weights from the same seed
+    st = O.AdamWState(sd, 1.5e-3, 1e-4)
+    batches = [O.synth_batch(8, 1000, 5, seed=s) for s in range(3)]
+    mean_loss = ref.loop.train_one_epoch(model, bench._Batches(batches), opt, torch.device("cpu"))
+    losses = [float(O.train_step(sd, x, y, st)["loss"]) for x, y in batches]
+    assert mean_loss == sum(l * 8 for l in losses) / 24
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+
+
+def test_reference_demo_loop_equals_the_port_bit_for_bit(ref):
+    """train_one_epoch_demo (src/training/loop_demo.py:13-45) on the FiLM model."""
+    bench = _bench()
+    torch.set_num_threads(4)
+    torch.manual_seed(42)
+    model = ref.ecg_multimodal.ECGMultimodal(num_labels=5)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-4)
+    sd = O.init_state_dict("mm", 5, seed=42)
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    st = O.AdamWState(sd, 1e-4, 1e-4)
+    batches = [O.synth_batch(8, 1000, 5, seed=10 + s, with_demo=True) for s in range(2)]
+    mean_loss = ref.loop_demo.train_one_epoch_demo(model, bench._Batches(batches), opt, torch.device("cpu"))
+    losses = [float(O.train_step(sd, x, y, st, demo=d)["loss"]) for x, d, y in batches]
+    assert mean_loss == sum(losses) / 2
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+
+
+def test_reference_gradcam_equals_the_port_bit_for_bit(ref):
+    torch.set_num_threads(4)
+    torch.manual_seed(42)
+    model = ref.ecg_cnn.ECGCNN(12, 256, 5).eval()
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    x, _ = O.synth_batch(2, 1000, 5, seed=3)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        cam = ref.grad_cam_1d.GradCAM1D(model, model.backbone[-1].net[0])
+        for i in range(2):
+            for c in (0, 4):
+                got = cam.generate_cam(x[i:i + 1], c, signal_length=1000)
+                assert torch.equal(got, O.gradcam_v1(sd, x[i:i + 1], c, 1000)), (i, c)
+
+
+def test_bench_reference_arm_line(ref):
+    """`bench.py --impl reference` prints the contract's line, runs the staged reference (kind "reference"), and names the
+    workload with exactly the `config` object the b200 arm of the same command line prints."""
+    bench = _bench()
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--batch", "8", "--steps", "2",
+                          "--warmup", "3"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "reference" and d["steps"] == 2
+    assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+    class A:                                                  # the same command line, parsed for the b200 arm
+        config, batch, seq_len, steps, precision = 1, 8, None, 2, "auto"
+    w = bench.resolve(A, 1)
+    assert d["config"] == bench.workload_config(w, 1, "bf16")
+    assert d["metric"] == w["metric"] == "ECG samples/sec train step (12x1000)"
+
+
+def test_both_arms_build_config_with_one_function():
+    """`config` carries no run-specific extras: both arms call workload_config(w, world, precision) and nothing else, so the
+    driver's same-config check compares equal objects."""
+    import inspect
+    bench = _bench()
+    assert list(inspect.signature(bench.workload_config).parameters) == ["w", "world", "precision"]
+    src = inspect.getsource(bench)
+    assert src.count('"config": workload_config(') == 3       # reference arm, train arm, Grad-CAM arm
+    for n in (1, 2, 8):
+        for cfg in (1, 2, 3, 4):
+            class A:
+                config, batch, seq_len, steps, precision = cfg, None, None, None, "auto"
+            w = bench.resolve(A, n)
+            c = bench.workload_config(w, n, "bf16")
+            assert set(c) == {"workload", "batch_per_gpu", "global_batch", "seq_len", "parallelism", "precision", "l2"}
+            assert c["workload"].startswith(f"configs[{cfg}]") and c["parallelism"] == f"dp{n}"
