@@ -13,6 +13,8 @@ Files staged:
     src/models/ecg_cnn.py, src/models/ecg_multimodal.py           -- the models
     src/training/loop.py, loop_demo.py, metrics.py                -- train_one_epoch[_demo], eval_one_epoch[_demo]
     src/interpretability/grad_cam_1d.py                           -- GradCAM1D
+    scripts/00_demo_inference.py (+ src/utils/seed.py)            -- the one reference script that runs on the shipped demo
+                                                                     data: driven end to end with the model import swapped
 
     python oracle/make_ref.py [--reference /root/reference]
 
@@ -39,6 +41,9 @@ FILES = (
     "src/training/loop_demo.py",
     "src/training/metrics.py",
     "src/interpretability/grad_cam_1d.py",
+    # one runnable caller of the path, for the end-to-end import-swap test (tests/test_gpu_reference_scripts.py):
+    "src/utils/seed.py",
+    "scripts/00_demo_inference.py",
 )
 
 

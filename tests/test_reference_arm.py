@@ -142,3 +142,22 @@ def test_both_arms_build_config_with_one_function():
             c = bench.workload_config(w, n, "bf16")
             assert set(c) == {"workload", "batch_per_gpu", "global_batch", "seq_len", "parallelism", "precision", "l2"}
             assert c["workload"].startswith(f"configs[{cfg}]") and c["parallelism"] == f"dp{n}"
+
+
+def test_demo_script_harness_on_the_unswapped_reference(ref, tmp_path, expected_probs, demo_inputs):
+    """tests/ref_scripts.py drives scripts/00_demo_inference.py (unmodified, staged) end to end.  Here WITHOUT the import swap
+    and on the CPU: the script's printed probabilities are the shipped known-answer row and the CAM it hands to its plot is
+    the oracle's script-order Grad-CAM bit for bit -- so the GPU test that runs the same harness WITH the swap
+    (tests/test_gpu_reference_scripts.py) measures the product, not the harness."""
+    if torch.cuda.is_available():
+        pytest.skip("the script picks cuda when it is there; the CPU leg of the harness check runs in the CPU suite")
+    from conftest import load_ckpt
+    import ref_scripts
+    x, _ = demo_inputs
+    sd = load_ckpt("ecg_baseline_best.pth")
+    for row, c in ((3, 0), (0, 4)):
+        got = ref_scripts.run_demo_inference(tmp_path, row, c, swap=False)
+        assert got["device"] == "cpu" and got["model_module"] == "src.models.ecg_cnn"
+        want = torch.tensor(expected_probs["baseline_prob"][row])
+        assert float((torch.from_numpy(got["probs"]) - want).abs().max()) <= 5.1e-4        # printed with 3 decimals
+        assert torch.equal(got["cam"], O.gradcam_v2(sd, x[row:row + 1], c, x.shape[-1]))
