@@ -175,6 +175,16 @@ def test_committed_bench_lines_follow_the_driver_contract():
         r = json.loads(fh.read().strip().splitlines()[-1])
     assert r["impl"] == "reference" and r["e2e"]["h2d_bytes_per_step"] == 0 and r["cpu_baseline"]["kind"] == "port"
     assert set(r["config"]) <= set(head["config"])          # the two arms name the workload with the same keys
+    # the last lines of the round: the reference arm runs the UNMODIFIED reference staged in oracle/_ref, and both arms of the
+    # same command line print one and the same `config` object (run details moved under `method`)
+    with open(os.path.join(ROOT, "profiles", "r02_bench_n1_final.json")) as fh:
+        head = json.loads(fh.read().strip().splitlines()[-1])
+    with open(os.path.join(ROOT, "profiles", "r02_bench_reference_arm_final.json")) as fh:
+        r = json.loads(fh.read().strip().splitlines()[-1])
+    assert r["impl"] == "reference" and r["cpu_baseline"]["kind"] == "reference" == head["cpu_baseline"]["kind"]
+    assert r["config"] == head["config"] and r["metric"] == head["metric"] and r["unit"] == head["unit"]
+    assert "l2" in head["config"] and {"repeats", "timing", "e2e_input"} <= set(head["method"])
+    assert head["gpu_launches"] > 0 and head["e2e"]["h2d_bytes_per_step"] > 0 and len(head["layers"]) >= 20
 
 
 def test_pair_kernel_selection_rules_on_the_host():
