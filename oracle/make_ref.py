@@ -15,6 +15,7 @@ Files staged:
     src/interpretability/grad_cam_1d.py                           -- GradCAM1D
     scripts/00_demo_inference.py (+ src/utils/seed.py)            -- the one reference script that runs on the shipped demo
                                                                      data: driven end to end with the model import swapped
+    scripts/12_grad_cam_ecg_demo.py, scripts/13_grad_cam_af.py    -- their script-local Grad-CAM classes / compute_demo_importance
 
     python oracle/make_ref.py [--reference /root/reference]
 
@@ -44,6 +45,9 @@ FILES = (
     # one runnable caller of the path, for the end-to-end import-swap test (tests/test_gpu_reference_scripts.py):
     "src/utils/seed.py",
     "scripts/00_demo_inference.py",
+    # the script-local Grad-CAM classes V2 / V3 and compute_demo_importance, run as written on the product models:
+    "scripts/12_grad_cam_ecg_demo.py",
+    "scripts/13_grad_cam_af.py",
 )
 
 

@@ -88,3 +88,48 @@ def run_demo_inference(tmp_path, row: int, class_idx: int, swap: bool):
     dev = re.search(r"\[INFO\] Device: (\S+)", text).group(1)
     return {"probs": np.array(probs, dtype=np.float32), "cam": seen["cam"], "device": dev,
             "model_module": seen["model_module"], "stdout": text}
+
+
+def load_script(name: str):
+    """Import a staged reference script as a module WITHOUT running its main(): scripts/12_grad_cam_ecg_demo.py and
+    13_grad_cam_af.py define their Grad-CAM classes (and compute_demo_importance) at module level.  What they import but
+    this image lacks (matplotlib, and the Dataset classes whose modules need wfdb) is stubbed with empty modules: none of it
+    is touched by the classes under test."""
+    R = make_ref.load()
+    assert R is not None, "oracle/_ref not staged"
+    stubs = {"matplotlib": {}, "matplotlib.pyplot": {}, "seaborn": {},
+             "src.datasets": {"__path__": []},
+             "src.datasets.ptbxl_ecg_multimodal": {"PTBXLECGMultimodalDataset": object},
+             "src.datasets.ptbxl_af": {"PTBXLAFDataset": object}}
+    added = []
+    for mod, attrs in stubs.items():
+        if mod in sys.modules:
+            continue
+        try:
+            if not mod.startswith("src."):
+                importlib.import_module(mod)
+                continue
+        except ImportError:
+            pass
+        m = types.ModuleType(mod)
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[mod] = m
+        added.append(mod)
+    if not hasattr(sys.modules["matplotlib"], "pyplot"):
+        sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    arch = os.environ.get("TORCH_CUDA_ARCH_LIST")               # scripts/13:15 sets it at import; keep the test process as it was
+    try:
+        spec = importlib.util.spec_from_file_location("_ref_script_" + re.sub(r"\W", "_", name),
+                                                      os.path.join(R.root, "scripts", name))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for m in added:
+            if m.startswith("src."):
+                sys.modules.pop(m, None)
+        if arch is None:
+            os.environ.pop("TORCH_CUDA_ARCH_LIST", None)
+        else:
+            os.environ["TORCH_CUDA_ARCH_LIST"] = arch
+    return mod

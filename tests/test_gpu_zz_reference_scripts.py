@@ -120,3 +120,43 @@ def test_reference_gradcam_class_on_the_product_model(ref, demo_inputs):
             assert got.shape == want.shape
             assert float((got - want).abs().max()) < 1e-3, (row, c)
             assert _peak_ok(got, want), (row, c)
+
+
+def test_script_local_gradcam_classes_on_the_product_models(ref, demo_inputs):
+    """scripts/12_grad_cam_ecg_demo.py:17-97 (GradCAM1D_ECGMultimodal: full backward hook on
+    model.ecg_backbone.backbone[-1].net[0], two-input forward; compute_demo_importance: gradient w.r.t. x_demo) and
+    scripts/13_grad_cam_af.py:22-76 (GradCAM1D_AF), imported as written, on P.ECGMultimodal / P.ECGCNN with the shipped
+    checkpoints."""
+    import numpy as np
+    import ref_scripts
+    x, d = demo_inputs
+    T = x.shape[-1]
+    m12 = ref_scripts.load_script("12_grad_cam_ecg_demo.py")
+    m13 = ref_scripts.load_script("13_grad_cam_af.py")
+
+    sd = load_ckpt("ecg_multimodal_best.pth")
+    mm = P.ECGMultimodal()
+    mm.load_state_dict(sd)
+    mm = mm.to(DEV).eval()
+    g = m12.GradCAM1D_ECGMultimodal(mm, mm.ecg_backbone.backbone[-1].net[0])
+    for j, c in ((0, 0), (2, 3), (5, 1)):
+        xe, xd = x[3 + j:4 + j], d[j:j + 1]
+        got = g.generate_cam(xe.to(DEV), xd.to(DEV), c, T)
+        want = O.gradcam_v2(sd, xe, c, T, demo=xd, eps=1e-8)
+        assert got.shape == want.shape and float((got - want).abs().max()) < 1e-3, (j, c)
+        assert _peak_ok(got, want), (j, c)
+        imp = m12.compute_demo_importance(mm, xe.to(DEV), xd.to(DEV), c)
+        np.testing.assert_allclose(imp, O.demo_importance(sd, xe, xd, c).numpy(), atol=TOL)
+    g.remove_hooks()
+
+    sa = load_ckpt("af_binary_best.pth")
+    af = P.ECGCNN(12, 256, 1)
+    af.load_state_dict(sa)
+    af = af.to(DEV).eval()
+    g = m13.GradCAM1D_AF(af, af.backbone[-1].net[0])
+    for row in (6, 8):
+        got = g.generate_cam(x[row:row + 1].to(DEV), T)
+        want = O.gradcam_v2(sa, x[row:row + 1], 0, T)
+        assert got.shape == want.shape and float((got - want).abs().max()) < 1e-3, row
+        assert _peak_ok(got, want), row
+    g.remove_hooks()

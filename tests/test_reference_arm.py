@@ -161,3 +161,40 @@ def test_demo_script_harness_on_the_unswapped_reference(ref, tmp_path, expected_
         want = torch.tensor(expected_probs["baseline_prob"][row])
         assert float((torch.from_numpy(got["probs"]) - want).abs().max()) <= 5.1e-4        # printed with 3 decimals
         assert torch.equal(got["cam"], O.gradcam_v2(sd, x[row:row + 1], c, x.shape[-1]))
+
+
+def test_script_local_gradcam_classes_equal_the_port_on_the_reference_models(ref, demo_inputs):
+    """scripts/12_grad_cam_ecg_demo.py (GradCAM1D_ECGMultimodal, compute_demo_importance) and scripts/13_grad_cam_af.py
+    (GradCAM1D_AF), imported as written from oracle/_ref, on the REFERENCE models with the shipped checkpoints (CPU): bit-equal
+    to the oracle's V2 / V3 restatements.  The GPU twin (tests/test_gpu_zz_reference_scripts.py) hands the same classes the
+    product models."""
+    from conftest import load_ckpt
+    import numpy as np
+    import ref_scripts
+    torch.set_num_threads(4)
+    x, d = demo_inputs
+    T = x.shape[-1]
+    m12 = ref_scripts.load_script("12_grad_cam_ecg_demo.py")
+    m13 = ref_scripts.load_script("13_grad_cam_af.py")
+    assert "src.datasets" not in sys.modules and os.environ.get("TORCH_CUDA_ARCH_LIST") != "native"
+
+    sd = load_ckpt("ecg_multimodal_best.pth")
+    mm = ref.ecg_multimodal.ECGMultimodal()
+    mm.load_state_dict(sd)
+    mm.eval()
+    g = m12.GradCAM1D_ECGMultimodal(mm, mm.ecg_backbone.backbone[-1].net[0])
+    for j, c in ((0, 0), (2, 3)):
+        xe, xd = x[3 + j:4 + j], d[j:j + 1]
+        assert torch.equal(g.generate_cam(xe, xd, c, T), O.gradcam_v2(sd, xe, c, T, demo=xd, eps=1e-8)), (j, c)
+        imp = m12.compute_demo_importance(mm, xe, xd, c)
+        assert np.array_equal(imp, O.demo_importance(sd, xe, xd, c).numpy()), (j, c)
+    g.remove_hooks()
+
+    sa = load_ckpt("af_binary_best.pth")
+    af = ref.ecg_cnn.ECGCNN(12, 256, 1)
+    af.load_state_dict(sa)
+    af.eval()
+    g = m13.GradCAM1D_AF(af, af.backbone[-1].net[0])
+    for row in (6, 8):
+        assert torch.equal(g.generate_cam(x[row:row + 1], T), O.gradcam_v2(sa, x[row:row + 1], 0, T)), row
+    g.remove_hooks()
