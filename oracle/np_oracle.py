@@ -8,8 +8,11 @@ ecg_oracle.py calls the same ATen ops the reference calls; this file restates th
   AdaptiveAvgPool1d(1) + squeeze             mean over time                                                           ecg_cnn.py:61-62
   proj, head (Linear)                        x @ W.T + b                                                              ecg_cnn.py:63-64
   DemoEncoder, film_gen, FiLM                relu(Linear) x2; gamma, beta = chunk(film, 2); (1 + tanh(gamma)) * z + beta   ecg_multimodal.py:44-59,88-99
-Pinned in tests/test_oracle_golden.py against the golden logits produced by the unmodified reference and against the
-shipped prediction CSV rows."""
+  Grad-CAM (V1 / V2 / V3 orderings)          closed-form gradient through eval BN / ReLU / MaxPool (first-index ties) / GAP,
+                                             no autograd; F.interpolate(linear, align_corners=False) restated      grad_cam_1d.py:75-101, scripts/00, 12, 13
+  one ECGCNN training step                   train-mode BN, BCE, the backward pass, AdamW                            loop.py:22-36
+Pinned in tests/test_oracle_golden.py against the golden logits / gradients / CAM curves produced by the unmodified
+reference, the shipped prediction CSV rows and the shipped CAM file (argmax 620)."""
 import numpy as np
 
 EPS = 1e-5
@@ -64,6 +67,68 @@ def multimodal_logits(sd, x, d):
 
 def sigmoid(x):
     return 1.0 / (1.0 + np.exp(-x))
+
+
+# ------------------------------------------------------------------ Grad-CAM without autograd (closed form)
+# In eval mode the gradient of logit c w.r.t. the raw 4th-conv output A (256 x L') is
+#     G_c[ch, t] = v_c[ch] * s[ch] * mask[ch, t] / L_p,      s = gamma_bn / sqrt(running_var + eps),
+#     mask[ch, t] = [t < 2 L_p] and [BN(A)[ch, t] > 0] and [t is the FIRST argmax of its pool pair]   (MaxPool1d ties -> first),
+#     v_c = W_head[c] @ W_proj   (FiLM: (W_head[c] * (1 + tanh gamma_film(d))) @ W_proj),
+# so the channel weights of grad_cam_1d.py:85 are mean_t G_c and the CAM needs no backward pass.
+def conv4_raw_and_mask(sd, prefix, x):
+    """Raw 4th-conv output A (B,256,L') and the routing mask of the BN -> ReLU -> MaxPool(2) -> mean that follows it."""
+    h = x.astype(np.float64)
+    for i in range(3):
+        h = conv_block(sd, f"{prefix}backbone.{i}.", h)
+    p4 = f"{prefix}backbone.3."
+    a = conv1d_k15(h, sd[p4 + "net.0.weight"], sd[p4 + "net.0.bias"])
+    g, be = sd[p4 + "net.1.weight"].astype(np.float64), sd[p4 + "net.1.bias"].astype(np.float64)
+    m, v = sd[p4 + "net.1.running_mean"].astype(np.float64), sd[p4 + "net.1.running_var"].astype(np.float64)
+    s = g / np.sqrt(v + EPS)
+    r = (a - m[None, :, None]) * s[None, :, None] + be[None, :, None]
+    lp = a.shape[2] // 2
+    even, odd = r[:, :, 0:2 * lp:2], r[:, :, 1:2 * lp:2]
+    mask = np.zeros_like(a)
+    mask[:, :, 0:2 * lp:2] = (even >= odd) & (even > 0)            # ties -> first index; ReLU backward mask is out > 0
+    mask[:, :, 1:2 * lp:2] = (odd > even) & (odd > 0)
+    return a, mask, s, lp
+
+
+def linear_upsample(cam, out_len):
+    """F.interpolate(mode='linear', align_corners=False) along the last axis (grad_cam_1d.py:96-101)."""
+    L = cam.shape[-1]
+    src = np.maximum((np.arange(out_len) + 0.5) * (L / out_len) - 0.5, 0.0)
+    i0 = np.floor(src).astype(np.int64)
+    i1 = np.minimum(i0 + 1, L - 1)
+    lam = src - i0
+    return (1.0 - lam) * cam[..., i0] + lam * cam[..., i1]
+
+
+def gradcam(sd, x, class_idx, signal_length=None, variant="v1", eps=1e-9, demo=None):
+    """One window x (1,12,T) -> CAM.  variant "v1": GradCAM1D.generate_cam (grad_cam_1d.py:75-101: normalise at L', /max only
+    if max > 0, THEN upsample); "v2": the script classes (scripts/00:39-61, 13:51-76; 12:44-75 with eps 1e-8 and `demo`):
+    upsample THEN (cam - min) / (max + eps)."""
+    prefix = "" if demo is None else "ecg_backbone."
+    a, mask, s, lp = conv4_raw_and_mask(sd, prefix, x)
+    wh = sd["head.weight"].astype(np.float64)[class_idx]
+    if demo is not None:
+        h = np.maximum(linear(demo.astype(np.float64), sd["demo_encoder.mlp.0.weight"], sd["demo_encoder.mlp.0.bias"]), 0.0)
+        h = np.maximum(linear(h, sd["demo_encoder.mlp.2.weight"], sd["demo_encoder.mlp.2.bias"]), 0.0)
+        film = linear(h, sd["film_gen.weight"], sd["film_gen.bias"])[0]
+        wh = wh * (1.0 + np.tanh(film[:wh.shape[0]]))
+    v = wh @ sd[prefix + "proj.weight"].astype(np.float64)                     # (256,)
+    w = v * s * mask[0].sum(axis=1) / (lp * a.shape[2])                       # mean over t of G_c
+    cam = np.maximum((w[:, None] * a[0]).sum(axis=0), 0.0)                    # relu(sum_ch w * A)
+    if variant == "v1":
+        cam = cam - cam.min()
+        if cam.max() > 0:
+            cam = cam / cam.max()
+        if signal_length is not None and cam.shape[-1] != signal_length:
+            cam = linear_upsample(cam, signal_length)
+        return cam
+    cam = linear_upsample(cam, signal_length)
+    cam = cam - cam.min()
+    return cam / (cam.max() + eps)
 
 
 # ------------------------------------------------------------------ one training step of ECGCNN in numpy (float64)

@@ -146,6 +146,39 @@ def test_numpy_restatement_matches_the_live_reference_and_shipped_rows(golden, d
         assert np.abs(N.sigmoid(logits) - exp).max() < 5e-4, ckpt
 
 
+def test_numpy_closed_form_gradcam_matches_the_shipped_cam_and_the_live_reference(golden, demo_inputs):
+    """oracle/np_oracle.gradcam: Grad-CAM WITHOUT autograd (closed-form gradient through eval BatchNorm / ReLU / MaxPool / GAP,
+    numpy float64) against (1) the CAM file the reference ships (argmax 620), (2) the golden V1 / V2 / V3 curves the unmodified
+    reference produced through hooks + backward(): the three orderings of normalise / upsample and the FiLM-scaled head."""
+    import os
+    from conftest import GOLDEN
+    from oracle import np_oracle as N
+    x, d = demo_inputs
+    xs, ds = x.numpy(), d.numpy()
+    base = {k: v.numpy() for k, v in load_ckpt("ecg_baseline_best.pth").items()}
+    shipped = np.load(os.path.join(GOLDEN, "sample_0_MI_cam.npy"))
+    cam = N.gradcam(base, xs[0:1], 0, 5000, variant="v1")
+    assert cam.argmax() == shipped.argmax() == 620 and np.abs(cam - shipped).max() < 6e-4
+    for c in range(5):
+        for key, got in ((f"cam/v1_base_s0_c{c}_T", N.gradcam(base, xs[0:1], c, 5000, variant="v1")),
+                         (f"cam/v1_base_s0_c{c}_lo", N.gradcam(base, xs[0:1], c, None, variant="v1")),
+                         (f"cam/v2_base_s4_c{c}", N.gradcam(base, xs[4:5], c, 5000, variant="v2", eps=1e-9))):
+            ref = golden[key]
+            assert got.shape == ref.shape and np.abs(got - ref).max() < 2e-4, key
+            if ref.max() - np.partition(ref, -2)[-2] > 1e-3:                    # a clear maximum: same peak index
+                assert got.argmax() == ref.argmax(), key
+    af = {k: v.numpy() for k, v in load_ckpt("af_binary_best.pth").items()}
+    for srow in (0, 7):
+        ref = golden[f"cam/v2_af_s{srow}"]
+        assert np.abs(N.gradcam(af, xs[srow:srow + 1], 0, 5000, variant="v2", eps=1e-9) - ref).max() < 2e-4, srow
+    mm = {k: v.numpy() for k, v in load_ckpt("ecg_multimodal_best.pth").items()}
+    for j in (0, 5):
+        for c in (0, 3):
+            ref = golden[f"cam/v3_mm_j{j}_c{c}"]
+            got = N.gradcam(mm, xs[3 + j:4 + j], c, 5000, variant="v2", eps=1e-8, demo=ds[j:j + 1])
+            assert np.abs(got - ref).max() < 2e-4, (j, c)
+
+
 def test_numpy_train_step_matches_the_live_reference(golden):
     """oracle/np_oracle.train_step_cnn (train-mode BatchNorm, BCE, the whole backward pass and AdamW in numpy float64)
     against step 0 of the unmodified reference's golden trajectory: loss, logits, every gradient, and -- through the
