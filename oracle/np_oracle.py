@@ -10,7 +10,7 @@ ecg_oracle.py calls the same ATen ops the reference calls; this file restates th
   DemoEncoder, film_gen, FiLM                relu(Linear) x2; gamma, beta = chunk(film, 2); (1 + tanh(gamma)) * z + beta   ecg_multimodal.py:44-59,88-99
   Grad-CAM (V1 / V2 / V3 orderings)          closed-form gradient through eval BN / ReLU / MaxPool (first-index ties) / GAP,
                                              no autograd; F.interpolate(linear, align_corners=False) restated      grad_cam_1d.py:75-101, scripts/00, 12, 13
-  one ECGCNN training step                   train-mode BN, BCE, the backward pass, AdamW                            loop.py:22-36
+  one training step (ECGCNN, ECGMultimodal)  train-mode BN, BCE, the backward pass (incl. FiLM / demo encoder), AdamW    loop.py:22-36, loop_demo.py:25-41
 Pinned in tests/test_oracle_golden.py against the golden logits / gradients / CAM curves produced by the unmodified
 reference, the shipped prediction CSV rows and the shipped CAM file (argmax 620)."""
 import numpy as np
@@ -149,13 +149,16 @@ def conv1d_k15_backward(x, w, dy):
     return dxp[:, :, pad:pad + L], dw, dy.sum(axis=(0, 2))
 
 
-def train_step_cnn(sd, x, y, lr, wd, step=1, m=None, v=None):
-    """Returns (loss, logits, grads dict, updated parameter dict) for one step from state `sd` (numpy arrays)."""
+def train_step(sd, x, y, lr, wd, step=1, m=None, v=None, demo=None):
+    """Returns (loss, logits, grads dict, updated parameter dict) for one step from state `sd` (numpy arrays).
+    demo=None: ECGCNN (loop.py:22-36).  demo (B,5): ECGMultimodal with FiLM conditioning (loop_demo.py:25-41;
+    ecg_multimodal.py:88-99) -- the demo encoder, film_gen and the FiLM product in the forward and the backward pass."""
     x = x.astype(np.float64); y = y.astype(np.float64)
+    pre = "" if demo is None else "ecg_backbone."
     cache = []
     h = x
     for i in range(4):
-        p = f"backbone.{i}."
+        p = f"{pre}backbone.{i}."
         w, b = sd[p + "net.0.weight"], sd[p + "net.0.bias"]
         a = conv1d_k15(h, w, b)
         mean = a.mean(axis=(0, 2)); var = a.var(axis=(0, 2))                       # biased, as batch_norm normalises
@@ -169,18 +172,38 @@ def train_step_cnn(sd, x, y, lr, wd, step=1, m=None, v=None):
         cache.append((h, w, xhat, rstd, g, r, r0 >= r1, lp))                       # first index wins ties
         h = pooled
     gap = h.mean(axis=2)
-    z = linear(gap, sd["proj.weight"], sd["proj.bias"])
-    logits = linear(z, sd["head.weight"], sd["head.bias"])
+    z = linear(gap, sd[pre + "proj.weight"], sd[pre + "proj.bias"])
+    if demo is not None:
+        d = demo.astype(np.float64)
+        h1 = np.maximum(linear(d, sd["demo_encoder.mlp.0.weight"], sd["demo_encoder.mlp.0.bias"]), 0.0)
+        h2 = np.maximum(linear(h1, sd["demo_encoder.mlp.2.weight"], sd["demo_encoder.mlp.2.bias"]), 0.0)
+        film = linear(h2, sd["film_gen.weight"], sd["film_gen.bias"])
+        f = z.shape[1]
+        tg = np.tanh(film[:, :f])                                                  # gamma = first half of the chunk
+        feat = (1.0 + tg) * z + film[:, f:]
+    else:
+        feat = z
+    logits = linear(feat, sd["head.weight"], sd["head.bias"])
     loss = np.mean(np.maximum(logits, 0) - logits * y + np.log1p(np.exp(-np.abs(logits))))
     grads = {}
     dlog = (sigmoid(logits) - y) / logits.size
-    grads["head.weight"] = dlog.T @ z; grads["head.bias"] = dlog.sum(0)
-    dz = dlog @ sd["head.weight"].astype(np.float64)
-    grads["proj.weight"] = dz.T @ gap; grads["proj.bias"] = dz.sum(0)
-    dgap = dz @ sd["proj.weight"].astype(np.float64)
+    grads["head.weight"] = dlog.T @ feat; grads["head.bias"] = dlog.sum(0)
+    dfeat = dlog @ sd["head.weight"].astype(np.float64)
+    if demo is not None:
+        dz = dfeat * (1.0 + tg)
+        dfilm = np.concatenate([dfeat * z * (1.0 - tg * tg), dfeat], axis=1)
+        grads["film_gen.weight"] = dfilm.T @ h2; grads["film_gen.bias"] = dfilm.sum(0)
+        dh2 = (dfilm @ sd["film_gen.weight"].astype(np.float64)) * (h2 > 0)
+        grads["demo_encoder.mlp.2.weight"] = dh2.T @ h1; grads["demo_encoder.mlp.2.bias"] = dh2.sum(0)
+        dh1 = (dh2 @ sd["demo_encoder.mlp.2.weight"].astype(np.float64)) * (h1 > 0)
+        grads["demo_encoder.mlp.0.weight"] = dh1.T @ d; grads["demo_encoder.mlp.0.bias"] = dh1.sum(0)
+    else:
+        dz = dfeat
+    grads[pre + "proj.weight"] = dz.T @ gap; grads[pre + "proj.bias"] = dz.sum(0)
+    dgap = dz @ sd[pre + "proj.weight"].astype(np.float64)
     dp = np.repeat(dgap[:, :, None], h.shape[2], axis=2) / h.shape[2]
     for i in (3, 2, 1, 0):
-        p = f"backbone.{i}."
+        p = f"{pre}backbone.{i}."
         hin, w, xhat, rstd, g, r, first, lp = cache[i]
         dr = np.zeros_like(r)
         dr[:, :, 0:2 * lp:2] = np.where(first, dp, 0.0)
@@ -200,3 +223,7 @@ def train_step_cnn(sd, x, y, lr, wd, step=1, m=None, v=None):
         vk = (1 - b2) * gk * gk if v is None else b2 * v[k] + (1 - b2) * gk * gk
         new[k] = pk - lr / (1 - b1 ** step) * mk / (np.sqrt(vk) / np.sqrt(1 - b2 ** step) + eps)
     return loss, logits, grads, new
+
+
+def train_step_cnn(sd, x, y, lr, wd, step=1, m=None, v=None):
+    return train_step(sd, x, y, lr, wd, step=step, m=m, v=v)

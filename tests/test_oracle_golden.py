@@ -179,17 +179,20 @@ def test_numpy_closed_form_gradcam_matches_the_shipped_cam_and_the_live_referenc
             assert np.abs(got - ref).max() < 2e-4, (j, c)
 
 
-def test_numpy_train_step_matches_the_live_reference(golden):
-    """oracle/np_oracle.train_step_cnn (train-mode BatchNorm, BCE, the whole backward pass and AdamW in numpy float64)
-    against step 0 of the unmodified reference's golden trajectory: loss, logits, every gradient, and -- through the
-    torch oracle, itself pinned to the same trajectory -- the updated weights."""
+@pytest.mark.parametrize("tag,kind", [("train_cnn", "cnn"), ("train_mm", "mm")])
+def test_numpy_train_step_matches_the_live_reference(golden, tag, kind):
+    """oracle/np_oracle.train_step (train-mode BatchNorm, BCE, the whole backward pass and AdamW in numpy float64; for the
+    multimodal model also the demo encoder, film_gen and the FiLM product) against step 0 of the unmodified reference's
+    golden trajectory: loss, logits, every gradient, and -- through the torch oracle, itself pinned to the same
+    trajectory -- the updated weights."""
     from oracle import np_oracle as N
-    tag = "train_cnn"
     B, T, nl, lr, wd, steps = golden[f"{tag}/cfg"]
-    sd_t = O.init_state_dict("cnn", int(nl), seed=42)
+    sd_t = O.init_state_dict(kind, int(nl), seed=42)
     sd = {k: v.numpy() for k, v in sd_t.items()}
     x, y = golden[f"{tag}/x"], golden[f"{tag}/y"]
-    loss, logits, grads, new = N.train_step_cnn(sd, x, y, float(lr), float(wd))
+    demo = golden[f"{tag}/demo"] if kind == "mm" else None
+    loss, logits, grads, new = N.train_step(sd, x, y, float(lr), float(wd), demo=demo)
+    assert set(grads) == set(O.param_keys(sd_t))
     assert abs(loss - float(golden[f"{tag}/step0/loss"])) < 1e-6
     np.testing.assert_allclose(logits, golden[f"{tag}/step0/logits"], rtol=1e-4, atol=1e-5)
     for k, g in grads.items():
@@ -200,14 +203,17 @@ def test_numpy_train_step_matches_the_live_reference(golden):
             continue
         _check_sig(golden, f"{tag}/step0/grad", k, torch.from_numpy(g))
     st = O.AdamWState(sd_t, float(lr), float(wd))
-    O.train_step(sd_t, torch.from_numpy(x), torch.from_numpy(y), st)
+    O.train_step(sd_t, torch.from_numpy(x), torch.from_numpy(y), st, demo=None if demo is None else torch.from_numpy(demo))
     for k, v in new.items():
         if k.endswith("net.0.bias"):
             continue
         ref = sd_t[k].double().numpy()
         # the first Adam step moves every weight by ~lr * g / (|g| + eps): entries whose gradient sits at the fp32 noise
-        # floor move by a different fraction of lr in float64 -- bound the difference by a tenth of one step
-        assert np.abs(v - ref).max() <= 0.1 * float(lr), k
+        # floor move by a different fraction of lr in float64 -- bound the worst entry by a quarter of one step and
+        # 99.9 % of the entries by a hundredth of it
+        diff = np.abs(v - ref)
+        assert diff.max() <= 0.25 * float(lr), k
+        assert np.quantile(diff, 0.999) <= 0.01 * float(lr), k
 
 
 @pytest.mark.parametrize("kind", ["cnn", "mm"])
