@@ -963,6 +963,7 @@ class TrainStep:
         """Drop the captured graphs and the NVLink peer mappings (call before destroy_process_group())."""
         self.graph = None
         self.graphs = None
+        self._closed = True
         torch.cuda.synchronize(self.dev)
         for name in ("_symm_handles", "peer_p", "peer_g", "peer_f", "peer_bnx", "peer_inbox"):
             if hasattr(self, name):
@@ -971,6 +972,8 @@ class TrainStep:
     def run(self, slot=None):
         """One optimizer step on whatever input slot `slot` (default: the current one) holds.  Returns that slot's loss
         buffer (device scalar, overwritten the next time the same slot is run)."""
+        if getattr(self, "_closed", False):
+            raise EcgB200Error("TrainStep.close() was called: the graphs and peer mappings are gone, build a new engine")
         if slot is not None and int(slot) != self.cur:
             self._select(int(slot))
         group = self.opt.param_groups[0]
