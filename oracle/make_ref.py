@@ -8,6 +8,9 @@ where they lie under /root/reference -- into the git-ignored directory oracle/_r
 GPU box with the snapshot (where /root/reference does not exist) and `bench.py --impl reference` /
 `cpu_baseline` can time the reference's OWN code (`cpu_baseline.kind = "reference"`) instead of the oracle port.
 No reference source enters the repository's history: oracle/_ref/ is listed in .gitignore (not in .gpurunignore).
+(Staging sourceless bytecode instead -- py_compile output only, no .py at all -- was tried and works here, but *.pyc
+files do not travel with the gpurun snapshot: on the GPU box verify() failed and the reference arm fell back to the
+port, profiles/r02_gpu_reference_scripts.log vs the skipped run.  So the unmodified .py files are what is staged.)
 
 Files staged:
     src/models/ecg_cnn.py, src/models/ecg_multimodal.py           -- the models
