@@ -198,3 +198,22 @@ def test_script_local_gradcam_classes_equal_the_port_on_the_reference_models(ref
     for row in (6, 8):
         assert torch.equal(g.generate_cam(x[row:row + 1], T), O.gradcam_v2(sa, x[row:row + 1], 0, T)), row
     g.remove_hooks()
+
+
+def test_bench_reference_arm_under_torchrun_prints_one_line(ref):
+    """The driver launches the reference arm like the b200 arm (torchrun, one process per GPU): rank 0 alone runs the
+    reference and prints the line, the other ranks exit 0 without work."""
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "bench.py"),
+                          "--impl", "reference", "--gpus", "2", "--batch", "8", "--steps", "1", "--warmup", "3"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["config"]["parallelism"] == "dp2"
+    assert d["config"]["batch_per_gpu"] == 8 and d["config"]["global_batch"] == 16 and d["scaling"] == "weak"
